@@ -431,11 +431,11 @@ static void nh_cell_op(const orc_nh *op, int64_t cell, double (*u)[MAXP3], doubl
     if (op->formulation == 0) { /* :701-840 */
       const double *F = op->cached_tensor2 + iq * 9;
       const double detF = det3(F), cs = op->cached_scalar[iq];
-      double bbar[9], tau_bar[9], tau[9], s[9], jc[9], tau_iso[9];
+      double tau_bar[9], tau[9], s[9], jc[9], tau_iso[9];
       for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
         double b = 0.0;
         for (int k = 0; k < 3; ++k) b += (F[i * 3 + k] * cs) * (F[j * 3 + k] * cs);
-        bbar[i * 3 + j] = b; tau_bar[i * 3 + j] = b * (2.0 * m->c_1);
+        tau_bar[i * 3 + j] = b * (2.0 * m->c_1);
         s[i * 3 + j] = 0.5 * (g[i * 3 + j] + g[j * 3 + i]);
       }
       const double tr_tau_bar = tau_bar[0] + tau_bar[4] + tau_bar[8];

@@ -1,0 +1,153 @@
+"""CPU tests that pin the oracle: the reference has no
+operator-level golden vectors, so the restatement is pinned by
+self-consistency — dense numpy twin vs sum-factorised C, all cache levels are
+the same operator (the reference's own goldens say so, tests/solid/*/*.output),
+symmetry, finite differences of the residual (mf_elasticity.h:1801-1834),
+scipy-assembled Laplace."""
+import numpy as np
+import pytest
+
+from common import MAT, c_cells, displacement, make_mesh, np_cells, rel
+from oracle import c_oracle as CO
+from oracle import np_oracle as NO
+
+LEVELS = NO.NeoHookOperator.LEVELS
+
+
+def _np_op(m, level, formulation=1):
+    cd = np_cells(m)
+    op = NO.NeoHookOperator(cd, NO.Material(formulation=formulation, **MAT))
+    op.initialize(displacement(m), level)
+    op.cache()
+    return op
+
+
+def _c_op(m, level, formulation=1):
+    op = CO.NeoHookOperator(c_cells(m), formulation=formulation, **MAT)
+    op.initialize(displacement(m), level)
+    op.cache()
+    return op
+
+
+def test_shape_1d_matches():
+    for p in range(1, 7):
+        S, D, w = NO.shape_1d(p, p + 1)
+        S2, D2, C2, w2, nodes, qp = CO.shape_1d(p, p + 1)
+        assert np.abs(S - S2).max() < 1e-13 and np.abs(D - D2).max() < 2e-12 and np.abs(w - w2).max() < 1e-14
+        assert np.abs(C2 @ S2 - D2).max() < 1e-11  # collocation derivative identity
+        assert abs(w.sum() - 1) < 1e-14 and np.allclose(S.sum(1), 1)
+
+
+@pytest.mark.parametrize("p", [1, 2, 3])
+@pytest.mark.parametrize("level", LEVELS)
+def test_c_vs_numpy_vmult(p, level):
+    m = make_mesh(p)
+    src = np.random.default_rng(p).uniform(-1, 1, 3 * m.n_nodes)
+    a, b = np.zeros_like(src), np.zeros_like(src)
+    _np_op(m, level).vmult(a, src)
+    _c_op(m, level).vmult(b, src)
+    assert rel(b, a) < 1e-13
+
+
+def test_formulation0_c_vs_numpy():
+    m = make_mesh(2)
+    src = np.random.default_rng(0).uniform(-1, 1, 3 * m.n_nodes)
+    a, b = np.zeros_like(src), np.zeros_like(src)
+    _np_op(m, "tensor2", 0).vmult(a, src)
+    _c_op(m, "tensor2", 0).vmult(b, src)
+    assert rel(b, a) < 1e-13
+
+
+def test_cache_levels_are_the_same_operator():
+    m = make_mesh(2)
+    src = np.random.default_rng(1).uniform(-1, 1, 3 * m.n_nodes)
+    outs = []
+    for level in LEVELS:
+        d = np.zeros_like(src)
+        _c_op(m, level).vmult(d, src)
+        outs.append(d)
+    for d in outs[1:]:
+        assert rel(d, outs[0]) < 1e-12
+
+
+def test_symmetry_and_constrained_identity():
+    m = make_mesh(2)
+    op = _c_op(m, "tensor2")
+    rng = np.random.default_rng(2)
+    u, v = rng.uniform(-1, 1, (2, 3 * m.n_nodes))
+    Au, Av = np.zeros_like(u), np.zeros_like(u)
+    op.vmult(Au, u)
+    op.vmult(Av, v)
+    assert abs(v @ Au - u @ Av) < 1e-12 * abs(v @ Au)
+    c = m.constrained_dofs(3)
+    assert np.array_equal(Au[c], u[c])  # mf_nh_operator.h:623-624
+
+
+@pytest.mark.parametrize("formulation", [0, 1])
+def test_tangent_is_derivative_of_residual(formulation):
+    """A(u) d = -dR/du d  (R = -internal - inertia, mf_elasticity.h:1830-1834) with
+    a = alpha_1 * u so that the inertia term linearises to rho*alpha_1*M."""
+    m = make_mesh(2, clamp=())
+    cd = np_cells(m)
+    mat = NO.Material(formulation=formulation, **MAT)
+    u = displacement(m)
+    op = NO.NeoHookOperator(cd, mat)
+    op.initialize(u, "tensor2")
+    op.cache()
+    d = np.random.default_rng(3).uniform(-1, 1, u.shape)
+    Ad = np.zeros_like(u)
+    op.vmult(Ad, d)
+    eps = 1e-6
+    R = lambda w: NO.nh_residual(cd, mat, w, MAT["alpha_1"] * w, np.zeros(3))
+    fd = -(R(u + eps * d) - R(u - eps * d)) / (2 * eps)
+    assert rel(fd, Ad) < 1e-7
+
+
+def test_diagonal_matches_explicit():
+    m = make_mesh(1, ncells=(2, 2, 2))
+    op = _c_op(m, "tensor2")
+    diag = op.compute_diagonal().copy()
+    n = 3 * m.n_nodes
+    for i in range(0, n, 7):
+        e = np.zeros(n)
+        e[i] = 1
+        out = np.zeros(n)
+        op.vmult(out, e)
+        assert abs(out[i] - diag[i]) < 1e-12 * abs(diag[i])
+    npop = _np_op(m, "tensor2")
+    assert rel(npop.compute_diagonal(), diag) < 1e-13
+
+
+def test_laplace_against_assembled_matrix():
+    import scipy.sparse as sp
+
+    p = 2
+    m = make_mesh(p, ncomp=1, clamp=((0, 0), (1, 1)))
+    cd = np_cells(m, 1)
+    dt = 0.1
+    op = NO.LaplaceOperator(cd, dt)
+    # assemble M + dt K densely per cell from the same tables
+    N, dN = cd.N, cd.dN
+    rows, cols, vals = [], [], []
+    for c in range(cd.n_cells):
+        G = np.einsum("qef,fqa->qea", cd.invjac[c], dN)  # physical gradients of basis
+        Ke = np.einsum("q,qa,qb->ab", cd.JxW[c], N, N) + dt * np.einsum("q,qea,qeb->ab", cd.JxW[c], G, G)
+        idx = cd.dof_idx[c]
+        rows.append(np.repeat(idx, len(idx)))
+        cols.append(np.tile(idx, len(idx)))
+        vals.append(Ke.ravel())
+    A = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
+                      shape=(cd.n_dofs, cd.n_dofs)).tocsr().toarray()
+    con = cd.constrained
+    A[con, :] = 0
+    A[:, con] = 0
+    A[con, con] = 1
+    src = np.random.default_rng(4).uniform(-1, 1, cd.n_dofs)
+    d = np.zeros_like(src)
+    op.vmult(d, src)
+    assert rel(d, A @ src) < 1e-13
+    cop = CO.LaplaceOperator(c_cells(m, 1), dt)
+    d2 = np.zeros_like(src)
+    cop.vmult(d2, src)
+    assert rel(d2, d) < 1e-13
+    assert rel(cop.compute_diagonal(), np.diag(A)) < 1e-13
