@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: neo-Hookean tangent `vmult` (FP64, tensor2 caching)
+on a synthetic 3-D box mesh (BASELINE.json configs[2]/[4]: ~5e7 DoF per GPU).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
+  python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port on the host cores
+
+One JSON line on stdout (rank 0).  A "step" is one vmult over the whole mesh.
+`value`  = DoFs/s with vectors and tables resident in HBM (CUDA events),
+`e2e`    = DoFs/s through b200mf_nh_vmult_host: pinned host src -> H2D -> vmult -> D2H -> host dst,
+`roofline.achieved` = algorithmic bytes (tensor2 with symmetric tau) / kernel time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "matrix-free-dealii-precice_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+CELLS_PER_DIR = {1: 254, 2: 127, 3: 85, 4: 64, 5: 51, 6: 42}  # SURVEY.md §8d config 3 (~5e7 DoF)
+MAT = dict(mu=0.5e6, nu=0.4, rho=1000.0, alpha_1=1.0 / (0.25 * 0.01**2), formulation=1)
+METRIC = "nh_tangent_vmult_dofs_per_s"
+
+
+def algorithmic_bytes_per_cell(p, esize=8):
+    """src read + dst write per unique DoF, one uint32 per node, and the q-point
+    table the kernel actually streams: deformed metric (9+1) + c1, c2, symmetric tau/J (6) = 18 values."""
+    n = p + 1
+    return 2 * esize * 3 * p**3 + 4 * n**3 + 18 * esize * n**3
+
+
+def build_problem(p, ncell_dir, dtype="f64"):
+    from b200mf import MatrixFree, NeoHookOperator
+    from b200mf.mesh import StructuredMesh, synthetic_displacement
+
+    m = StructuredMesh((ncell_dir,) * 3, p)
+    m.clamp([(0, 0)], 3)
+    u = synthetic_displacement(m.node_coordinates(), 0.05)
+    mf = MatrixFree.from_mesh(m, 3, dtype=dtype)
+    op = NeoHookOperator()
+    op.set_material(mf, MAT)
+    op.initialize(u, "tensor2")
+    op.cache()
+    return m, mf, op
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_oracle_rate(p, ncell_dir, min_seconds=10.0, max_reps=50):
+    """DoFs/s of the CPU oracle port (oracle/mf_oracle.c, OpenMP over cells, all host threads)."""
+    from b200mf.mesh import StructuredMesh, synthetic_displacement
+    from oracle import c_oracle as CO
+
+    m = StructuredMesh((ncell_dir,) * 3, p)
+    m.clamp([(0, 0)], 3)
+    invjac, jxw = CO.q1_metric(m.vertices, p + 1)
+    cells = CO.Cells(p, p + 1, 3, m.dof_index(3), m.constrained_dofs(3), invjac, jxw)
+    mat = {k: v for k, v in MAT.items() if k != "formulation"}
+    op = CO.NeoHookOperator(cells, formulation=1, **mat)
+    op.initialize(synthetic_displacement(m.node_coordinates(), 0.05), "tensor2")
+    op.cache()
+    n = 3 * m.n_nodes
+    src = np.random.default_rng(0).uniform(-1, 1, n)
+    dst = np.zeros(n)
+    op.vmult(dst, src)  # warm-up
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        op.vmult(dst, src)
+        reps += 1
+        el = time.perf_counter() - t0
+        if el > min_seconds or reps >= max_reps:
+            break
+    return n * reps / el, n, reps, CO.num_threads(), el / reps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    p = args.degree
+    nc = args.cpu_cells
+    times = []
+    from b200mf.mesh import StructuredMesh, synthetic_displacement
+    from oracle import c_oracle as CO
+
+    m = StructuredMesh((nc,) * 3, p)
+    m.clamp([(0, 0)], 3)
+    invjac, jxw = CO.q1_metric(m.vertices, p + 1)
+    cells = CO.Cells(p, p + 1, 3, m.dof_index(3), m.constrained_dofs(3), invjac, jxw)
+    mat = {k: v for k, v in MAT.items() if k != "formulation"}
+    op = CO.NeoHookOperator(cells, formulation=1, **mat)
+    op.initialize(synthetic_displacement(m.node_coordinates(), 0.05), "tensor2")
+    op.cache()
+    n = 3 * m.n_nodes
+    src = np.random.default_rng(0).uniform(-1, 1, n)
+    dst = np.zeros(n)
+    for _ in range(args.warmup):
+        op.vmult(dst, src)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        op.vmult(dst, src)
+    el = time.perf_counter() - t0
+    val = n * args.steps / el
+    sample = f"Q{p} box {nc}^3 cells = {n} DoFs per step (bounded sample of the {CELLS_PER_DIR[p]}^3-cell workload)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "DoFs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(p, CELLS_PER_DIR[p] if args.cells is None else args.cells, args.gpus),
+        "cpu_baseline": {"value": val, "unit": "DoFs/s", "cores": CO.num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "DoFs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference needs deal.II>=9.6 + preCICE>=3 (absent): CPU arm = oracle/mf_oracle.c port, OpenMP over cells",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(p, nc, ngpus):
+    return {"workload": f"neo-Hookean tangent vmult, tensor2 caching, Q{p}, box {nc}^3 cells per GPU",
+            "degree": p, "cells_per_gpu": nc**3, "dofs_per_gpu": 3 * (nc * p + 1) ** 3, "caching": "tensor2",
+            "parallelism": f"dd{ngpus}", "l2": "vectors+tables per step >> 126 MB L2 (no flush needed)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--degree", type=int, default=3)
+    ap.add_argument("--cells", type=int, default=None, help="cells per direction per GPU (default: ~5e7 DoF)")
+    ap.add_argument("--cpu-cells", type=int, default=None, help="cells per direction of the CPU sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="also report Q1..Q6 device-resident rates")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    args = ap.parse_args()
+    p = args.degree
+    if args.cpu_cells is None:
+        args.cpu_cells = {1: 64, 2: 40, 3: 28, 4: 20, 5: 16, 6: 14}[p]
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import b200mf
+    from b200mf import DeviceVector
+
+    L = b200mf.load()
+    nc = CELLS_PER_DIR[p] if args.cells is None else args.cells
+    es = 8 if args.dtype == "f64" else 4
+    m, mf, op = build_problem(p, nc, args.dtype)
+    n = 3 * m.n_nodes
+    src_h = np.random.default_rng(rank).uniform(-1, 1, n)
+    src_h[m.constrained_dofs(3)] = 0.0
+    src, dst = DeviceVector(mf, src_h), DeviceVector(mf)
+    stream = torch.cuda.current_stream()
+    mf.set_stream(stream.cuda_stream)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        op.vmult(dst, src)
+    barrier()
+    launches0 = L.b200mf_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    with ClockSampler(local_rank) as clocks:
+        ev[0].record(stream)
+        for i in range(args.steps):
+            op.vmult(dst, src)
+            ev[i + 1].record(stream)
+        barrier()
+    launches = L.b200mf_launch_count() - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    if dist is not None:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms = total_ms / args.steps
+    dofs_total = n * world  # weak scaling: every rank owns a brick of the same size
+    value = dofs_total / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (the cell loop; memset + constrained fix-up are the rest of the step)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg_bytes = algorithmic_bytes_per_cell(p, es) * m.n_cells
+    achieved = alg_bytes / (ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
+                "algorithmic_bytes_per_dof": algorithmic_bytes_per_cell(p, es) / (3 * p**3),
+                "timed": "whole vmult step (memset + cell loop + constrained fix-up), CUDA events"}
+
+    # ---- e2e: host buffers through the C-ABI host entry point ----------------------------------
+    e2e = None
+    if not args.no_e2e and args.dtype == "f64":
+        hs = torch.from_numpy(src_h).pin_memory()
+        hd = torch.empty(n, dtype=torch.float64).pin_memory()
+        import ctypes as C
+
+        for _ in range(2):
+            b200mf.lib.check(L.b200mf_nh_vmult_host(op.h, C.c_void_p(hd.data_ptr()), C.c_void_p(hs.data_ptr())))
+        barrier()
+        k = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(k):
+            b200mf.lib.check(L.b200mf_nh_vmult_host(op.h, C.c_void_p(hd.data_ptr()), C.c_void_p(hs.data_ptr())))
+        barrier()
+        el = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([el], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            el = float(t.item())
+        e2e = {"value": dofs_total * k / el, "unit": "DoFs/s", "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 8,
+               "steps": k, "ms_per_step": 1e3 * el / k}
+
+    sweep = None
+    if args.sweep and rank == 0:
+        sweep = {}
+        del src, dst, op, mf
+        for q in range(1, 7):
+            mq, mfq, opq = build_problem(q, CELLS_PER_DIR[q], args.dtype)
+            nq = 3 * mq.n_nodes
+            s, d = DeviceVector(mfq, np.random.default_rng(q).uniform(-1, 1, nq)), DeviceVector(mfq)
+            for _ in range(3):
+                opq.vmult(d, s)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                opq.vmult(d, s)
+            e1.record()
+            torch.cuda.synchronize()
+            msq = e0.elapsed_time(e1) / 10
+            gb = algorithmic_bytes_per_cell(q, es) * mq.n_cells / (msq * 1e-3) / 1e9
+            sweep[f"Q{q}"] = {"dofs": nq, "ms": msq, "dofs_per_s": nq / (msq * 1e-3), "GB/s": gb, "frac": gb / peak}
+            del s, d, opq, mfq
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, ncpu, reps, threads, sec = cpu_oracle_rate(p, args.cpu_cells)
+        cpu = {"value": v, "unit": "DoFs/s", "cores": threads, "kind": "port",
+               "sample": f"Q{p} box {args.cpu_cells}^3 cells = {ncpu} DoFs x {reps} vmults ({sec:.2f} s each), oracle/mf_oracle.c"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "DoFs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+            "data": "synthetic", "config": workload_config(p, nc, world), "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(),
+        }
+        if sweep:
+            line["sweep"] = sweep
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

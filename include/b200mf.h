@@ -1,0 +1,179 @@
+/* b200mf — B200-native (sm_100a) matrix-free operator application.
+ *
+ * C ABI of the drop-in boundary.  Every entry point names the
+ * reference interface it replaces; paths are relative to the reference tree
+ * (davidscn/matrix-free-dealii-precice).  The reference-side binding (a C++
+ * shim class with the duck-typed deal.II operator surface) is shown in
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++/torch types cross this boundary;
+ *  - every function returns 0 on success, a negative b200mf_status otherwise;
+ *    b200mf_last_error() returns a thread-local message (the shim turns a
+ *    non-zero status into deal.II's AssertThrow, src/solid.cc:64-89);
+ *  - "dvec" arguments are DEVICE pointers to vectors in the library's internal
+ *    numbering (see b200mf_vec_*); "host" arguments are caller-owned host arrays
+ *    in the caller's (deal.II) numbering, local size n_dofs = owned + ghosts;
+ *  - one caller thread per context (the reference runs one thread per rank,
+ *    src/solid.cc:30-31); all work of a context is ordered on its stream.
+ */
+#ifndef B200MF_H
+#define B200MF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  B200MF_OK = 0,
+  B200MF_ERR_ARG = -1,     /* invalid argument / unsupported configuration */
+  B200MF_ERR_CUDA = -2,    /* CUDA runtime error */
+  B200MF_ERR_STATE = -3,   /* call order violated (e.g. vmult before cache) */
+  B200MF_ERR_NUMERIC = -4, /* det F <= 0, non-positive diagonal */
+  B200MF_ERR_NCCL = -5
+} b200mf_status;
+
+typedef enum { B200MF_F64 = 0, B200MF_F32 = 1 } b200mf_dtype;
+
+/* MF caching levels, include/solid_mechanics/mf_nh_operator.h:215-223 and the
+ * "MF caching" .prm key (include/parameter/parameter_handling.h:177-254). */
+typedef enum {
+  B200MF_CACHE_SCALAR_REFERENTIAL = 0,
+  B200MF_CACHE_TENSOR2 = 1,
+  B200MF_CACHE_TENSOR4 = 2,
+  B200MF_CACHE_TENSOR4_NS = 3
+} b200mf_caching;
+
+typedef struct b200mf_ctx b200mf_ctx;         /* replaces MatrixFree<3,Number> (+DoFInfo, MappingInfo) */
+typedef struct b200mf_nh b200mf_nh;           /* replaces NeoHookOperator<3,Number>, mf_nh_operator.h:99-237 */
+typedef struct b200mf_laplace b200mf_laplace; /* replaces LaplaceOperator<3,number>, heat_transfer.h:81-127 */
+
+const char *b200mf_last_error(void);
+/* number of CUDA kernels this library has launched in this process (bench.py "gpu_launches") */
+int64_t b200mf_launch_count(void);
+int b200mf_version(void);
+
+/* ------------------------------------------------------------------------
+ * Cell-batch data ("MatrixFree").  Replaces MatrixFree::reinit as called by
+ * Solid::reinit_matrix_free / reinit_multi_grid_matrix_free
+ * (include/solid_mechanics/mf_elasticity.h:933-1055) and
+ * LaplaceProblem::setup_system (include/heat_transfer/heat_transfer.h:430-509).
+ * All host arrays are copied; they may be freed after the call.
+ * ------------------------------------------------------------------------ */
+typedef struct {
+  int degree;        /* FE_Q degree p, 1..6 (README.md:60; include/base/fe_integrator.h:10-22) */
+  int n_q_points_1d; /* must be degree+1 (every shipped .prm uses Quadrature order = p+1) */
+  int n_components;  /* 3 = FESystem(FE_Q(p),3) solid; 1 = scalar heat */
+  int dtype;         /* b200mf_dtype: FP64 system operator or FP32 level operator (mf_elasticity.h:363-367) */
+  int64_t n_cells;
+  int64_t n_dofs;  /* local vector size: owned + ghost entries (LA::distributed::Vector) */
+  int64_t n_owned; /* owned entries come first; == n_dofs on one rank */
+
+  /* Exactly one of dof_indices / node_indices.
+   * dof_indices: [n_cells][n_components*(p+1)^3] local DoF indices in FEEvaluation order
+   *   (component-major, lexicographic within a component, x fastest) — what
+   *   FEEvaluation::read_dof_values walks (mf_nh_operator.h:640-646).
+   * node_indices: [n_cells][(p+1)^3] scalar node indices; DoF = n_components*node + c. */
+  const uint32_t *dof_indices;
+  const uint32_t *node_indices;
+
+  /* MatrixFree::get_constrained_dofs(): local indices (mf_nh_operator.h:623-624, 1043-1044) */
+  const uint32_t *constrained_dofs;
+  int64_t n_constrained;
+
+  /* Reference-configuration mapping (StaticMappingQ1, mf_elasticity.h:739-746).
+   * Either the 8 vertices per cell (lexicographic, x fastest): [n_cells][8][3] — the
+   * library evaluates the Q1 metric on the device — or explicit MappingInfo arrays
+   * inverse_jacobian [n_cells][nq^3][3][3] with [e][f] = d xi_f / d x_e
+   * (mf_nh_operator.h:872-887) and jxw [n_cells][nq^3]. */
+  const double *vertices;
+  const double *inverse_jacobian;
+  const double *jxw;
+
+  const uint8_t *material_id; /* [n_cells] or NULL (all 0); mf_nh_operator.h:402-404, 656-658 */
+} b200mf_ctx_desc;
+
+int b200mf_ctx_create(b200mf_ctx **ctx, const b200mf_ctx_desc *desc);
+int b200mf_ctx_destroy(b200mf_ctx *ctx);
+/* all work of this context (and of operators built on it) is enqueued on `cuda_stream` (cudaStream_t; NULL = default) */
+int b200mf_ctx_set_stream(b200mf_ctx *ctx, void *cuda_stream);
+int b200mf_ctx_synchronize(b200mf_ctx *ctx);
+int64_t b200mf_ctx_n_dofs(const b200mf_ctx *ctx);
+size_t b200mf_ctx_memory_consumption(const b200mf_ctx *ctx); /* MatrixFree::memory_consumption, mf_elasticity.h:982-990 */
+
+/* ------------------------------------------------------------------------
+ * Device vectors (LinearAlgebra::distributed::Vector<Number> local part).
+ * MatrixFree::initialize_dof_vector (mf_elasticity.h:693-706).  Element type is
+ * the context's dtype; numbering is the library's internal one (nodes
+ * interleaved n_components*node+c), upload/download translate.
+ * ------------------------------------------------------------------------ */
+int b200mf_vec_create(b200mf_ctx *ctx, void **dvec); /* zero-initialised */
+int b200mf_vec_destroy(b200mf_ctx *ctx, void *dvec);
+int b200mf_vec_upload(b200mf_ctx *ctx, void *dvec, const void *host);         /* host dtype = ctx dtype */
+int b200mf_vec_download(b200mf_ctx *ctx, void *host, const void *dvec);
+int b200mf_vec_upload_f64(b200mf_ctx *ctx, void *dvec, const double *host);   /* converts when ctx is FP32 */
+int b200mf_vec_download_f64(b200mf_ctx *ctx, double *host, const void *dvec);
+
+/* ------------------------------------------------------------------------
+ * NeoHookOperator (include/solid_mechanics/mf_nh_operator.h)
+ * ------------------------------------------------------------------------ */
+typedef struct { /* Material_Compressible_Neo_Hook_One_Field ctor, include/solid_mechanics/material.h:78-94 */
+  double mu, nu, rho, alpha_1;
+  int formulation; /* 0: vol/iso split, 1: coupled (material.h:116-161) */
+} b200mf_material;
+
+/* NeoHookOperator() + set_material (mf_nh_operator.h:527-539): material for material_id==0, inclusion otherwise */
+int b200mf_nh_create(b200mf_nh **op, b200mf_ctx *ctx, const b200mf_material *material,
+                     const b200mf_material *material_inclusion);
+int b200mf_nh_destroy(b200mf_nh *op); /* clear(), mf_nh_operator.h:313-327 */
+/* initialize(data_current, data_reference, displacement, caching), mf_nh_operator.h:331-388.  The
+ * deformed-frame MatrixFree is not needed: the library derives J_cur = F J_ref (MappingQEulerian). */
+int b200mf_nh_initialize(b200mf_nh *op, int caching);
+/* cache(), mf_nh_operator.h:392-523.  *n_nonpositive_detF receives the number of quadrature points
+ * violating the reference's debug assertion det F > 0 (:430-435); returns B200MF_ERR_NUMERIC if > 0. */
+int b200mf_nh_cache(b200mf_nh *op, const void *displacement_dvec, int64_t *n_nonpositive_detF);
+int b200mf_nh_cache_host(b200mf_nh *op, const double *displacement_host, int64_t *n_nonpositive_detF);
+/* vmult / Tvmult / vmult_add / Tvmult_add, mf_nh_operator.h:543-625 (operator is symmetric) */
+int b200mf_nh_vmult(b200mf_nh *op, void *dst_dvec, const void *src_dvec);
+int b200mf_nh_vmult_add(b200mf_nh *op, void *dst_dvec, const void *src_dvec);
+int b200mf_nh_Tvmult(b200mf_nh *op, void *dst_dvec, const void *src_dvec);
+int b200mf_nh_Tvmult_add(b200mf_nh *op, void *dst_dvec, const void *src_dvec);
+/* parity / drop-in mode: caller-owned host vectors, H2D + vmult + D2H */
+int b200mf_nh_vmult_host(b200mf_nh *op, double *dst_host, const double *src_host);
+/* compute_diagonal(), mf_nh_operator.h:1023-1060: fills diagonal and inverse (constrained -> 1) */
+int b200mf_nh_compute_diagonal(b200mf_nh *op);
+int b200mf_nh_diagonal(b200mf_nh *op, const void **diag_dvec, const void **inv_diag_dvec); /* get_matrix_diagonal_inverse :157-161 */
+int b200mf_nh_diagonal_host(b200mf_nh *op, double *diag_host, double *inv_diag_host);
+/* precondition_Jacobi(dst, src, omega), mf_nh_operator.h:281-291 */
+int b200mf_nh_precondition_jacobi(b200mf_nh *op, void *dst_dvec, const void *src_dvec, double omega);
+/* el(row,row), mf_nh_operator.h:1064-1073 (row in caller numbering) */
+int b200mf_nh_el(b200mf_nh *op, int64_t row, double *value);
+int64_t b200mf_nh_m(const b200mf_nh *op); /* m() == n(), mf_nh_operator.h:295-309 */
+size_t b200mf_nh_memory_consumption(const b200mf_nh *op); /* mf_nh_operator.h:241-260 */
+/* test hook: copy one cached quadrature table to the host in natural order [n_cells][nq^3].
+ * field ids: see B200MF_QF_* */
+int b200mf_nh_qdata_host(b200mf_nh *op, int field, double *out);
+int b200mf_nh_n_qfields(const b200mf_nh *op);
+
+/* ------------------------------------------------------------------------
+ * LaplaceOperator: (M + dt*c*K) u, include/heat_transfer/heat_transfer.h:81-250
+ * ------------------------------------------------------------------------ */
+/* coefficient: [n_cells][nq^3] table (evaluate_coefficient :150-166) or NULL for c == 1 (:64-71) */
+int b200mf_laplace_create(b200mf_laplace **op, b200mf_ctx *ctx, double delta_t, const double *coefficient);
+int b200mf_laplace_destroy(b200mf_laplace *op);
+int b200mf_laplace_set_delta_t(b200mf_laplace *op, double delta_t); /* set_delta_t :141-146 */
+int b200mf_laplace_vmult(b200mf_laplace *op, void *dst_dvec, const void *src_dvec);     /* Base::vmult -> apply_add :194-201 */
+int b200mf_laplace_vmult_add(b200mf_laplace *op, void *dst_dvec, const void *src_dvec);
+int b200mf_laplace_Tvmult(b200mf_laplace *op, void *dst_dvec, const void *src_dvec);
+int b200mf_laplace_vmult_host(b200mf_laplace *op, double *dst_host, const double *src_host);
+int b200mf_laplace_compute_diagonal(b200mf_laplace *op); /* :205-230 */
+int b200mf_laplace_diagonal(b200mf_laplace *op, const void **diag_dvec, const void **inv_diag_dvec);
+int b200mf_laplace_diagonal_host(b200mf_laplace *op, double *diag_host, double *inv_diag_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MF_H */

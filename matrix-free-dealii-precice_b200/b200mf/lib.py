@@ -1,0 +1,109 @@
+"""ctypes binding of libb200mf.so (include/b200mf.h).  There is no CPU fallback:
+a missing library or a missing CUDA device raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200mf.so")
+
+F64, F32 = 0, 1
+CACHING = {"scalar_referential": 0, "tensor2": 1, "tensor4": 2, "tensor4_ns": 3}
+
+
+class B200mfError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"b200mf status {code}: {msg}")
+        self.code = code
+
+
+class CtxDesc(C.Structure):
+    _fields_ = [
+        ("degree", C.c_int), ("n_q_points_1d", C.c_int), ("n_components", C.c_int), ("dtype", C.c_int),
+        ("n_cells", C.c_int64), ("n_dofs", C.c_int64), ("n_owned", C.c_int64),
+        ("dof_indices", C.c_void_p), ("node_indices", C.c_void_p),
+        ("constrained_dofs", C.c_void_p), ("n_constrained", C.c_int64),
+        ("vertices", C.c_void_p), ("inverse_jacobian", C.c_void_p), ("jxw", C.c_void_p),
+        ("material_id", C.c_void_p),
+    ]
+
+
+class Material(C.Structure):
+    _fields_ = [("mu", C.c_double), ("nu", C.c_double), ("rho", C.c_double), ("alpha_1", C.c_double),
+                ("formulation", C.c_int)]
+
+
+_lib = None
+
+_vp, _i64, _i32, _dbl = C.c_void_p, C.c_int64, C.c_int, C.c_double
+_PP = C.POINTER(C.c_void_p)
+
+# name -> (restype, argtypes); every symbol include/b200mf.h declares
+SIGNATURES = {
+    "b200mf_last_error": (C.c_char_p, []),
+    "b200mf_launch_count": (_i64, []),
+    "b200mf_version": (_i32, []),
+    "b200mf_ctx_create": (_i32, [_PP, C.POINTER(CtxDesc)]),
+    "b200mf_ctx_destroy": (_i32, [_vp]),
+    "b200mf_ctx_set_stream": (_i32, [_vp, _vp]),
+    "b200mf_ctx_synchronize": (_i32, [_vp]),
+    "b200mf_ctx_n_dofs": (_i64, [_vp]),
+    "b200mf_ctx_memory_consumption": (C.c_size_t, [_vp]),
+    "b200mf_vec_create": (_i32, [_vp, _PP]),
+    "b200mf_vec_destroy": (_i32, [_vp, _vp]),
+    "b200mf_vec_upload": (_i32, [_vp, _vp, _vp]),
+    "b200mf_vec_download": (_i32, [_vp, _vp, _vp]),
+    "b200mf_vec_upload_f64": (_i32, [_vp, _vp, _vp]),
+    "b200mf_vec_download_f64": (_i32, [_vp, _vp, _vp]),
+    "b200mf_nh_create": (_i32, [_PP, _vp, C.POINTER(Material), C.POINTER(Material)]),
+    "b200mf_nh_destroy": (_i32, [_vp]),
+    "b200mf_nh_initialize": (_i32, [_vp, _i32]),
+    "b200mf_nh_cache": (_i32, [_vp, _vp, C.POINTER(_i64)]),
+    "b200mf_nh_cache_host": (_i32, [_vp, _vp, C.POINTER(_i64)]),
+    "b200mf_nh_vmult": (_i32, [_vp, _vp, _vp]),
+    "b200mf_nh_vmult_add": (_i32, [_vp, _vp, _vp]),
+    "b200mf_nh_Tvmult": (_i32, [_vp, _vp, _vp]),
+    "b200mf_nh_Tvmult_add": (_i32, [_vp, _vp, _vp]),
+    "b200mf_nh_vmult_host": (_i32, [_vp, _vp, _vp]),
+    "b200mf_nh_compute_diagonal": (_i32, [_vp]),
+    "b200mf_nh_diagonal": (_i32, [_vp, _PP, _PP]),
+    "b200mf_nh_diagonal_host": (_i32, [_vp, _vp, _vp]),
+    "b200mf_nh_precondition_jacobi": (_i32, [_vp, _vp, _vp, _dbl]),
+    "b200mf_nh_el": (_i32, [_vp, _i64, C.POINTER(_dbl)]),
+    "b200mf_nh_m": (_i64, [_vp]),
+    "b200mf_nh_memory_consumption": (C.c_size_t, [_vp]),
+    "b200mf_nh_qdata_host": (_i32, [_vp, _i32, _vp]),
+    "b200mf_nh_n_qfields": (_i32, [_vp]),
+    "b200mf_laplace_create": (_i32, [_PP, _vp, _dbl, _vp]),
+    "b200mf_laplace_destroy": (_i32, [_vp]),
+    "b200mf_laplace_set_delta_t": (_i32, [_vp, _dbl]),
+    "b200mf_laplace_vmult": (_i32, [_vp, _vp, _vp]),
+    "b200mf_laplace_vmult_add": (_i32, [_vp, _vp, _vp]),
+    "b200mf_laplace_Tvmult": (_i32, [_vp, _vp, _vp]),
+    "b200mf_laplace_vmult_host": (_i32, [_vp, _vp, _vp]),
+    "b200mf_laplace_compute_diagonal": (_i32, [_vp]),
+    "b200mf_laplace_diagonal": (_i32, [_vp, _PP, _PP]),
+    "b200mf_laplace_diagonal_host": (_i32, [_vp, _vp, _vp]),
+}
+
+
+def load():
+    """Load libb200mf.so and bind every symbol; raises if the library is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with __graft_entry__.build() "
+                              "(make -C matrix-free-dealii-precice_b200/csrc); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise B200mfError(rc, load().b200mf_last_error().decode())
+    return rc

@@ -111,6 +111,18 @@ class StructuredMesh:
         """Support points: Q1 map of the cell vertices at the GLL points."""
         dim = self.dim
         x1 = _gll(self.p)
+        if self.mapping is None and not self.periodic_x:
+            # axis-aligned box: tensor grid of (cell origin + h * GLL point)
+            g = self.node_grid_index()
+            coords = np.empty((self.n_nodes, dim))
+            for d in range(dim):
+                h = (self.upper[d] - self.lower[d]) / self.ncells[d]
+                cell, loc = np.divmod(g[:, d], self.p)
+                last = cell == self.ncells[d]
+                cell = np.where(last, cell - 1, cell)
+                loc = np.where(last, self.p, loc)
+                coords[:, d] = self.lower[d] + h * (cell + x1[loc])
+            return coords
         lin = np.stack([1.0 - x1, x1], axis=1)
         Nv = lin
         for _ in range(dim - 1):

@@ -1,0 +1,277 @@
+"""Host-side mirror of the reference's operator interface on top of the C ABI.
+
+Names follow the reference so that the parity tests read like its call sites:
+  MatrixFree          <- dealii::MatrixFree<3,Number>            (mf_elasticity.h:933-992)
+  DeviceVector        <- LinearAlgebra::distributed::Vector       (mf_elasticity.h:693-706)
+  NeoHookOperator     <- include/solid_mechanics/mf_nh_operator.h:99-237
+  LaplaceOperator     <- include/heat_transfer/heat_transfer.h:81-127
+All arithmetic runs in libb200mf.so on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import lib as _l
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class MatrixFree:
+    """Cell-batch data resident in HBM (index maps, constraint masks, metric)."""
+
+    def __init__(self, degree, n_components, n_dofs, *, dof_indices=None, node_indices=None, constrained_dofs=None,
+                 vertices=None, inverse_jacobian=None, jxw=None, material_id=None, dtype="f64", n_owned=None,
+                 n_q_points_1d=None):
+        L = _l.load()
+        self.degree, self.n_components, self.n_dofs = int(degree), int(n_components), int(n_dofs)
+        self.dtype = dtype
+        self.np_dtype = np.float64 if dtype == "f64" else np.float32
+        keep = []
+
+        def arr(a, dt):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=dt)
+            keep.append(a)
+            return a
+
+        d = _l.CtxDesc()
+        d.degree = self.degree
+        d.n_q_points_1d = self.degree + 1 if n_q_points_1d is None else int(n_q_points_1d)
+        d.n_components = self.n_components
+        d.dtype = _l.F64 if dtype == "f64" else _l.F32
+        idx = dof_indices if dof_indices is not None else node_indices
+        d.n_cells = int(np.asarray(idx).shape[0])
+        d.n_dofs = self.n_dofs
+        d.n_owned = self.n_dofs if n_owned is None else int(n_owned)
+        d.dof_indices = _ptr(arr(dof_indices, np.uint32))
+        d.node_indices = _ptr(arr(node_indices, np.uint32))
+        con = arr(constrained_dofs, np.uint32)
+        d.constrained_dofs = _ptr(con)
+        d.n_constrained = 0 if con is None else con.size
+        d.vertices = _ptr(arr(vertices, np.float64))
+        d.inverse_jacobian = _ptr(arr(inverse_jacobian, np.float64))
+        d.jxw = _ptr(arr(jxw, np.float64))
+        d.material_id = _ptr(arr(material_id, np.uint8))
+        self.n_cells = d.n_cells
+        h = C.c_void_p()
+        _l.check(L.b200mf_ctx_create(C.byref(h), C.byref(d)))
+        self.h = h
+
+    @classmethod
+    def from_mesh(cls, mesh, n_components, dtype="f64", full_dof_map=False, explicit_metric=None):
+        """Build from a b200mf.mesh.StructuredMesh (synthetic benchmarks / tests)."""
+        con = np.flatnonzero(mesh.constrained_dofs(n_components)).astype(np.uint32)
+        kw = dict(constrained_dofs=con, material_id=mesh.material_id, dtype=dtype)
+        if explicit_metric is not None:
+            kw.update(inverse_jacobian=explicit_metric[0], jxw=explicit_metric[1])
+        else:
+            kw.update(vertices=mesh.vertices)
+        if full_dof_map:
+            kw.update(dof_indices=mesh.dof_index(n_components))
+        else:
+            kw.update(node_indices=mesh.cell_nodes)
+        return cls(mesh.p, n_components, mesh.n_nodes * n_components, **kw)
+
+    def set_stream(self, cuda_stream):
+        _l.check(_l.load().b200mf_ctx_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        _l.check(_l.load().b200mf_ctx_synchronize(self.h))
+
+    def memory_consumption(self):
+        return _l.load().b200mf_ctx_memory_consumption(self.h)
+
+    def initialize_dof_vector(self):
+        return DeviceVector(self)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            _l.load().b200mf_ctx_destroy(self.h)
+            self.h = None
+
+
+class DeviceVector:
+    """Device-resident vector in the library's internal numbering."""
+
+    def __init__(self, mf: MatrixFree, host=None):
+        self.mf = mf
+        p = C.c_void_p()
+        _l.check(_l.load().b200mf_vec_create(mf.h, C.byref(p)))
+        self.ptr = p
+        if host is not None:
+            self.upload(host)
+
+    def upload(self, host):
+        h = np.ascontiguousarray(host, dtype=np.float64)
+        assert h.size == self.mf.n_dofs
+        _l.check(_l.load().b200mf_vec_upload_f64(self.mf.h, self.ptr, _ptr(h)))
+        self.mf.synchronize()
+        return self
+
+    def download(self):
+        out = np.empty(self.mf.n_dofs, dtype=np.float64)
+        _l.check(_l.load().b200mf_vec_download_f64(self.mf.h, _ptr(out), self.ptr))
+        return out
+
+    def __del__(self):
+        if getattr(self, "ptr", None) and getattr(self.mf, "h", None):
+            _l.load().b200mf_vec_destroy(self.mf.h, self.ptr)
+            self.ptr = None
+
+
+def _dv(x):
+    return x.ptr if isinstance(x, DeviceVector) else C.c_void_p(int(x))
+
+
+class NeoHookOperator:
+    """mf_nh_operator.h:99-237.  `initialize(displacement, caching)` keeps a
+    reference to the displacement vector like the original (:339-341)."""
+
+    def __init__(self):
+        self.h = None
+        self.mf = None
+        self.displacement = None
+
+    def set_material(self, mf: MatrixFree, material: dict, material_inclusion: dict | None = None):
+        """mf_nh_operator.h:527-539; material = dict(mu, nu, rho, alpha_1, formulation)."""
+        self.clear()
+        self.mf = mf
+        m0 = _l.Material(material["mu"], material["nu"], material["rho"], material["alpha_1"],
+                         int(material.get("formulation", 1)))
+        mi = material_inclusion or material
+        m1 = _l.Material(mi["mu"], mi["nu"], mi["rho"], mi["alpha_1"], int(mi.get("formulation", 1)))
+        h = C.c_void_p()
+        _l.check(_l.load().b200mf_nh_create(C.byref(h), mf.h, C.byref(m0), C.byref(m1)))
+        self.h = h
+
+    def initialize(self, displacement, caching: str):
+        if caching not in _l.CACHING:
+            raise ValueError("Unknown caching")  # mf_nh_operator.h:385
+        self.displacement = displacement
+        _l.check(_l.load().b200mf_nh_initialize(self.h, _l.CACHING[caching]))
+
+    def cache(self):
+        bad = C.c_int64(0)
+        L = _l.load()
+        if isinstance(self.displacement, DeviceVector):
+            _l.check(L.b200mf_nh_cache(self.h, self.displacement.ptr, C.byref(bad)))
+        else:
+            d = np.ascontiguousarray(self.displacement, dtype=np.float64)
+            _l.check(L.b200mf_nh_cache_host(self.h, _ptr(d), C.byref(bad)))
+
+    def vmult(self, dst, src):
+        L = _l.load()
+        if isinstance(dst, np.ndarray):
+            s = np.ascontiguousarray(src, dtype=np.float64)
+            assert dst.dtype == np.float64 and dst.flags.c_contiguous
+            _l.check(L.b200mf_nh_vmult_host(self.h, _ptr(dst), _ptr(s)))
+        else:
+            _l.check(L.b200mf_nh_vmult(self.h, _dv(dst), _dv(src)))
+
+    def vmult_add(self, dst, src):
+        _l.check(_l.load().b200mf_nh_vmult_add(self.h, _dv(dst), _dv(src)))
+
+    def Tvmult(self, dst, src):
+        if isinstance(dst, np.ndarray):
+            return self.vmult(dst, src)
+        _l.check(_l.load().b200mf_nh_Tvmult(self.h, _dv(dst), _dv(src)))
+
+    def Tvmult_add(self, dst, src):
+        _l.check(_l.load().b200mf_nh_Tvmult_add(self.h, _dv(dst), _dv(src)))
+
+    def compute_diagonal(self):
+        _l.check(_l.load().b200mf_nh_compute_diagonal(self.h))
+
+    def get_matrix_diagonal(self):
+        d = np.empty(self.mf.n_dofs)
+        _l.check(_l.load().b200mf_nh_diagonal_host(self.h, _ptr(d), None))
+        return d
+
+    def get_matrix_diagonal_inverse(self):
+        d = np.empty(self.mf.n_dofs)
+        _l.check(_l.load().b200mf_nh_diagonal_host(self.h, None, _ptr(d)))
+        return d
+
+    def precondition_Jacobi(self, dst, src, omega):
+        _l.check(_l.load().b200mf_nh_precondition_jacobi(self.h, _dv(dst), _dv(src), float(omega)))
+
+    def el(self, row, col):
+        assert row == col  # mf_nh_operator.h:1067
+        v = C.c_double()
+        _l.check(_l.load().b200mf_nh_el(self.h, int(row), C.byref(v)))
+        return v.value
+
+    def m(self):
+        return _l.load().b200mf_nh_m(self.h)
+
+    n = m
+
+    def memory_consumption(self):
+        return _l.load().b200mf_nh_memory_consumption(self.h)
+
+    def qdata(self, field):
+        n = self.mf.degree + 1
+        out = np.empty((self.mf.n_cells, n**3))
+        _l.check(_l.load().b200mf_nh_qdata_host(self.h, int(field), _ptr(out)))
+        return out
+
+    def clear(self):
+        if getattr(self, "h", None):
+            _l.load().b200mf_nh_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.clear()
+        except Exception:
+            pass
+
+
+class LaplaceOperator:
+    """heat_transfer.h:81-127 (+ MatrixFreeOperators::Base surface)."""
+
+    def __init__(self, mf: MatrixFree, delta_t, coefficient=None):
+        self.mf = mf
+        coef = None if coefficient is None else np.ascontiguousarray(coefficient, dtype=np.float64)
+        h = C.c_void_p()
+        _l.check(_l.load().b200mf_laplace_create(C.byref(h), mf.h, float(delta_t), _ptr(coef)))
+        self.h = h
+
+    def set_delta_t(self, dt):
+        _l.check(_l.load().b200mf_laplace_set_delta_t(self.h, float(dt)))
+
+    def vmult(self, dst, src):
+        L = _l.load()
+        if isinstance(dst, np.ndarray):
+            s = np.ascontiguousarray(src, dtype=np.float64)
+            _l.check(L.b200mf_laplace_vmult_host(self.h, _ptr(dst), _ptr(s)))
+        else:
+            _l.check(L.b200mf_laplace_vmult(self.h, _dv(dst), _dv(src)))
+
+    Tvmult = vmult
+
+    def vmult_add(self, dst, src):
+        _l.check(_l.load().b200mf_laplace_vmult_add(self.h, _dv(dst), _dv(src)))
+
+    def compute_diagonal(self):
+        _l.check(_l.load().b200mf_laplace_compute_diagonal(self.h))
+
+    def get_matrix_diagonal(self):
+        d = np.empty(self.mf.n_dofs)
+        _l.check(_l.load().b200mf_laplace_diagonal_host(self.h, _ptr(d), None))
+        return d
+
+    def get_matrix_diagonal_inverse(self):
+        d = np.empty(self.mf.n_dofs)
+        _l.check(_l.load().b200mf_laplace_diagonal_host(self.h, None, _ptr(d)))
+        return d
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            _l.load().b200mf_laplace_destroy(self.h)
+            self.h = None

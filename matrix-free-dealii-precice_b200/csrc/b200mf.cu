@@ -1,0 +1,1051 @@
+// libb200mf: C ABI (include/b200mf.h) over the sm_100a kernels.
+// Host logic only in this file: numbering, table layout, launches.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <memory>
+#include <numeric>
+
+#include "common.h"
+#include "ops.cuh"
+
+namespace b200mf {
+
+thread_local std::string g_last_error;
+std::atomic<int64_t> g_launches{0};
+
+int set_error(int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+// ---------------------------------------------------------------------------
+// 1-D basis (host, long double Newton iterations)
+static void legendre(int n, long double x, long double &P, long double &dP, long double &ddP) {
+  long double p0 = 1.0L, p1 = x;
+  if (n == 0) {
+    P = 1;
+    dP = ddP = 0;
+    return;
+  }
+  for (int k = 2; k <= n; ++k) {
+    long double pk = ((2.0L * k - 1.0L) * x * p1 - (k - 1.0L) * p0) / k;
+    p0 = p1;
+    p1 = pk;
+  }
+  P = p1;
+  dP = n * (x * p1 - p0) / (x * x - 1.0L);
+  ddP = (2.0L * x * dP - n * (n + 1.0L) * p1) / (1.0L - x * x);
+}
+
+static void lagrange(int n, const long double *nodes, long double x, long double *v, long double *d) {
+  for (int i = 0; i < n; ++i) {
+    long double den = 1, num = 1, s = 0;
+    for (int j = 0; j < n; ++j)
+      if (j != i) {
+        den *= nodes[i] - nodes[j];
+        num *= x - nodes[j];
+      }
+    for (int m = 0; m < n; ++m)
+      if (m != i) {
+        long double t = 1;
+        for (int j = 0; j < n; ++j)
+          if (j != i && j != m) t *= x - nodes[j];
+        s += t;
+      }
+    v[i] = num / den;
+    d[i] = s / den;
+  }
+}
+
+void compute_shape_1d(int p, Shape1D &out) {
+  const int n = p + 1;
+  const long double pi = 3.141592653589793238462643383279502884L;
+  long double nd[8], xq[8], wq[8];
+  nd[0] = -1;
+  nd[p] = 1;
+  for (int i = 1; i < p; ++i) {
+    long double z = -cosl(pi * i / p);
+    for (int it = 0; it < 100; ++it) {
+      long double P, dP, ddP;
+      legendre(p, z, P, dP, ddP);
+      long double dz = dP / ddP;
+      z -= dz;
+      if (fabsl(dz) < 1e-19L) break;
+    }
+    nd[i] = z;
+  }
+  for (int i = 0; i <= p / 2; ++i) {
+    long double a = 0.5L * (nd[p - i] - nd[i]);
+    nd[i] = -a;
+    nd[p - i] = a;
+  }
+  for (int i = 0; i < n; ++i) {
+    long double z = -cosl(pi * (i + 0.75L) / (n + 0.5L));
+    long double P, dP, ddP;
+    for (int it = 0; it < 100; ++it) {
+      legendre(n, z, P, dP, ddP);
+      long double dz = P / dP;
+      z -= dz;
+      if (fabsl(dz) < 1e-19L) break;
+    }
+    legendre(n, z, P, dP, ddP);
+    xq[i] = z;
+    wq[i] = 2.0L / ((1.0L - z * z) * dP * dP);
+  }
+  for (int i = 0; i < n / 2; ++i) {
+    long double a = 0.5L * (xq[n - 1 - i] - xq[i]);
+    xq[i] = -a;
+    xq[n - 1 - i] = a;
+    long double ww = 0.5L * (wq[i] + wq[n - 1 - i]);
+    wq[i] = wq[n - 1 - i] = ww;
+  }
+  if (n % 2) xq[n / 2] = 0;
+  for (int i = 0; i < n; ++i) {
+    nd[i] = 0.5L * (nd[i] + 1.0L);
+    xq[i] = 0.5L * (xq[i] + 1.0L);
+    wq[i] *= 0.5L;
+  }
+  out.n = n;
+  long double v[8], d[8];
+  for (int q = 0; q < n; ++q) {
+    lagrange(n, nd, xq[q], v, d);
+    for (int i = 0; i < n; ++i) {
+      out.S[q * n + i] = (double)v[i];
+      out.D[q * n + i] = (double)d[i];
+    }
+    lagrange(n, xq, xq[q], v, d);
+    for (int r = 0; r < n; ++r) out.C[q * n + r] = (double)d[r];
+    out.w[q] = (double)wq[q];
+    out.xq[q] = (double)xq[q];
+  }
+  for (int i = 0; i < n; ++i) out.nodes[i] = (double)nd[i];
+}
+
+static int upload_shape_constants() {
+  static bool done = false;
+  if (done) return 0;
+  static double hd[MAXN + 1][2][MAXN * MAXN];
+  static float hf[MAXN + 1][2][MAXN * MAXN];
+  memset(hd, 0, sizeof hd);
+  for (int N = 2; N <= MAXN; ++N) {
+    Shape1D s;
+    compute_shape_1d(N - 1, s);
+    for (int i = 0; i < N * N; ++i) {
+      hd[N][0][i] = s.S[i];
+      hd[N][1][i] = s.C[i];
+    }
+  }
+  for (int N = 0; N <= MAXN; ++N)
+    for (int m = 0; m < 2; ++m)
+      for (int i = 0; i < MAXN * MAXN; ++i) hf[N][m][i] = (float)hd[N][m][i];
+  B2_CUDA(cudaMemcpyToSymbol(c_shape_d, hd, sizeof hd));
+  B2_CUDA(cudaMemcpyToSymbol(c_shape_f, hf, sizeof hf));
+  done = true;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// small kernels
+struct QuadPts {
+  double xq[MAXN], wq[MAXN];
+};
+
+// Q1 metric of StaticMappingQ1 at the Gauss points, written straight into the group layout.
+// invjac[e][f] = d xi_f / d x_e (mf_nh_operator.h:872-887), JxW = det J * w.
+template <typename T>
+__global__ void metric_from_vertices_kernel(int N, int cpg, int L, int64_t n_cells, int64_t n_cells_padded,
+                                            const double *__restrict__ vtx, QuadPts qp, T *__restrict__ mref) {
+  const int N2 = N * N, N3 = N2 * N;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_cells_padded * N3) return;
+  const int64_t cell = idx / N3;
+  const int q = (int)(idx % N3);
+  const int iq = q % N, jq = (q / N) % N, kq = q / N2;
+  const int64_t group = cell / cpg;
+  const int lane = (int)(cell % cpg) * N2 + kq * N + jq;
+  double Ki[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, jxw = 0.0;
+  if (cell < n_cells) {
+    const double *v = vtx + cell * 24;
+    const double xi[3] = {qp.xq[iq], qp.xq[jq], qp.xq[kq]};
+    double J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int m = 0; m < 8; ++m) {
+      double l[3], dl[3];
+      for (int d = 0; d < 3; ++d) {
+        const int bit = (m >> d) & 1;
+        l[d] = bit ? xi[d] : 1.0 - xi[d];
+        dl[d] = bit ? 1.0 : -1.0;
+      }
+      const double g[3] = {dl[0] * l[1] * l[2], l[0] * dl[1] * l[2], l[0] * l[1] * dl[2]};
+      for (int e = 0; e < 3; ++e)
+        for (int f = 0; f < 3; ++f) J[e * 3 + f] += v[m * 3 + e] * g[f];
+    }
+    const double det = J[0] * (J[4] * J[8] - J[5] * J[7]) - J[1] * (J[3] * J[8] - J[5] * J[6]) + J[2] * (J[3] * J[7] - J[4] * J[6]);
+    const double id = 1.0 / det;
+    double Ji[9];  // Ji[f][e] = d xi_f / d x_e
+    Ji[0] = (J[4] * J[8] - J[5] * J[7]) * id;
+    Ji[1] = (J[2] * J[7] - J[1] * J[8]) * id;
+    Ji[2] = (J[1] * J[5] - J[2] * J[4]) * id;
+    Ji[3] = (J[5] * J[6] - J[3] * J[8]) * id;
+    Ji[4] = (J[0] * J[8] - J[2] * J[6]) * id;
+    Ji[5] = (J[2] * J[3] - J[0] * J[5]) * id;
+    Ji[6] = (J[3] * J[7] - J[4] * J[6]) * id;
+    Ji[7] = (J[1] * J[6] - J[0] * J[7]) * id;
+    Ji[8] = (J[0] * J[4] - J[1] * J[3]) * id;
+    for (int e = 0; e < 3; ++e)
+      for (int f = 0; f < 3; ++f) Ki[e * 3 + f] = Ji[f * 3 + e];
+    jxw = det * qp.wq[iq] * qp.wq[jq] * qp.wq[kq];
+  }
+  const size_t FS = (size_t)N * L;
+  T *o = mref + (((size_t)group * MF_COUNT) * N + iq) * L + lane;
+  for (int i = 0; i < 9; ++i) o[(MF_K + i) * FS] = (T)Ki[i];
+  o[MF_W * FS] = (T)jxw;
+}
+
+// natural [cell][q][nf] (double) -> group layout T [group][nf][N][L]; padded cells get `pad`-pattern (identity K)
+template <typename T>
+__global__ void table_to_group_layout_kernel(int N, int cpg, int L, int nf, int64_t n_cells, int64_t n_cells_padded,
+                                             const double *__restrict__ in, T *__restrict__ out, int identity_pad) {
+  const int N2 = N * N, N3 = N2 * N;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_cells_padded * N3) return;
+  const int64_t cell = idx / N3;
+  const int q = (int)(idx % N3);
+  const int iq = q % N, jq = (q / N) % N, kq = q / N2;
+  const int64_t group = cell / cpg;
+  const int lane = (int)(cell % cpg) * N2 + kq * N + jq;
+  const size_t FS = (size_t)N * L;
+  T *o = out + (((size_t)group * nf) * N + iq) * L + lane;
+  for (int f = 0; f < nf; ++f) {
+    double v;
+    if (cell < n_cells)
+      v = in[((size_t)cell * N3 + q) * nf + f];
+    else
+      v = (identity_pad && (f == 0 || f == 4 || f == 8)) ? 1.0 : 0.0;
+    o[f * FS] = (T)v;
+  }
+}
+
+// group layout -> natural [cell][q] of one field (test hook)
+template <typename T>
+__global__ void field_from_group_layout_kernel(int N, int cpg, int L, int nf, int field, int64_t n_cells,
+                                               const T *__restrict__ in, double *__restrict__ out) {
+  const int N2 = N * N, N3 = N2 * N;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_cells * N3) return;
+  const int64_t cell = idx / N3;
+  const int q = (int)(idx % N3);
+  const int iq = q % N, jq = (q / N) % N, kq = q / N2;
+  const int64_t group = cell / cpg;
+  const int lane = (int)(cell % cpg) * N2 + kq * N + jq;
+  out[idx] = (double)in[((((size_t)group * nf) + field) * N + iq) * L + lane];
+}
+
+template <typename TO, typename TI>
+__global__ void permute_in_kernel(int64_t n, const int64_t *__restrict__ int2ext, const TI *__restrict__ ext, TO *__restrict__ in) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) in[i] = (TO)ext[int2ext ? int2ext[i] : i];
+}
+template <typename TO, typename TI>
+__global__ void permute_out_kernel(int64_t n, const int64_t *__restrict__ int2ext, TO *__restrict__ ext, const TI *__restrict__ in) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) ext[int2ext ? int2ext[i] : i] = (TO)in[i];
+}
+
+// dst[c] += src[c] on constrained rows (mf_nh_operator.h:623-624; MatrixFreeOperators::Base::vmult)
+template <typename T>
+__global__ void constrained_identity_kernel(int64_t n, const uint32_t *__restrict__ idx, T *__restrict__ dst, const T *__restrict__ src) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[idx[i]] += src[idx[i]];
+}
+
+// diag[constrained] = 1 (mf_nh_operator.h:1043-1044, heat_transfer.h:220)
+template <typename T>
+__global__ void set_constrained_one_kernel(int64_t n, const uint32_t *__restrict__ idx, T *__restrict__ diag) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) diag[idx[i]] = T(1);
+}
+// inv = 1/diag; counts non-positive entries (debug assertion mf_nh_operator.h:1049-1051)
+template <typename T>
+__global__ void invert_diagonal_kernel(int64_t n, const T *__restrict__ diag, T *__restrict__ inv, unsigned long long *n_bad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const T d = diag[i];
+    if (!(d > T(0))) atomicAdd(n_bad, 1ull);
+    inv[i] = T(1) / d;
+  }
+}
+// precondition_Jacobi: dst = omega * D^-1 src (mf_nh_operator.h:281-291)
+template <typename T>
+__global__ void jacobi_kernel(int64_t n, T *__restrict__ dst, const T *__restrict__ src, const T *__restrict__ inv, T omega) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = omega * inv[i] * src[i];
+}
+
+static inline unsigned nblocks(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+// ---------------------------------------------------------------------------
+// launch of the templated cell loop
+template <typename T, int N, class Op, bool DIAG = false>
+static int launch_cell_loop(const b200mf_ctx *ctx, const T *src, T *dst, const typename Op::Args &oa) {
+  using Ly = Layout<N, Op::NC>;
+  constexpr int GPB = Ly::WARP_MODE ? 4 : 1;
+  auto kern = cell_loop_kernel<T, N, Op, GPB, DIAG>;
+  const size_t smem = (size_t)GPB * Ly::GROUP_ELEMS * sizeof(T);
+  static int occ = 0;  // per instantiation
+  if (occ == 0) {
+    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Ly::TPG * GPB, smem));
+    if (occ < 1) return set_error(B200MF_ERR_CUDA, "cell kernel does not fit on an SM (N=%d)", N);
+  }
+  CellArgs<T> A;
+  A.n_groups = ctx->n_groups;
+  A.nidx = ctx->nidx;
+  A.src = src;
+  A.dst = dst;
+  const int64_t want = (ctx->n_groups + GPB - 1) / GPB;
+  const int64_t cap = (int64_t)ctx->sm_count * occ;
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min(want, cap));
+  kern<<<grid, Ly::TPG * GPB, smem, ctx->stream>>>(A, oa);
+  B2_LAUNCHED();
+  return 0;
+}
+
+#define B2_DISPATCH_N(N_, T_, ...)                                                  \
+  switch (N_) {                                                                      \
+    case 2: { constexpr int N = 2; using T = T_; __VA_ARGS__; } break;                      \
+    case 3: { constexpr int N = 3; using T = T_; __VA_ARGS__; } break;                      \
+    case 4: { constexpr int N = 4; using T = T_; __VA_ARGS__; } break;                      \
+    case 5: { constexpr int N = 5; using T = T_; __VA_ARGS__; } break;                      \
+    case 6: { constexpr int N = 6; using T = T_; __VA_ARGS__; } break;                      \
+    case 7: { constexpr int N = 7; using T = T_; __VA_ARGS__; } break;                      \
+    default: rc = set_error(B200MF_ERR_ARG, "unsupported degree %d", (N_) - 1);      \
+  }
+#define B2_DISPATCH(ctx_, ...)                                                      \
+  do {                                                                               \
+    if ((ctx_)->dtype == B200MF_F64) { B2_DISPATCH_N((ctx_)->N, double, __VA_ARGS__) }      \
+    else { B2_DISPATCH_N((ctx_)->N, float, __VA_ARGS__) }                                   \
+  } while (0)
+
+static inline size_t esize(const b200mf_ctx *c) { return c->dtype == B200MF_F64 ? 8 : 4; }
+
+}  // namespace b200mf
+
+using namespace b200mf;
+
+// ===========================================================================
+// ABI: misc
+extern "C" const char *b200mf_last_error(void) { return g_last_error.c_str(); }
+extern "C" int64_t b200mf_launch_count(void) { return g_launches.load(); }
+extern "C" int b200mf_version(void) { return 100; }
+
+// ===========================================================================
+// ABI: context
+extern "C" int b200mf_ctx_create(b200mf_ctx **out, const b200mf_ctx_desc *d) {
+  if (!out || !d) return set_error(B200MF_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (d->degree < 1 || d->degree > 6) return set_error(B200MF_ERR_ARG, "degree %d outside 1..6", d->degree);
+  if (d->n_q_points_1d != d->degree + 1)
+    return set_error(B200MF_ERR_ARG, "n_q_points_1d must be degree+1 (got %d for degree %d)", d->n_q_points_1d, d->degree);
+  if (d->n_components != 1 && d->n_components != 3) return set_error(B200MF_ERR_ARG, "n_components must be 1 or 3");
+  if (d->dtype != B200MF_F64 && d->dtype != B200MF_F32) return set_error(B200MF_ERR_ARG, "bad dtype");
+  if ((d->dof_indices == nullptr) == (d->node_indices == nullptr))
+    return set_error(B200MF_ERR_ARG, "exactly one of dof_indices / node_indices must be given");
+  if (d->n_cells < 0 || d->n_dofs <= 0 || d->n_owned < 0 || d->n_owned > d->n_dofs) return set_error(B200MF_ERR_ARG, "bad sizes");
+  if (!d->vertices && !(d->inverse_jacobian && d->jxw)) return set_error(B200MF_ERR_ARG, "need vertices or inverse_jacobian+jxw");
+  if (d->n_constrained > 0 && !d->constrained_dofs) return set_error(B200MF_ERR_ARG, "constrained_dofs is null");
+  B2_TRY(upload_shape_constants());
+
+  std::unique_ptr<b200mf_ctx> c(new b200mf_ctx());
+  memset(c.get(), 0, sizeof(b200mf_ctx));
+  c->degree = d->degree;
+  c->N = d->degree + 1;
+  c->NC = d->n_components;
+  c->dtype = d->dtype;
+  c->n_cells = d->n_cells;
+  c->n_dofs = d->n_dofs;
+  c->n_owned = d->n_owned;
+  const int N = c->N, N2 = N * N, N3 = N2 * N, NC = c->NC;
+  c->cpg = (N2 <= 32) ? 32 / N2 : 1;
+  c->L = c->cpg * N2;
+  c->n_groups = (c->n_cells + c->cpg - 1) / c->cpg;
+  compute_shape_1d(d->degree, c->shape);
+  int dev = 0;
+  B2_CUDA(cudaGetDevice(&dev));
+  B2_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, dev));
+
+  // ---- numbering: nodes, internal <-> caller permutation ---------------------
+  std::vector<uint32_t> node_of_cell((size_t)c->n_cells * N3);
+  std::vector<int64_t> int2ext;
+  bool identity = true;
+  if (d->node_indices) {
+    if (d->n_dofs % NC) return set_error(B200MF_ERR_ARG, "n_dofs not divisible by n_components");
+    c->n_nodes = d->n_dofs / NC;
+    c->n_int = d->n_dofs;
+    for (size_t i = 0; i < node_of_cell.size(); ++i) {
+      if ((int64_t)d->node_indices[i] >= c->n_nodes) return set_error(B200MF_ERR_ARG, "node index out of range");
+      node_of_cell[i] = d->node_indices[i];
+    }
+  } else {
+    // group the DoFs of the NC components that share a support point into nodes
+    const size_t ld = (size_t)NC * N3;
+    std::vector<int8_t> comp(d->n_dofs, -1);
+    std::vector<int64_t> lead(d->n_dofs, -1);  // DoF -> component-0 DoF of its node
+    for (int64_t cell = 0; cell < c->n_cells; ++cell)
+      for (int a = 0; a < N3; ++a) {
+        const uint32_t d0 = d->dof_indices[cell * ld + a];
+        for (int cc = 0; cc < NC; ++cc) {
+          const uint32_t dc = d->dof_indices[cell * ld + (size_t)cc * N3 + a];
+          if ((int64_t)dc >= d->n_dofs) return set_error(B200MF_ERR_ARG, "dof index %u out of range", dc);
+          if (comp[dc] == -1) {
+            comp[dc] = (int8_t)cc;
+            lead[dc] = d0;
+          } else if (comp[dc] != cc || lead[dc] != (int64_t)d0) {
+            return set_error(B200MF_ERR_ARG, "dof_indices: components of a support point are not consistent across cells (dof %u)", dc);
+          }
+        }
+      }
+    // node ids in ascending order of the component-0 DoF (keeps owned before ghost)
+    std::vector<int64_t> node_id(d->n_dofs, -1);
+    int64_t nn = 0;
+    for (int64_t i = 0; i < d->n_dofs; ++i)
+      if (comp[i] == 0) node_id[i] = nn++;
+    c->n_nodes = nn;
+    if (nn > (int64_t)NODE_MASK) return set_error(B200MF_ERR_ARG, "too many nodes per rank (%lld)", (long long)nn);
+    int64_t n_orphan = 0;
+    for (int64_t i = 0; i < d->n_dofs; ++i)
+      if (comp[i] == -1) ++n_orphan;
+    c->n_int = nn * NC + n_orphan;
+    int2ext.assign(c->n_int, 0);
+    int64_t orphan_pos = nn * NC;
+    for (int64_t i = 0; i < d->n_dofs; ++i) {
+      int64_t pos;
+      if (comp[i] == -1)
+        pos = orphan_pos++;
+      else
+        pos = node_id[lead[i]] * NC + comp[i];
+      int2ext[pos] = i;
+      if (pos != i) identity = false;
+    }
+    for (int64_t cell = 0; cell < c->n_cells; ++cell)
+      for (int a = 0; a < N3; ++a) node_of_cell[cell * N3 + a] = (uint32_t)node_id[d->dof_indices[cell * ld + a]];
+  }
+  if (c->n_nodes > (int64_t)NODE_MASK) return set_error(B200MF_ERR_ARG, "too many nodes per rank");
+  if (c->n_int >= (int64_t)1 << 32) return set_error(B200MF_ERR_ARG, "more than 2^32 local DoFs");
+
+  // ext -> int for the constrained list
+  std::vector<int64_t> ext2int;
+  if (!identity) {
+    ext2int.assign(d->n_dofs, -1);
+    for (int64_t i = 0; i < c->n_int; ++i) ext2int[int2ext[i]] = i;
+  }
+  std::vector<uint8_t> nflags(c->n_nodes, 0);
+  std::vector<uint32_t> cons_int(d->n_constrained);
+  for (int64_t i = 0; i < d->n_constrained; ++i) {
+    const uint32_t e = d->constrained_dofs[i];
+    if ((int64_t)e >= d->n_dofs) return set_error(B200MF_ERR_ARG, "constrained dof out of range");
+    const int64_t in = identity ? (int64_t)e : ext2int[e];
+    cons_int[i] = (uint32_t)in;
+    if (in < c->n_nodes * NC) nflags[in / NC] |= (uint8_t)(1u << (in % NC));
+  }
+  c->n_constrained = d->n_constrained;
+  if (!identity) c->h_ext2int = new std::vector<int64_t>(ext2int);
+
+  // ---- node index table in group layout [group][k][lane] ---------------------
+  {
+    const int L = c->L, cpg = c->cpg;
+    std::vector<uint32_t> nidx((size_t)c->n_groups * N * L, NODE_ALL_CONSTRAINED);
+    for (int64_t cell = 0; cell < c->n_cells; ++cell) {
+      const int64_t g = cell / cpg;
+      const int cw = (int)(cell % cpg);
+      for (int k = 0; k < N; ++k)
+        for (int ji = 0; ji < N2; ++ji) {
+          const uint32_t node = node_of_cell[cell * N3 + k * N2 + ji];
+          nidx[((size_t)g * N + k) * L + cw * N2 + ji] = node | ((uint32_t)nflags[node] << 29);
+        }
+    }
+    B2_CUDA(cudaMalloc(&c->nidx, nidx.size() * sizeof(uint32_t)));
+    B2_CUDA(cudaMemcpy(c->nidx, nidx.data(), nidx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    c->bytes += nidx.size() * sizeof(uint32_t);
+  }
+  if (!identity) {
+    B2_CUDA(cudaMalloc(&c->int2ext, int2ext.size() * sizeof(int64_t)));
+    B2_CUDA(cudaMemcpy(c->int2ext, int2ext.data(), int2ext.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+    c->bytes += int2ext.size() * sizeof(int64_t);
+  }
+  if (c->n_constrained) {
+    B2_CUDA(cudaMalloc(&c->constrained, cons_int.size() * sizeof(uint32_t)));
+    B2_CUDA(cudaMemcpy(c->constrained, cons_int.data(), cons_int.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    c->bytes += cons_int.size() * sizeof(uint32_t);
+  }
+  if (d->material_id) {
+    B2_CUDA(cudaMalloc(&c->matid, std::max<int64_t>(1, c->n_cells)));
+    B2_CUDA(cudaMemcpy(c->matid, d->material_id, c->n_cells, cudaMemcpyHostToDevice));
+    c->bytes += c->n_cells;
+  }
+  B2_CUDA(cudaMalloc(&c->stage, std::max<int64_t>(c->n_dofs, c->n_int) * sizeof(double)));
+  c->bytes += std::max<int64_t>(c->n_dofs, c->n_int) * sizeof(double);
+
+  // ---- reference metric -------------------------------------------------------
+  {
+    const size_t es = esize(c.get());
+    const size_t nel = (size_t)c->n_groups * MF_COUNT * N * c->L;
+    B2_CUDA(cudaMalloc(&c->mref, nel * es));
+    c->bytes += nel * es;
+    const int64_t padded = c->n_groups * c->cpg;
+    const int64_t nthreads = padded * N3;
+    if (d->vertices) {
+      double *dv = nullptr;
+      B2_CUDA(cudaMalloc(&dv, (size_t)c->n_cells * 24 * sizeof(double)));
+      B2_CUDA(cudaMemcpy(dv, d->vertices, (size_t)c->n_cells * 24 * sizeof(double), cudaMemcpyHostToDevice));
+      QuadPts qp;
+      for (int i = 0; i < N; ++i) {
+        qp.xq[i] = c->shape.xq[i];
+        qp.wq[i] = c->shape.w[i];
+      }
+      if (c->dtype == B200MF_F64)
+        metric_from_vertices_kernel<double><<<nblocks(nthreads, 256), 256>>>(N, c->cpg, c->L, c->n_cells, padded, dv, qp, (double *)c->mref);
+      else
+        metric_from_vertices_kernel<float><<<nblocks(nthreads, 256), 256>>>(N, c->cpg, c->L, c->n_cells, padded, dv, qp, (float *)c->mref);
+      B2_LAUNCHED();
+      B2_CUDA(cudaDeviceSynchronize());
+      cudaFree(dv);
+    } else {
+      // interleave K (9) and JxW (1) into one natural table, then reorder on the device
+      std::vector<double> nat((size_t)c->n_cells * N3 * MF_COUNT);
+      for (size_t cq = 0; cq < (size_t)c->n_cells * N3; ++cq) {
+        for (int i = 0; i < 9; ++i) nat[cq * MF_COUNT + i] = d->inverse_jacobian[cq * 9 + i];
+        nat[cq * MF_COUNT + MF_W] = d->jxw[cq];
+      }
+      double *dn = nullptr;
+      B2_CUDA(cudaMalloc(&dn, std::max<size_t>(8, nat.size() * sizeof(double))));
+      B2_CUDA(cudaMemcpy(dn, nat.data(), nat.size() * sizeof(double), cudaMemcpyHostToDevice));
+      if (c->dtype == B200MF_F64)
+        table_to_group_layout_kernel<double><<<nblocks(nthreads, 256), 256>>>(N, c->cpg, c->L, MF_COUNT, c->n_cells, padded, dn, (double *)c->mref, 1);
+      else
+        table_to_group_layout_kernel<float><<<nblocks(nthreads, 256), 256>>>(N, c->cpg, c->L, MF_COUNT, c->n_cells, padded, dn, (float *)c->mref, 1);
+      B2_LAUNCHED();
+      B2_CUDA(cudaDeviceSynchronize());
+      cudaFree(dn);
+    }
+  }
+  *out = c.release();
+  return 0;
+}
+
+extern "C" int b200mf_ctx_destroy(b200mf_ctx *c) {
+  if (!c) return 0;
+  cudaFree(c->nidx);
+  cudaFree(c->mref);
+  cudaFree(c->matid);
+  cudaFree(c->int2ext);
+  cudaFree(c->constrained);
+  cudaFree(c->stage);
+  delete c->h_ext2int;
+  delete c;
+  return 0;
+}
+
+extern "C" int b200mf_ctx_set_stream(b200mf_ctx *c, void *s) {
+  if (!c) return set_error(B200MF_ERR_ARG, "null ctx");
+  c->stream = (cudaStream_t)s;
+  return 0;
+}
+extern "C" int b200mf_ctx_synchronize(b200mf_ctx *c) {
+  if (!c) return set_error(B200MF_ERR_ARG, "null ctx");
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+extern "C" int64_t b200mf_ctx_n_dofs(const b200mf_ctx *c) { return c ? c->n_dofs : -1; }
+extern "C" size_t b200mf_ctx_memory_consumption(const b200mf_ctx *c) { return c ? c->bytes : 0; }
+
+// ===========================================================================
+// ABI: vectors
+extern "C" int b200mf_vec_create(b200mf_ctx *c, void **v) {
+  if (!c || !v) return set_error(B200MF_ERR_ARG, "null argument");
+  B2_CUDA(cudaMalloc(v, c->n_int * esize(c)));
+  B2_CUDA(cudaMemsetAsync(*v, 0, c->n_int * esize(c), c->stream));
+  return 0;
+}
+extern "C" int b200mf_vec_destroy(b200mf_ctx *, void *v) {
+  if (v) B2_CUDA(cudaFree(v));
+  return 0;
+}
+
+template <typename TD, typename TH>
+static int vec_upload_t(b200mf_ctx *c, TD *dvec, const TH *host) {
+  if (std::is_same<TD, TH>::value && !c->int2ext) {
+    B2_CUDA(cudaMemcpyAsync(dvec, host, c->n_int * sizeof(TD), cudaMemcpyHostToDevice, c->stream));
+    return 0;
+  }
+  B2_CUDA(cudaMemcpyAsync(c->stage, host, c->n_dofs * sizeof(TH), cudaMemcpyHostToDevice, c->stream));
+  permute_in_kernel<TD, TH><<<nblocks(c->n_int, 256), 256, 0, c->stream>>>(c->n_int, c->int2ext, (const TH *)c->stage, dvec);
+  B2_LAUNCHED();
+  return 0;
+}
+template <typename TD, typename TH>
+static int vec_download_t(b200mf_ctx *c, TH *host, const TD *dvec) {
+  if (std::is_same<TD, TH>::value && !c->int2ext) {
+    B2_CUDA(cudaMemcpyAsync(host, dvec, c->n_int * sizeof(TD), cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+  }
+  permute_out_kernel<TH, TD><<<nblocks(c->n_int, 256), 256, 0, c->stream>>>(c->n_int, c->int2ext, (TH *)c->stage, dvec);
+  B2_LAUNCHED();
+  B2_CUDA(cudaMemcpyAsync(host, c->stage, c->n_dofs * sizeof(TH), cudaMemcpyDeviceToHost, c->stream));
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int b200mf_vec_upload(b200mf_ctx *c, void *dvec, const void *host) {
+  if (!c || !dvec || !host) return set_error(B200MF_ERR_ARG, "null argument");
+  return c->dtype == B200MF_F64 ? vec_upload_t<double, double>(c, (double *)dvec, (const double *)host)
+                                : vec_upload_t<float, float>(c, (float *)dvec, (const float *)host);
+}
+extern "C" int b200mf_vec_download(b200mf_ctx *c, void *host, const void *dvec) {
+  if (!c || !dvec || !host) return set_error(B200MF_ERR_ARG, "null argument");
+  return c->dtype == B200MF_F64 ? vec_download_t<double, double>(c, (double *)host, (const double *)dvec)
+                                : vec_download_t<float, float>(c, (float *)host, (const float *)dvec);
+}
+extern "C" int b200mf_vec_upload_f64(b200mf_ctx *c, void *dvec, const double *host) {
+  if (!c || !dvec || !host) return set_error(B200MF_ERR_ARG, "null argument");
+  return c->dtype == B200MF_F64 ? vec_upload_t<double, double>(c, (double *)dvec, host)
+                                : vec_upload_t<float, double>(c, (float *)dvec, host);
+}
+extern "C" int b200mf_vec_download_f64(b200mf_ctx *c, double *host, const void *dvec) {
+  if (!c || !dvec || !host) return set_error(B200MF_ERR_ARG, "null argument");
+  return c->dtype == B200MF_F64 ? vec_download_t<double, double>(c, host, (const double *)dvec)
+                                : vec_download_t<float, double>(c, host, (const float *)dvec);
+}
+
+// ===========================================================================
+// NeoHookOperator
+struct b200mf_nh {
+  b200mf_ctx *ctx;
+  b200mf_material mat[2];
+  int caching;       // requested level (API parity); the device table is the tensor2 layout
+  bool initialized, cached, have_diag;
+  void *qd;          // T [group][NF][N][L]
+  size_t qd_bytes;
+  unsigned long long *n_bad;
+  void *diag, *inv_diag;
+  void *tmp_src, *tmp_dst;  // for the *_host entry points
+};
+
+static void derived(const b200mf_material &m, double &kappa, double &c_1, double &lambda, double &rho_alpha) {
+  kappa = (2.0 * m.mu * (1.0 + m.nu)) / (3.0 * (1.0 - 2.0 * m.nu));  // material.h:85
+  c_1 = m.mu / 2.0;
+  lambda = (2.0 * m.mu * m.nu) / (1.0 - 2.0 * m.nu);
+  rho_alpha = m.rho * m.alpha_1;
+}
+
+extern "C" int b200mf_nh_create(b200mf_nh **out, b200mf_ctx *ctx, const b200mf_material *mat, const b200mf_material *incl) {
+  if (!out || !ctx || !mat) return set_error(B200MF_ERR_ARG, "null argument");
+  if (ctx->NC != 3) return set_error(B200MF_ERR_ARG, "NeoHookOperator needs a 3-component context");
+  if (mat->formulation != 0 && mat->formulation != 1) return set_error(B200MF_ERR_ARG, "formulation must be 0 or 1");
+  if (!(mat->nu < 0.5 && mat->nu >= -1.0)) return set_error(B200MF_ERR_ARG, "Poisson ratio outside [-1,0.5) (material.h:88-89)");
+  std::unique_ptr<b200mf_nh> op(new b200mf_nh());
+  memset(op.get(), 0, sizeof(b200mf_nh));
+  op->ctx = ctx;
+  op->mat[0] = *mat;
+  op->mat[1] = incl ? *incl : *mat;
+  op->caching = -1;
+  B2_CUDA(cudaMalloc(&op->n_bad, sizeof(unsigned long long)));
+  *out = op.release();
+  return 0;
+}
+
+extern "C" int b200mf_nh_destroy(b200mf_nh *op) {
+  if (!op) return 0;
+  cudaFree(op->qd);
+  cudaFree(op->n_bad);
+  cudaFree(op->diag);
+  cudaFree(op->inv_diag);
+  cudaFree(op->tmp_src);
+  cudaFree(op->tmp_dst);
+  delete op;
+  return 0;
+}
+
+extern "C" int b200mf_nh_initialize(b200mf_nh *op, int caching) {
+  if (!op) return set_error(B200MF_ERR_ARG, "null op");
+  if (caching < B200MF_CACHE_SCALAR_REFERENTIAL || caching > B200MF_CACHE_TENSOR4_NS)
+    return set_error(B200MF_ERR_ARG, "Unknown caching");  // mf_nh_operator.h:385
+  if (op->mat[0].formulation == 0 && caching != B200MF_CACHE_TENSOR2)
+    return set_error(B200MF_ERR_ARG, "formulation 0 requires tensor2 caching (mf_nh_operator.h:419-424)");
+  if (caching != B200MF_CACHE_TENSOR2 || op->mat[0].formulation != 1)
+    return set_error(B200MF_ERR_ARG, "caching level %d / formulation %d not built yet", caching, op->mat[0].formulation);
+  b200mf_ctx *c = op->ctx;
+  op->caching = caching;
+  const size_t nel = (size_t)c->n_groups * QF_TENSOR2_COUNT * c->N * c->L;
+  if (op->qd) cudaFree(op->qd);
+  op->qd_bytes = nel * esize(c);
+  B2_CUDA(cudaMalloc(&op->qd, op->qd_bytes));
+  B2_CUDA(cudaMemsetAsync(op->qd, 0, op->qd_bytes, c->stream));
+  op->initialized = true;
+  op->cached = false;
+  op->have_diag = false;
+  return 0;
+}
+
+extern "C" int b200mf_nh_cache(b200mf_nh *op, const void *disp, int64_t *n_bad_out) {
+  if (!op || !disp) return set_error(B200MF_ERR_ARG, "null argument");
+  if (!op->initialized) return set_error(B200MF_ERR_STATE, "cache() before initialize()");
+  b200mf_ctx *c = op->ctx;
+  B2_CUDA(cudaMemsetAsync(op->n_bad, 0, sizeof(unsigned long long), c->stream));
+  double kappa[2], c_1[2], lambda[2], ra[2];
+  for (int m = 0; m < 2; ++m) derived(op->mat[m], kappa[m], c_1[m], lambda[m], ra[m]);
+  int rc = 0;
+  B2_DISPATCH(c, {
+    using Op = NHCacheTensor2Op<T, N>;
+    typename Op::Args oa;
+    oa.mref = (const T *)c->mref;
+    oa.qd = (T *)op->qd;
+    oa.matid = c->matid;
+    oa.n_cells = c->n_cells;
+    for (int m = 0; m < 2; ++m) {
+      oa.mu[m] = (T)op->mat[m].mu;
+      oa.lambda[m] = (T)lambda[m];
+    }
+    oa.n_bad = op->n_bad;
+    rc = launch_cell_loop<T, N, Op>(c, (const T *)disp, (T *)nullptr, oa);
+  });
+  B2_TRY(rc);
+  unsigned long long bad = 0;
+  B2_CUDA(cudaMemcpyAsync(&bad, op->n_bad, sizeof bad, cudaMemcpyDeviceToHost, c->stream));
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  if (n_bad_out) *n_bad_out = (int64_t)bad;
+  op->cached = true;
+  op->have_diag = false;
+  if (bad) return set_error(B200MF_ERR_NUMERIC, "det_F is not positive at %llu quadrature points", bad);  // :430-435
+  return 0;
+}
+
+static int nh_tmp(b200mf_nh *op) {
+  b200mf_ctx *c = op->ctx;
+  if (!op->tmp_src) B2_CUDA(cudaMalloc(&op->tmp_src, c->n_int * esize(c)));
+  if (!op->tmp_dst) B2_CUDA(cudaMalloc(&op->tmp_dst, c->n_int * esize(c)));
+  return 0;
+}
+
+extern "C" int b200mf_nh_cache_host(b200mf_nh *op, const double *disp, int64_t *n_bad_out) {
+  if (!op || !disp) return set_error(B200MF_ERR_ARG, "null argument");
+  B2_TRY(nh_tmp(op));
+  B2_TRY(b200mf_vec_upload_f64(op->ctx, op->tmp_src, disp));
+  return b200mf_nh_cache(op, op->tmp_src, n_bad_out);
+}
+
+static int nh_apply(b200mf_nh *op, void *dst, const void *src, bool zero_dst) {
+  if (!op || !dst || !src) return set_error(B200MF_ERR_ARG, "null argument");
+  if (dst == src) return set_error(B200MF_ERR_ARG, "vmult: dst aliases src");
+  if (!op->cached) return set_error(B200MF_ERR_STATE, "vmult before cache()");
+  b200mf_ctx *c = op->ctx;
+  if (zero_dst) B2_CUDA(cudaMemsetAsync(dst, 0, c->n_int * esize(c), c->stream));  // vmult: dst = 0, :548
+  double kappa[2], c_1[2], lambda[2], ra[2];
+  for (int m = 0; m < 2; ++m) derived(op->mat[m], kappa[m], c_1[m], lambda[m], ra[m]);
+  int rc = 0;
+  B2_DISPATCH(c, {
+    using Op = NHTensor2Op<T, N>;
+    typename Op::Args oa;
+    oa.qd = (const T *)op->qd;
+    oa.matid = c->matid;
+    oa.n_cells = c->n_cells;
+    for (int m = 0; m < 2; ++m) {
+      oa.lam2[m] = (T)(2.0 * lambda[m]);
+      oa.rho_alpha[m] = (T)ra[m];
+    }
+    rc = launch_cell_loop<T, N, Op>(c, (const T *)src, (T *)dst, oa);
+    if (rc == 0 && c->n_constrained) {
+      constrained_identity_kernel<T><<<nblocks(c->n_constrained, 256), 256, 0, c->stream>>>(c->n_constrained, c->constrained, (T *)dst, (const T *)src);
+      g_launches.fetch_add(1);
+    }
+  });
+  B2_TRY(rc);
+  B2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200mf_nh_vmult(b200mf_nh *op, void *dst, const void *src) { return nh_apply(op, dst, src, true); }
+extern "C" int b200mf_nh_vmult_add(b200mf_nh *op, void *dst, const void *src) { return nh_apply(op, dst, src, false); }
+extern "C" int b200mf_nh_Tvmult(b200mf_nh *op, void *dst, const void *src) { return nh_apply(op, dst, src, true); }       // :556-561
+extern "C" int b200mf_nh_Tvmult_add(b200mf_nh *op, void *dst, const void *src) { return nh_apply(op, dst, src, false); }  // :566-571
+
+extern "C" int b200mf_nh_vmult_host(b200mf_nh *op, double *dst, const double *src) {
+  if (!op || !dst || !src) return set_error(B200MF_ERR_ARG, "null argument");
+  B2_TRY(nh_tmp(op));
+  B2_TRY(b200mf_vec_upload_f64(op->ctx, op->tmp_src, src));
+  B2_TRY(nh_apply(op, op->tmp_dst, op->tmp_src, true));
+  return b200mf_vec_download_f64(op->ctx, dst, op->tmp_dst);
+}
+
+extern "C" int64_t b200mf_nh_m(const b200mf_nh *op) { return op ? op->ctx->n_dofs : -1; }
+extern "C" size_t b200mf_nh_memory_consumption(const b200mf_nh *op) { return op ? op->qd_bytes : 0; }
+extern "C" int b200mf_nh_n_qfields(const b200mf_nh *op) { return op && op->initialized ? QF_TENSOR2_COUNT : 0; }
+
+extern "C" int b200mf_nh_qdata_host(b200mf_nh *op, int field, double *out) {
+  if (!op || !out) return set_error(B200MF_ERR_ARG, "null argument");
+  if (!op->cached) return set_error(B200MF_ERR_STATE, "qdata before cache()");
+  if (field < 0 || field >= QF_TENSOR2_COUNT) return set_error(B200MF_ERR_ARG, "bad field");
+  b200mf_ctx *c = op->ctx;
+  const int64_t n = c->n_cells * c->N * c->N * c->N;
+  double *tmp = nullptr;
+  B2_CUDA(cudaMalloc(&tmp, n * sizeof(double)));
+  if (c->dtype == B200MF_F64)
+    field_from_group_layout_kernel<double><<<nblocks(n, 256), 256, 0, c->stream>>>(c->N, c->cpg, c->L, QF_TENSOR2_COUNT, field, c->n_cells, (const double *)op->qd, tmp);
+  else
+    field_from_group_layout_kernel<float><<<nblocks(n, 256), 256, 0, c->stream>>>(c->N, c->cpg, c->L, QF_TENSOR2_COUNT, field, c->n_cells, (const float *)op->qd, tmp);
+  B2_LAUNCHED();
+  B2_CUDA(cudaMemcpyAsync(out, tmp, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(tmp);
+  return 0;
+}
+
+
+template <class MakeArgsAndLaunch>
+static int finish_diagonal(b200mf_ctx *c, void *diag, void *inv, unsigned long long *n_bad, MakeArgsAndLaunch &&launch) {
+  B2_CUDA(cudaMemsetAsync(diag, 0, c->n_int * esize(c), c->stream));
+  B2_CUDA(cudaMemsetAsync(n_bad, 0, sizeof(unsigned long long), c->stream));
+  B2_TRY(launch());
+  if (c->dtype == B200MF_F64) {
+    if (c->n_constrained) {
+      set_constrained_one_kernel<double><<<nblocks(c->n_constrained, 256), 256, 0, c->stream>>>(c->n_constrained, c->constrained, (double *)diag);
+      B2_LAUNCHED();
+    }
+    // orphan entries (ghost slots no local cell touches) keep diag = 0 -> make them 1 as well
+    invert_diagonal_kernel<double><<<nblocks(c->n_nodes * c->NC, 256), 256, 0, c->stream>>>(c->n_nodes * c->NC, (const double *)diag, (double *)inv, n_bad);
+  } else {
+    if (c->n_constrained) {
+      set_constrained_one_kernel<float><<<nblocks(c->n_constrained, 256), 256, 0, c->stream>>>(c->n_constrained, c->constrained, (float *)diag);
+      B2_LAUNCHED();
+    }
+    invert_diagonal_kernel<float><<<nblocks(c->n_nodes * c->NC, 256), 256, 0, c->stream>>>(c->n_nodes * c->NC, (const float *)diag, (float *)inv, n_bad);
+  }
+  B2_LAUNCHED();
+  unsigned long long bad = 0;
+  B2_CUDA(cudaMemcpyAsync(&bad, n_bad, sizeof bad, cudaMemcpyDeviceToHost, c->stream));
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  if (bad)
+    return set_error(B200MF_ERR_NUMERIC, "No diagonal entry in a positive definite operator should be zero or negative (%llu entries)", bad);
+  return 0;
+}
+
+extern "C" int b200mf_nh_compute_diagonal(b200mf_nh *op) {
+  if (!op) return set_error(B200MF_ERR_ARG, "null op");
+  if (!op->cached) return set_error(B200MF_ERR_STATE, "compute_diagonal before cache()");
+  b200mf_ctx *c = op->ctx;
+  if (!op->diag) {
+    B2_CUDA(cudaMalloc(&op->diag, c->n_int * esize(c)));
+    B2_CUDA(cudaMalloc(&op->inv_diag, c->n_int * esize(c)));
+    B2_CUDA(cudaMemsetAsync(op->inv_diag, 0, c->n_int * esize(c), c->stream));
+  }
+  double kappa[2], c_1[2], lambda[2], ra[2];
+  for (int m = 0; m < 2; ++m) derived(op->mat[m], kappa[m], c_1[m], lambda[m], ra[m]);
+  int rc0 = finish_diagonal(c, op->diag, op->inv_diag, op->n_bad, [&]() {
+    int rc = 0;
+    B2_DISPATCH(c, {
+      using Op = NHTensor2Op<T, N>;
+      typename Op::Args oa;
+      oa.qd = (const T *)op->qd;
+      oa.matid = c->matid;
+      oa.n_cells = c->n_cells;
+      for (int m = 0; m < 2; ++m) {
+        oa.lam2[m] = (T)(2.0 * lambda[m]);
+        oa.rho_alpha[m] = (T)ra[m];
+      }
+      rc = launch_cell_loop<T, N, Op, true>(c, (const T *)nullptr, (T *)op->diag, oa);
+    });
+    return rc;
+  });
+  B2_TRY(rc0);
+  op->have_diag = true;
+  return 0;
+}
+
+extern "C" int b200mf_nh_diagonal(b200mf_nh *op, const void **diag, const void **inv) {
+  if (!op) return set_error(B200MF_ERR_ARG, "null op");
+  if (!op->have_diag) return set_error(B200MF_ERR_STATE, "diagonal not computed");
+  if (diag) *diag = op->diag;
+  if (inv) *inv = op->inv_diag;
+  return 0;
+}
+
+extern "C" int b200mf_nh_diagonal_host(b200mf_nh *op, double *diag, double *inv) {
+  if (!op) return set_error(B200MF_ERR_ARG, "null op");
+  if (!op->have_diag) return set_error(B200MF_ERR_STATE, "diagonal not computed");
+  if (diag) B2_TRY(b200mf_vec_download_f64(op->ctx, diag, op->diag));
+  if (inv) B2_TRY(b200mf_vec_download_f64(op->ctx, inv, op->inv_diag));
+  return 0;
+}
+
+extern "C" int b200mf_nh_precondition_jacobi(b200mf_nh *op, void *dst, const void *src, double omega) {
+  if (!op || !dst || !src) return set_error(B200MF_ERR_ARG, "null argument");
+  if (!op->have_diag) return set_error(B200MF_ERR_STATE, "precondition_Jacobi: inverse diagonal entries not available (mf_nh_operator.h:286-288)");
+  b200mf_ctx *c = op->ctx;
+  if (c->dtype == B200MF_F64)
+    jacobi_kernel<double><<<nblocks(c->n_int, 256), 256, 0, c->stream>>>(c->n_int, (double *)dst, (const double *)src, (const double *)op->inv_diag, omega);
+  else
+    jacobi_kernel<float><<<nblocks(c->n_int, 256), 256, 0, c->stream>>>(c->n_int, (float *)dst, (const float *)src, (const float *)op->inv_diag, (float)omega);
+  B2_LAUNCHED();
+  return 0;
+}
+
+extern "C" int b200mf_nh_el(b200mf_nh *op, int64_t row, double *value) {
+  if (!op || !value) return set_error(B200MF_ERR_ARG, "null argument");
+  if (!op->have_diag) return set_error(B200MF_ERR_STATE, "el(): diagonal not available (mf_nh_operator.h:1069-1071)");
+  b200mf_ctx *c = op->ctx;
+  if (row < 0 || row >= c->n_dofs) return set_error(B200MF_ERR_ARG, "row out of range");
+  const int64_t in = c->h_ext2int ? (*c->h_ext2int)[row] : row;
+  if (c->dtype == B200MF_F64) {
+    B2_CUDA(cudaMemcpyAsync(value, (const double *)op->diag + in, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+  } else {
+    float f;
+    B2_CUDA(cudaMemcpyAsync(&f, (const float *)op->diag + in, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    *value = f;
+  }
+  return 0;
+}
+
+// ===========================================================================
+// LaplaceOperator
+struct b200mf_laplace {
+  b200mf_ctx *ctx;
+  double delta_t;
+  void *coef;  // T [group][1][N][L] or nullptr
+  void *diag, *inv_diag;
+  void *tmp_src, *tmp_dst;
+  unsigned long long *n_bad;
+  bool have_diag;
+};
+
+extern "C" int b200mf_laplace_create(b200mf_laplace **out, b200mf_ctx *ctx, double delta_t, const double *coef) {
+  if (!out || !ctx) return set_error(B200MF_ERR_ARG, "null argument");
+  if (ctx->NC != 1) return set_error(B200MF_ERR_ARG, "LaplaceOperator needs a scalar context");
+  std::unique_ptr<b200mf_laplace> op(new b200mf_laplace());
+  memset(op.get(), 0, sizeof(b200mf_laplace));
+  op->ctx = ctx;
+  op->delta_t = delta_t;
+  if (coef) {
+    b200mf_ctx *c = ctx;
+    const int N = c->N, N3 = N * N * N;
+    const size_t nel = (size_t)c->n_groups * N * c->L;
+    double *dn = nullptr;
+    B2_CUDA(cudaMalloc(&dn, (size_t)c->n_cells * N3 * sizeof(double)));
+    B2_CUDA(cudaMemcpy(dn, coef, (size_t)c->n_cells * N3 * sizeof(double), cudaMemcpyHostToDevice));
+    B2_CUDA(cudaMalloc(&op->coef, nel * esize(c)));
+    const int64_t padded = c->n_groups * c->cpg;
+    if (c->dtype == B200MF_F64)
+      table_to_group_layout_kernel<double><<<nblocks(padded * N3, 256), 256>>>(N, c->cpg, c->L, 1, c->n_cells, padded, dn, (double *)op->coef, 0);
+    else
+      table_to_group_layout_kernel<float><<<nblocks(padded * N3, 256), 256>>>(N, c->cpg, c->L, 1, c->n_cells, padded, dn, (float *)op->coef, 0);
+    B2_LAUNCHED();
+    B2_CUDA(cudaDeviceSynchronize());
+    cudaFree(dn);
+  }
+  *out = op.release();
+  return 0;
+}
+
+extern "C" int b200mf_laplace_destroy(b200mf_laplace *op) {
+  if (!op) return 0;
+  cudaFree(op->coef);
+  cudaFree(op->n_bad);
+  cudaFree(op->diag);
+  cudaFree(op->inv_diag);
+  cudaFree(op->tmp_src);
+  cudaFree(op->tmp_dst);
+  delete op;
+  return 0;
+}
+
+extern "C" int b200mf_laplace_set_delta_t(b200mf_laplace *op, double dt) {
+  if (!op) return set_error(B200MF_ERR_ARG, "null op");
+  op->delta_t = dt;
+  op->have_diag = false;
+  return 0;
+}
+
+static int laplace_apply(b200mf_laplace *op, void *dst, const void *src, bool zero_dst) {
+  if (!op || !dst || !src) return set_error(B200MF_ERR_ARG, "null argument");
+  if (dst == src) return set_error(B200MF_ERR_ARG, "vmult: dst aliases src");
+  b200mf_ctx *c = op->ctx;
+  if (zero_dst) B2_CUDA(cudaMemsetAsync(dst, 0, c->n_int * esize(c), c->stream));
+  int rc = 0;
+  B2_DISPATCH(c, {
+    using Op = LaplaceOp<T, N>;
+    typename Op::Args oa;
+    oa.mref = (const T *)c->mref;
+    oa.coef = (const T *)op->coef;
+    oa.delta_t = (T)op->delta_t;
+    rc = launch_cell_loop<T, N, Op>(c, (const T *)src, (T *)dst, oa);
+    if (rc == 0 && c->n_constrained) {
+      constrained_identity_kernel<T><<<nblocks(c->n_constrained, 256), 256, 0, c->stream>>>(c->n_constrained, c->constrained, (T *)dst, (const T *)src);
+      g_launches.fetch_add(1);
+    }
+  });
+  B2_TRY(rc);
+  B2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200mf_laplace_vmult(b200mf_laplace *op, void *dst, const void *src) { return laplace_apply(op, dst, src, true); }
+extern "C" int b200mf_laplace_vmult_add(b200mf_laplace *op, void *dst, const void *src) { return laplace_apply(op, dst, src, false); }
+extern "C" int b200mf_laplace_Tvmult(b200mf_laplace *op, void *dst, const void *src) { return laplace_apply(op, dst, src, true); }
+
+extern "C" int b200mf_laplace_vmult_host(b200mf_laplace *op, double *dst, const double *src) {
+  if (!op || !dst || !src) return set_error(B200MF_ERR_ARG, "null argument");
+  b200mf_ctx *c = op->ctx;
+  if (!op->tmp_src) B2_CUDA(cudaMalloc(&op->tmp_src, c->n_int * esize(c)));
+  if (!op->tmp_dst) B2_CUDA(cudaMalloc(&op->tmp_dst, c->n_int * esize(c)));
+  B2_TRY(b200mf_vec_upload_f64(c, op->tmp_src, src));
+  B2_TRY(laplace_apply(op, op->tmp_dst, op->tmp_src, true));
+  return b200mf_vec_download_f64(c, dst, op->tmp_dst);
+}
+
+extern "C" int b200mf_laplace_compute_diagonal(b200mf_laplace *op) {
+  if (!op) return set_error(B200MF_ERR_ARG, "null op");
+  b200mf_ctx *c = op->ctx;
+  if (!op->diag) {
+    B2_CUDA(cudaMalloc(&op->diag, c->n_int * esize(c)));
+    B2_CUDA(cudaMalloc(&op->inv_diag, c->n_int * esize(c)));
+    B2_CUDA(cudaMemsetAsync(op->inv_diag, 0, c->n_int * esize(c), c->stream));
+    B2_CUDA(cudaMalloc(&op->n_bad, sizeof(unsigned long long)));
+  }
+  int rc0 = finish_diagonal(c, op->diag, op->inv_diag, op->n_bad, [&]() {
+    int rc = 0;
+    B2_DISPATCH(c, {
+      using Op = LaplaceOp<T, N>;
+      typename Op::Args oa;
+      oa.mref = (const T *)c->mref;
+      oa.coef = (const T *)op->coef;
+      oa.delta_t = (T)op->delta_t;
+      rc = launch_cell_loop<T, N, Op, true>(c, (const T *)nullptr, (T *)op->diag, oa);
+    });
+    return rc;
+  });
+  B2_TRY(rc0);
+  op->have_diag = true;
+  return 0;
+}
+extern "C" int b200mf_laplace_diagonal(b200mf_laplace *op, const void **diag, const void **inv) {
+  if (!op) return set_error(B200MF_ERR_ARG, "null op");
+  if (!op->have_diag) return set_error(B200MF_ERR_STATE, "diagonal not computed");
+  if (diag) *diag = op->diag;
+  if (inv) *inv = op->inv_diag;
+  return 0;
+}
+extern "C" int b200mf_laplace_diagonal_host(b200mf_laplace *op, double *diag, double *inv) {
+  if (!op) return set_error(B200MF_ERR_ARG, "null op");
+  if (!op->have_diag) return set_error(B200MF_ERR_STATE, "diagonal not computed");
+  if (diag) B2_TRY(b200mf_vec_download_f64(op->ctx, diag, op->diag));
+  if (inv) B2_TRY(b200mf_vec_download_f64(op->ctx, inv, op->inv_diag));
+  return 0;
+}

@@ -1,0 +1,66 @@
+// Host-side internals of libb200mf (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/b200mf.h"
+
+namespace b200mf {
+
+extern thread_local std::string g_last_error;
+extern std::atomic<int64_t> g_launches;
+
+int set_error(int code, const char *fmt, ...);
+
+#define B2_CUDA(call)                                                                                  \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess)                                                                             \
+      return b200mf::set_error(B200MF_ERR_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+#define B2_TRY(call)            \
+  do {                          \
+    int rc_ = (call);           \
+    if (rc_ != 0) return rc_;   \
+  } while (0)
+
+#define B2_LAUNCHED()                      \
+  do {                                     \
+    b200mf::g_launches.fetch_add(1);       \
+    B2_CUDA(cudaGetLastError());           \
+  } while (0)
+
+// 1-D basis on [0,1]: FE_Q(p) on Gauss-Lobatto points, QGauss(n)
+struct Shape1D {
+  int n;
+  double S[49], D[49], C[49], w[7], xq[7], nodes[7];
+};
+void compute_shape_1d(int p, Shape1D &out);
+
+}  // namespace b200mf
+
+struct b200mf_ctx {
+  int degree, N, NC, dtype;
+  int64_t n_cells, n_groups, n_dofs, n_owned;  // caller's local vector size
+  int64_t n_nodes, n_int;                      // internal vector length (NC*n_nodes + orphans)
+  int cpg, L;                                  // cells per group, dense lanes per group
+  cudaStream_t stream;
+  int sm_count;
+  // device data
+  uint32_t *nidx;        // [group][N][L]
+  void *mref;            // T [group][MF_COUNT][N][L] reference-configuration metric
+  uint8_t *matid;        // [n_cells] or nullptr
+  int64_t *int2ext;      // [n_int] or nullptr when identity
+  uint32_t *constrained; // internal indices of constrained DoFs
+  int64_t n_constrained;
+  void *stage;           // staging buffer, n_dofs elements of double
+  size_t bytes;
+  b200mf::Shape1D shape;
+  std::vector<int64_t> *h_ext2int;  // caller index -> internal index, nullptr when identity
+};

@@ -1,0 +1,238 @@
+"""GPU parity tests (call through the C ABI): CUDA operators vs the CPU oracle
+on the same seeded inputs.  Tolerances: FP64 <= 1e-12 relative l2 (BASELINE.json
+north_star); FP32 level operators <= 2e-5."""
+import numpy as np
+import pytest
+
+from b200mf import B200mfError, DeviceVector, LaplaceOperator, MatrixFree, NeoHookOperator
+from common import MAT, c_cells, displacement, make_mesh, rel
+from oracle import c_oracle as CO
+
+pytestmark = pytest.mark.gpu
+
+TOL64 = 1e-12
+TOL32 = 2e-5
+MATD = dict(formulation=1, **MAT)
+
+NCELLS = {1: (5, 4, 3), 2: (4, 3, 3), 3: (3, 3, 2), 4: (3, 2, 2), 5: (2, 2, 2), 6: (2, 2, 1)}
+
+
+def oracle_nh(m, u, level="tensor2", formulation=1, mu_inclusion=None):
+    op = CO.NeoHookOperator(c_cells(m), formulation=formulation, mu_inclusion=mu_inclusion, **MAT)
+    op.initialize(u, level)
+    op.cache()
+    return op
+
+
+def gpu_nh(m, u, dtype="f64", full_dof_map=False, inclusion=None, explicit_metric=None):
+    mf = MatrixFree.from_mesh(m, 3, dtype=dtype, full_dof_map=full_dof_map, explicit_metric=explicit_metric)
+    op = NeoHookOperator()
+    op.set_material(mf, MATD, inclusion)
+    op.initialize(u, "tensor2")
+    op.cache()
+    return mf, op
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6])
+def test_nh_vmult_fp64(p):
+    m = make_mesh(p, NCELLS[p])
+    u = displacement(m)
+    src = np.random.default_rng(p).uniform(-1, 1, 3 * m.n_nodes)
+    ref = np.zeros_like(src)
+    oracle_nh(m, u).vmult(ref, src)
+    mf, op = gpu_nh(m, u)
+    out = np.zeros_like(src)
+    op.vmult(out, src)  # host-vector entry point
+    assert rel(out, ref) < TOL64
+    # device-vector entry points: vmult, Tvmult, vmult_add
+    s, d = DeviceVector(mf, src), DeviceVector(mf)
+    op.vmult(d, s)
+    assert rel(d.download(), ref) < TOL64
+    op.Tvmult(d, s)
+    assert rel(d.download(), ref) < TOL64
+    op.vmult_add(d, s)
+    assert rel(d.download(), 2 * ref) < TOL64
+    assert op.m() == 3 * m.n_nodes
+
+
+@pytest.mark.parametrize("p", [2, 3])
+def test_nh_cache_tables(p):
+    """cache(): deformed metric J_cur = F J_ref and the tensor2 tables vs the oracle's
+    (mf_nh_operator.h:440-478)."""
+    m = make_mesh(p, NCELLS[p])
+    u = displacement(m)
+    orc = oracle_nh(m, u)
+    mf, op = gpu_nh(m, u)
+    import ctypes as C
+    nq3 = (p + 1) ** 3
+    n = m.n_cells * nq3
+
+    def tab(ptr, k):
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(n * k,)).reshape(m.n_cells, nq3, k).copy()
+
+    # read the oracle's tables through its struct layout is brittle: recompute from numpy twin instead
+    from common import np_cells
+    from oracle import np_oracle as NO
+    nop = NO.NeoHookOperator(np_cells(m), NO.Material(formulation=1, **MAT))
+    nop.initialize(u, "tensor2")
+    nop.cache()
+    K = np.stack([op.qdata(i) for i in range(9)], -1).reshape(m.n_cells, nq3, 3, 3)
+    assert rel(K, nop.invjac_cur) < TOL64
+    assert rel(op.qdata(9), nop.JxW_cur) < TOL64
+    assert rel(op.qdata(10), nop.cached_scalar) < TOL64
+    assert rel(op.qdata(11), nop.cached_second_scalar) < TOL64
+    T = nop.cached_tensor2
+    for s, (i, j) in enumerate([(0, 0), (1, 1), (2, 2), (0, 1), (0, 2), (1, 2)]):
+        assert rel(op.qdata(12 + s), T[..., i, j]) < 1e-11
+
+
+def test_nh_full_dof_map_blocked_numbering():
+    """dof_indices path with a non-interleaved caller numbering (component blocks):
+    the library renumbers internally and translates at upload/download."""
+    p = 2
+    m = make_mesh(p, NCELLS[p])
+    nn = m.n_nodes
+    nl = (p + 1) ** 3
+    dof = np.empty((m.n_cells, 3 * nl), dtype=np.int64)
+    for c in range(3):
+        dof[:, c * nl:(c + 1) * nl] = c * nn + m.cell_nodes
+    con_nodes = m.constrained_nodes  # [n_nodes, 3]
+    con = np.concatenate([c * nn + np.flatnonzero(con_nodes[:, c]) for c in range(3)]).astype(np.uint32)
+    conmask = np.zeros(3 * nn, dtype=bool)
+    conmask[con] = True
+    u_int = displacement(m)  # interleaved
+    u = u_int.reshape(nn, 3).T.reshape(-1).copy()  # blocked
+    invjac, jxw = CO.q1_metric(m.vertices, p + 1)
+    cells = CO.Cells(p, p + 1, 3, dof, conmask, invjac, jxw)
+    orc = CO.NeoHookOperator(cells, formulation=1, **MAT)
+    orc.initialize(u, "tensor2")
+    orc.cache()
+    src = np.random.default_rng(5).uniform(-1, 1, 3 * nn)
+    ref = np.zeros_like(src)
+    orc.vmult(ref, src)
+    mf = MatrixFree(p, 3, 3 * nn, dof_indices=dof, constrained_dofs=con, vertices=m.vertices)
+    op = NeoHookOperator()
+    op.set_material(mf, MATD)
+    op.initialize(u, "tensor2")
+    op.cache()
+    out = np.zeros_like(src)
+    op.vmult(out, src)
+    assert rel(out, ref) < TOL64
+    op.compute_diagonal()
+    d = orc.compute_diagonal()
+    assert rel(op.get_matrix_diagonal(), d) < TOL64
+    assert abs(op.el(7, 7) - d[7]) < 1e-12 * abs(d[7])
+
+
+def test_nh_explicit_metric_and_inclusion():
+    p = 2
+    m = make_mesh(p, NCELLS[p])
+    m.material_id[::3] = 2  # inclusion cells (material_id != 0 -> material_inclusion, :656-658)
+    u = displacement(m)
+    incl = dict(MATD, mu=100 * MATD["mu"])  # mf_elasticity.h:472
+    src = np.random.default_rng(7).uniform(-1, 1, 3 * m.n_nodes)
+    ref = np.zeros_like(src)
+    oracle_nh(m, u, mu_inclusion=incl["mu"]).vmult(ref, src)
+    metric = CO.q1_metric(m.vertices, p + 1)
+    for em in (None, metric):
+        mf, op = gpu_nh(m, u, inclusion=incl, explicit_metric=em)
+        out = np.zeros_like(src)
+        op.vmult(out, src)
+        assert rel(out, ref) < TOL64
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4])
+def test_nh_diagonal_and_jacobi(p):
+    m = make_mesh(p, (2, 2, 2))
+    u = displacement(m)
+    orc = oracle_nh(m, u)
+    d = orc.compute_diagonal()
+    mf, op = gpu_nh(m, u)
+    op.compute_diagonal()
+    assert rel(op.get_matrix_diagonal(), d) < TOL64
+    assert rel(op.get_matrix_diagonal_inverse(), 1.0 / d) < TOL64
+    src = np.random.default_rng(p).uniform(-1, 1, 3 * m.n_nodes)
+    s, o = DeviceVector(mf, src), DeviceVector(mf)
+    op.precondition_Jacobi(o, s, 0.65)
+    assert rel(o.download(), 0.65 * src / d) < TOL64
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6])
+def test_nh_vmult_fp32_level_operator(p):
+    m = make_mesh(p, NCELLS[p])
+    u = displacement(m)
+    src = np.random.default_rng(p).uniform(-1, 1, 3 * m.n_nodes)
+    ref = np.zeros_like(src)
+    oracle_nh(m, u).vmult(ref, src)
+    mf, op = gpu_nh(m, u, dtype="f32")
+    out = np.zeros_like(src)
+    op.vmult(out, src)
+    assert rel(out, ref) < TOL32
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("with_coef", [False, True])
+def test_laplace_vmult_and_diagonal(p, with_coef):
+    m = make_mesh(p, NCELLS[p], ncomp=1, clamp=((0, 0), (1, 1)))
+    cells = c_cells(m, 1)
+    nq3 = (p + 1) ** 3
+    coef = np.random.default_rng(1).uniform(0.5, 2.0, (m.n_cells, nq3)) if with_coef else None
+    dt = 0.1
+    orc = CO.LaplaceOperator(cells, dt, coef)
+    src = np.random.default_rng(p).uniform(-1, 1, m.n_nodes)
+    ref = np.zeros_like(src)
+    orc.vmult(ref, src)
+    mf = MatrixFree.from_mesh(m, 1)
+    op = LaplaceOperator(mf, dt, coef)
+    out = np.zeros_like(src)
+    op.vmult(out, src)
+    assert rel(out, ref) < TOL64
+    if p <= 4:
+        op.compute_diagonal()
+        assert rel(op.get_matrix_diagonal(), orc.compute_diagonal()) < TOL64
+
+
+def test_laplace_fp32():
+    p = 4
+    m = make_mesh(p, NCELLS[p], ncomp=1, clamp=((0, 0),))
+    orc = CO.LaplaceOperator(c_cells(m, 1), 0.1)
+    src = np.random.default_rng(0).uniform(-1, 1, m.n_nodes)
+    ref = np.zeros_like(src)
+    orc.vmult(ref, src)
+    mf = MatrixFree.from_mesh(m, 1, dtype="f32")
+    out = np.zeros_like(src)
+    LaplaceOperator(mf, 0.1).vmult(out, src)
+    assert rel(out, ref) < TOL32
+
+
+def test_error_behaviour():
+    m = make_mesh(2, (2, 2, 2))
+    mf = MatrixFree.from_mesh(m, 3)
+    op = NeoHookOperator()
+    op.set_material(mf, MATD)
+    s, d = DeviceVector(mf), DeviceVector(mf)
+    op.initialize(displacement(m), "tensor2")
+    with pytest.raises(B200mfError, match="before cache"):
+        op.vmult(d, s)
+    # det F <= 0 is reported (debug assertion mf_nh_operator.h:430-435)
+    op.initialize(-40.0 * displacement(m), "tensor2")
+    with pytest.raises(B200mfError, match="det_F is not positive"):
+        op.cache()
+    with pytest.raises(B200mfError):
+        MatrixFree(7, 3, 3 * m.n_nodes, node_indices=m.cell_nodes, vertices=m.vertices)
+
+
+def test_symmetry_large_random():
+    """size-independent property at a larger size: v^T A u == u^T A v."""
+    p = 3
+    m = make_mesh(p, (12, 10, 9), permute=None)
+    u = displacement(m)
+    mf, op = gpu_nh(m, u)
+    rng = np.random.default_rng(11)
+    a, b = rng.uniform(-1, 1, (2, 3 * m.n_nodes))
+    Aa, Ab = np.zeros_like(a), np.zeros_like(a)
+    op.vmult(Aa, a)
+    op.vmult(Ab, b)
+    assert abs(b @ Aa - a @ Ab) < 1e-11 * abs(b @ Aa)
+    con = m.constrained_dofs(3)
+    assert np.array_equal(Aa[con], a[con])
