@@ -160,7 +160,7 @@ struct QuadPts {
 // Q1 metric of StaticMappingQ1 at the Gauss points, written straight into the group layout.
 // invjac[e][f] = d xi_f / d x_e (mf_nh_operator.h:872-887), JxW = det J * w.
 template <typename T>
-__global__ void metric_from_vertices_kernel(int N, int cpg, int L, int64_t n_cells, int64_t n_cells_padded,
+__global__ void metric_from_vertices_kernel(int N, int cpg, int L, int64_t gstride, int64_t n_cells, int64_t n_cells_padded,
                                             const double *__restrict__ vtx, QuadPts qp, T *__restrict__ mref) {
   const int N2 = N * N, N3 = N2 * N;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -203,14 +203,14 @@ __global__ void metric_from_vertices_kernel(int N, int cpg, int L, int64_t n_cel
     jxw = det * qp.wq[iq] * qp.wq[jq] * qp.wq[kq];
   }
   const size_t FS = (size_t)N * L;
-  T *o = mref + (((size_t)group * MF_COUNT) * N + iq) * L + lane;
+  T *o = mref + (size_t)group * gstride + (size_t)iq * L + lane;
   for (int i = 0; i < 9; ++i) o[(MF_K + i) * FS] = (T)Ki[i];
   o[MF_W * FS] = (T)jxw;
 }
 
 // natural [cell][q][nf] (double) -> group layout T [group][nf][N][L]; padded cells get `pad`-pattern (identity K)
 template <typename T>
-__global__ void table_to_group_layout_kernel(int N, int cpg, int L, int nf, int64_t n_cells, int64_t n_cells_padded,
+__global__ void table_to_group_layout_kernel(int N, int cpg, int L, int nf, int64_t gstride, int64_t n_cells, int64_t n_cells_padded,
                                              const double *__restrict__ in, T *__restrict__ out, int identity_pad) {
   const int N2 = N * N, N3 = N2 * N;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -221,7 +221,7 @@ __global__ void table_to_group_layout_kernel(int N, int cpg, int L, int nf, int6
   const int64_t group = cell / cpg;
   const int lane = (int)(cell % cpg) * N2 + kq * N + jq;
   const size_t FS = (size_t)N * L;
-  T *o = out + (((size_t)group * nf) * N + iq) * L + lane;
+  T *o = out + (size_t)group * gstride + (size_t)iq * L + lane;
   for (int f = 0; f < nf; ++f) {
     double v;
     if (cell < n_cells)
@@ -234,7 +234,7 @@ __global__ void table_to_group_layout_kernel(int N, int cpg, int L, int nf, int6
 
 // group layout -> natural [cell][q] of one field (test hook)
 template <typename T>
-__global__ void field_from_group_layout_kernel(int N, int cpg, int L, int nf, int field, int64_t n_cells,
+__global__ void field_from_group_layout_kernel(int N, int cpg, int L, int64_t gstride, int field, int64_t n_cells,
                                                const T *__restrict__ in, double *__restrict__ out) {
   const int N2 = N * N, N3 = N2 * N;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -244,18 +244,24 @@ __global__ void field_from_group_layout_kernel(int N, int cpg, int L, int nf, in
   const int iq = q % N, jq = (q / N) % N, kq = q / N2;
   const int64_t group = cell / cpg;
   const int lane = (int)(cell % cpg) * N2 + kq * N + jq;
-  out[idx] = (double)in[((((size_t)group * nf) + field) * N + iq) * L + lane];
+  out[idx] = (double)in[(size_t)group * gstride + ((size_t)field * N + iq) * L + lane];
 }
 
 template <typename TO, typename TI>
 __global__ void permute_in_kernel(int64_t n, const int64_t *__restrict__ int2ext, const TI *__restrict__ ext, TO *__restrict__ in) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) in[i] = (TO)ext[int2ext ? int2ext[i] : i];
+  if (i < n) {
+    const int64_t e = int2ext ? int2ext[i] : i;
+    in[i] = e >= 0 ? (TO)ext[e] : TO(0);  // e < 0: padding slot between component blocks
+  }
 }
 template <typename TO, typename TI>
 __global__ void permute_out_kernel(int64_t n, const int64_t *__restrict__ int2ext, TO *__restrict__ ext, const TI *__restrict__ in) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) ext[int2ext ? int2ext[i] : i] = (TO)in[i];
+  if (i < n) {
+    const int64_t e = int2ext ? int2ext[i] : i;
+    if (e >= 0) ext[e] = (TO)in[i];
+  }
 }
 
 // dst[c] += src[c] on constrained rows (mf_nh_operator.h:623-624; MatrixFreeOperators::Base::vmult)
@@ -273,9 +279,14 @@ __global__ void set_constrained_one_kernel(int64_t n, const uint32_t *__restrict
 }
 // inv = 1/diag; counts non-positive entries (debug assertion mf_nh_operator.h:1049-1051)
 template <typename T>
-__global__ void invert_diagonal_kernel(int64_t n, const T *__restrict__ diag, T *__restrict__ inv, unsigned long long *n_bad) {
+__global__ void invert_diagonal_kernel(int64_t n, int64_t cstride, int64_t n_nodes, const T *__restrict__ diag, T *__restrict__ inv,
+                                       unsigned long long *n_bad) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
+    if (i % cstride >= n_nodes) {  // padding slot
+      inv[i] = T(0);
+      return;
+    }
     const T d = diag[i];
     if (!(d > T(0))) atomicAdd(n_bad, 1ull);
     inv[i] = T(1) / d;
@@ -292,29 +303,70 @@ static inline unsigned nblocks(int64_t n, int bs) { return (unsigned)((n + bs - 
 
 // ---------------------------------------------------------------------------
 // launch of the templated cell loop
-template <typename T, int N, class Op, bool DIAG = false>
-static int launch_cell_loop(const b200mf_ctx *ctx, const T *src, T *dst, const typename Op::Args &oa) {
-  using Ly = Layout<N, Op::NC>;
-  constexpr int GPB = Ly::WARP_MODE ? 4 : 1;
-  auto kern = cell_loop_kernel<T, N, Op, GPB, DIAG>;
-  const size_t smem = (size_t)GPB * Ly::GROUP_ELEMS * sizeof(T);
+// tuning: groups (warps) per block and the __launch_bounds__ minimum blocks per SM (register cap)
+static int g_tune_gpb = 0, g_tune_minb = 0;  // 0 = default; set by b200mf_set_tuning (experiments)
+
+template <typename T, int N, class Op, bool DIAG, int GPB, int MINB>
+static int launch_variant(const b200mf_ctx *ctx, const T *src, T *dst, const typename Op::Args &oa) {
+  using Ly = Layout<N, Op::NC, sizeof(T) / 4>;
+  auto kern = cell_loop_kernel<T, N, Op, GPB, DIAG, MINB>;
+  const size_t smem = (size_t)GPB * KernelSmem<T, N, Op>::GROUP_BYTES;
   static int occ = 0;  // per instantiation
   if (occ == 0) {
     B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // occupancy the registers allow with the largest carve-out, then give shared memory exactly what
+    // those blocks need and leave the rest to L1 (the DoF gather re-reads sectors: L1 hits matter)
+    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int occ_max = 0;
+    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_max, kern, Ly::TPG * GPB, smem));
+    if (occ_max < 1) return set_error(B200MF_ERR_CUDA, "cell kernel does not fit on an SM (N=%d, %zu B shared)", N, smem);
+    int pct = (int)((occ_max * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+    pct = std::min(100, std::max(1, pct));
+    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Ly::TPG * GPB, smem));
-    if (occ < 1) return set_error(B200MF_ERR_CUDA, "cell kernel does not fit on an SM (N=%d)", N);
+    if (occ < 1) occ = occ_max;
   }
   CellArgs<T> A;
   A.n_groups = ctx->n_groups;
   A.nidx = ctx->nidx;
   A.src = src;
   A.dst = dst;
+  A.cstride = ctx->cstride;
   const int64_t want = (ctx->n_groups + GPB - 1) / GPB;
   const int64_t cap = (int64_t)ctx->sm_count * occ;
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min(want, cap));
   kern<<<grid, Ly::TPG * GPB, smem, ctx->stream>>>(A, oa);
   B2_LAUNCHED();
   return 0;
+}
+
+template <typename T, int N, class Op, bool DIAG = false>
+static int launch_cell_loop(const b200mf_ctx *ctx, const T *src, T *dst, const typename Op::Args &oa) {
+  using Ly = Layout<N, Op::NC, sizeof(T) / 4>;
+  if constexpr (!Ly::WARP_MODE) {
+    return launch_variant<T, N, Op, DIAG, 1, 1>(ctx, src, dst, oa);
+  } else {
+#ifdef B2_EXPERIMENT
+    if constexpr (!DIAG && Op::INTEGRATE && Op::NC == 3 && std::is_same<T, double>::value && N >= 3 && N <= 5) {
+      const int key = g_tune_gpb * 10 + g_tune_minb;
+      switch (key) {
+        case 11: return launch_variant<T, N, Op, DIAG, 1, 1>(ctx, src, dst, oa);
+        case 31: return launch_variant<T, N, Op, DIAG, 3, 1>(ctx, src, dst, oa);
+        case 61: return launch_variant<T, N, Op, DIAG, 6, 1>(ctx, src, dst, oa);
+        case 21: return launch_variant<T, N, Op, DIAG, 2, 1>(ctx, src, dst, oa);
+        case 26: return launch_variant<T, N, Op, DIAG, 2, 6>(ctx, src, dst, oa);
+        case 41: return launch_variant<T, N, Op, DIAG, 4, 1>(ctx, src, dst, oa);
+        case 43: return launch_variant<T, N, Op, DIAG, 4, 3>(ctx, src, dst, oa);
+        case 81: return launch_variant<T, N, Op, DIAG, 8, 1>(ctx, src, dst, oa);
+        default: break;
+      }
+    }
+#endif
+    // warps per block from the B200 sweep (profiles/r01_sweep_*.jsonl): shared memory (cell buffers + staged
+    // table) bounds the resident warps, small blocks pack an SM best; N = 5 prefers 4-warp blocks
+    constexpr int GPB = (N == 5) ? 4 : (N == 2 ? 4 : 1);
+    return launch_variant<T, N, Op, DIAG, GPB, 1>(ctx, src, dst, oa);
+  }
 }
 
 #define B2_DISPATCH_N(N_, T_, ...)                                                  \
@@ -334,6 +386,10 @@ static int launch_cell_loop(const b200mf_ctx *ctx, const T *src, T *dst, const t
   } while (0)
 
 static inline size_t esize(const b200mf_ctx *c) { return c->dtype == B200MF_F64 ? 8 : 4; }
+// elements between groups of a [group][NF][N][L] table (== Layout::table_stride)
+static inline int64_t table_stride_rt(const b200mf_ctx *c, int NF) {
+  return (int64_t)round_up((size_t)NF * c->N * c->L, 16 / esize(c));
+}
 
 }  // namespace b200mf
 
@@ -344,6 +400,11 @@ using namespace b200mf;
 extern "C" const char *b200mf_last_error(void) { return g_last_error.c_str(); }
 extern "C" int64_t b200mf_launch_count(void) { return g_launches.load(); }
 extern "C" int b200mf_version(void) { return 100; }
+extern "C" int b200mf_set_tuning(int groups_per_block, int min_blocks_per_sm) {
+  g_tune_gpb = groups_per_block;
+  g_tune_minb = min_blocks_per_sm;
+  return 0;
+}
 
 // ===========================================================================
 // ABI: context
@@ -381,17 +442,20 @@ extern "C" int b200mf_ctx_create(b200mf_ctx **out, const b200mf_ctx_desc *d) {
   B2_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, dev));
 
   // ---- numbering: nodes, internal <-> caller permutation ---------------------
+  // internal vector layout: component blocks, DoF (node, c) at c*cstride + node; DoFs no local cell
+  // touches ("orphans", e.g. extra ghost slots) are appended after the blocks.
   std::vector<uint32_t> node_of_cell((size_t)c->n_cells * N3);
-  std::vector<int64_t> int2ext;
-  bool identity = true;
+  std::vector<int64_t> ext_of_nodecomp;  // [node*NC + c] -> caller DoF
+  std::vector<int64_t> orphans;
   if (d->node_indices) {
     if (d->n_dofs % NC) return set_error(B200MF_ERR_ARG, "n_dofs not divisible by n_components");
     c->n_nodes = d->n_dofs / NC;
-    c->n_int = d->n_dofs;
     for (size_t i = 0; i < node_of_cell.size(); ++i) {
       if ((int64_t)d->node_indices[i] >= c->n_nodes) return set_error(B200MF_ERR_ARG, "node index out of range");
       node_of_cell[i] = d->node_indices[i];
     }
+    ext_of_nodecomp.resize(d->n_dofs);
+    for (int64_t i = 0; i < d->n_dofs; ++i) ext_of_nodecomp[i] = i;
   } else {
     // group the DoFs of the NC components that share a support point into nodes
     const size_t ld = (size_t)NC * N3;
@@ -417,34 +481,52 @@ extern "C" int b200mf_ctx_create(b200mf_ctx **out, const b200mf_ctx_desc *d) {
     for (int64_t i = 0; i < d->n_dofs; ++i)
       if (comp[i] == 0) node_id[i] = nn++;
     c->n_nodes = nn;
-    if (nn > (int64_t)NODE_MASK) return set_error(B200MF_ERR_ARG, "too many nodes per rank (%lld)", (long long)nn);
-    int64_t n_orphan = 0;
-    for (int64_t i = 0; i < d->n_dofs; ++i)
-      if (comp[i] == -1) ++n_orphan;
-    c->n_int = nn * NC + n_orphan;
-    int2ext.assign(c->n_int, 0);
-    int64_t orphan_pos = nn * NC;
+    ext_of_nodecomp.assign(nn * NC, -1);
     for (int64_t i = 0; i < d->n_dofs; ++i) {
-      int64_t pos;
       if (comp[i] == -1)
-        pos = orphan_pos++;
+        orphans.push_back(i);
       else
-        pos = node_id[lead[i]] * NC + comp[i];
-      int2ext[pos] = i;
-      if (pos != i) identity = false;
+        ext_of_nodecomp[node_id[lead[i]] * NC + comp[i]] = i;
     }
     for (int64_t cell = 0; cell < c->n_cells; ++cell)
       for (int a = 0; a < N3; ++a) node_of_cell[cell * N3 + a] = (uint32_t)node_id[d->dof_indices[cell * ld + a]];
   }
-  if (c->n_nodes > (int64_t)NODE_MASK) return set_error(B200MF_ERR_ARG, "too many nodes per rank");
+  if (c->n_nodes > (int64_t)NODE_MASK) return set_error(B200MF_ERR_ARG, "too many nodes per rank (%lld)", (long long)c->n_nodes);
+  c->cstride = (int64_t)round_up((size_t)c->n_nodes, 32);
+  c->n_int = c->cstride * NC + (int64_t)orphans.size();
   if (c->n_int >= (int64_t)1 << 32) return set_error(B200MF_ERR_ARG, "more than 2^32 local DoFs");
-
-  // ext -> int for the constrained list
-  std::vector<int64_t> ext2int;
+  // scalar contexts with the caller's own numbering need no translation
+  bool identity = (NC == 1 && orphans.empty());
+  if (identity)
+    for (int64_t i = 0; i < c->n_nodes; ++i)
+      if (ext_of_nodecomp[i] != i) {
+        identity = false;
+        break;
+      }
+  std::vector<int64_t> int2ext, ext2int;
   if (!identity) {
+    int2ext.assign(c->n_int, -1);
     ext2int.assign(d->n_dofs, -1);
-    for (int64_t i = 0; i < c->n_int; ++i) ext2int[int2ext[i]] = i;
+    for (int64_t node = 0; node < c->n_nodes; ++node)
+      for (int cc = 0; cc < NC; ++cc) {
+        const int64_t e = ext_of_nodecomp[node * NC + cc], in = cc * c->cstride + node;
+        int2ext[in] = e;
+        if (e >= 0) ext2int[e] = in;
+      }
+    for (size_t k = 0; k < orphans.size(); ++k) {
+      int2ext[c->cstride * NC + (int64_t)k] = orphans[k];
+      ext2int[orphans[k]] = c->cstride * NC + (int64_t)k;
+    }
+    // owned nodes must precede ghost nodes inside every component block
+    for (int64_t node = 0; node + 1 < c->n_nodes; ++node) {
+      const bool o0 = ext_of_nodecomp[node * NC] < d->n_owned, o1 = ext_of_nodecomp[(node + 1) * NC] < d->n_owned;
+      if (!o0 && o1) return set_error(B200MF_ERR_ARG, "owned DoFs must precede ghost DoFs");
+    }
   }
+  c->n_owned_nodes = 0;
+  for (int64_t node = 0; node < c->n_nodes; ++node)
+    if (ext_of_nodecomp[node * NC] < d->n_owned) ++c->n_owned_nodes;
+
   std::vector<uint8_t> nflags(c->n_nodes, 0);
   std::vector<uint32_t> cons_int(d->n_constrained);
   for (int64_t i = 0; i < d->n_constrained; ++i) {
@@ -452,7 +534,7 @@ extern "C" int b200mf_ctx_create(b200mf_ctx **out, const b200mf_ctx_desc *d) {
     if ((int64_t)e >= d->n_dofs) return set_error(B200MF_ERR_ARG, "constrained dof out of range");
     const int64_t in = identity ? (int64_t)e : ext2int[e];
     cons_int[i] = (uint32_t)in;
-    if (in < c->n_nodes * NC) nflags[in / NC] |= (uint8_t)(1u << (in % NC));
+    if (in < c->cstride * NC) nflags[in % c->cstride] |= (uint8_t)(1u << (in / c->cstride));
   }
   c->n_constrained = d->n_constrained;
   if (!identity) c->h_ext2int = new std::vector<int64_t>(ext2int);
@@ -495,8 +577,10 @@ extern "C" int b200mf_ctx_create(b200mf_ctx **out, const b200mf_ctx_desc *d) {
   // ---- reference metric -------------------------------------------------------
   {
     const size_t es = esize(c.get());
-    const size_t nel = (size_t)c->n_groups * MF_COUNT * N * c->L;
+    const int64_t gs = table_stride_rt(c.get(), MF_COUNT);
+    const size_t nel = (size_t)c->n_groups * gs;
     B2_CUDA(cudaMalloc(&c->mref, nel * es));
+    B2_CUDA(cudaMemset(c->mref, 0, nel * es));
     c->bytes += nel * es;
     const int64_t padded = c->n_groups * c->cpg;
     const int64_t nthreads = padded * N3;
@@ -510,9 +594,9 @@ extern "C" int b200mf_ctx_create(b200mf_ctx **out, const b200mf_ctx_desc *d) {
         qp.wq[i] = c->shape.w[i];
       }
       if (c->dtype == B200MF_F64)
-        metric_from_vertices_kernel<double><<<nblocks(nthreads, 256), 256>>>(N, c->cpg, c->L, c->n_cells, padded, dv, qp, (double *)c->mref);
+        metric_from_vertices_kernel<double><<<nblocks(nthreads, 256), 256>>>(N, c->cpg, c->L, gs, c->n_cells, padded, dv, qp, (double *)c->mref);
       else
-        metric_from_vertices_kernel<float><<<nblocks(nthreads, 256), 256>>>(N, c->cpg, c->L, c->n_cells, padded, dv, qp, (float *)c->mref);
+        metric_from_vertices_kernel<float><<<nblocks(nthreads, 256), 256>>>(N, c->cpg, c->L, gs, c->n_cells, padded, dv, qp, (float *)c->mref);
       B2_LAUNCHED();
       B2_CUDA(cudaDeviceSynchronize());
       cudaFree(dv);
@@ -527,9 +611,9 @@ extern "C" int b200mf_ctx_create(b200mf_ctx **out, const b200mf_ctx_desc *d) {
       B2_CUDA(cudaMalloc(&dn, std::max<size_t>(8, nat.size() * sizeof(double))));
       B2_CUDA(cudaMemcpy(dn, nat.data(), nat.size() * sizeof(double), cudaMemcpyHostToDevice));
       if (c->dtype == B200MF_F64)
-        table_to_group_layout_kernel<double><<<nblocks(nthreads, 256), 256>>>(N, c->cpg, c->L, MF_COUNT, c->n_cells, padded, dn, (double *)c->mref, 1);
+        table_to_group_layout_kernel<double><<<nblocks(nthreads, 256), 256>>>(N, c->cpg, c->L, MF_COUNT, gs, c->n_cells, padded, dn, (double *)c->mref, 1);
       else
-        table_to_group_layout_kernel<float><<<nblocks(nthreads, 256), 256>>>(N, c->cpg, c->L, MF_COUNT, c->n_cells, padded, dn, (float *)c->mref, 1);
+        table_to_group_layout_kernel<float><<<nblocks(nthreads, 256), 256>>>(N, c->cpg, c->L, MF_COUNT, gs, c->n_cells, padded, dn, (float *)c->mref, 1);
       B2_LAUNCHED();
       B2_CUDA(cudaDeviceSynchronize());
       cudaFree(dn);
@@ -547,6 +631,7 @@ extern "C" int b200mf_ctx_destroy(b200mf_ctx *c) {
   cudaFree(c->int2ext);
   cudaFree(c->constrained);
   cudaFree(c->stage);
+  free_partitioner(c);
   delete c->h_ext2int;
   delete c;
   return 0;
@@ -581,7 +666,7 @@ extern "C" int b200mf_vec_destroy(b200mf_ctx *, void *v) {
 template <typename TD, typename TH>
 static int vec_upload_t(b200mf_ctx *c, TD *dvec, const TH *host) {
   if (std::is_same<TD, TH>::value && !c->int2ext) {
-    B2_CUDA(cudaMemcpyAsync(dvec, host, c->n_int * sizeof(TD), cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(dvec, host, c->n_dofs * sizeof(TD), cudaMemcpyHostToDevice, c->stream));
     return 0;
   }
   B2_CUDA(cudaMemcpyAsync(c->stage, host, c->n_dofs * sizeof(TH), cudaMemcpyHostToDevice, c->stream));
@@ -592,7 +677,7 @@ static int vec_upload_t(b200mf_ctx *c, TD *dvec, const TH *host) {
 template <typename TD, typename TH>
 static int vec_download_t(b200mf_ctx *c, TH *host, const TD *dvec) {
   if (std::is_same<TD, TH>::value && !c->int2ext) {
-    B2_CUDA(cudaMemcpyAsync(host, dvec, c->n_int * sizeof(TD), cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA(cudaMemcpyAsync(host, dvec, c->n_dofs * sizeof(TD), cudaMemcpyDeviceToHost, c->stream));
     B2_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
   }
@@ -683,7 +768,7 @@ extern "C" int b200mf_nh_initialize(b200mf_nh *op, int caching) {
     return set_error(B200MF_ERR_ARG, "caching level %d / formulation %d not built yet", caching, op->mat[0].formulation);
   b200mf_ctx *c = op->ctx;
   op->caching = caching;
-  const size_t nel = (size_t)c->n_groups * QF_TENSOR2_COUNT * c->N * c->L;
+  const size_t nel = (size_t)c->n_groups * table_stride_rt(c, QF_TENSOR2_COUNT);
   if (op->qd) cudaFree(op->qd);
   op->qd_bytes = nel * esize(c);
   B2_CUDA(cudaMalloc(&op->qd, op->qd_bytes));
@@ -699,13 +784,15 @@ extern "C" int b200mf_nh_cache(b200mf_nh *op, const void *disp, int64_t *n_bad_o
   if (!op->initialized) return set_error(B200MF_ERR_STATE, "cache() before initialize()");
   b200mf_ctx *c = op->ctx;
   B2_CUDA(cudaMemsetAsync(op->n_bad, 0, sizeof(unsigned long long), c->stream));
+  B2_TRY(update_ghost_values(c, const_cast<void *>(disp)));  // cache() reads ghosted displacement
   double kappa[2], c_1[2], lambda[2], ra[2];
   for (int m = 0; m < 2; ++m) derived(op->mat[m], kappa[m], c_1[m], lambda[m], ra[m]);
   int rc = 0;
   B2_DISPATCH(c, {
     using Op = NHCacheTensor2Op<T, N>;
     typename Op::Args oa;
-    oa.mref = (const T *)c->mref;
+    oa.stage = (const T *)c->mref;
+    oa.stage2 = nullptr;
     oa.qd = (T *)op->qd;
     oa.matid = c->matid;
     oa.n_cells = c->n_cells;
@@ -747,13 +834,15 @@ static int nh_apply(b200mf_nh *op, void *dst, const void *src, bool zero_dst) {
   if (!op->cached) return set_error(B200MF_ERR_STATE, "vmult before cache()");
   b200mf_ctx *c = op->ctx;
   if (zero_dst) B2_CUDA(cudaMemsetAsync(dst, 0, c->n_int * esize(c), c->stream));  // vmult: dst = 0, :548
+  B2_TRY(update_ghost_values(c, const_cast<void *>(src)));                          // :610
   double kappa[2], c_1[2], lambda[2], ra[2];
   for (int m = 0; m < 2; ++m) derived(op->mat[m], kappa[m], c_1[m], lambda[m], ra[m]);
   int rc = 0;
   B2_DISPATCH(c, {
     using Op = NHTensor2Op<T, N>;
     typename Op::Args oa;
-    oa.qd = (const T *)op->qd;
+    oa.stage = (const T *)op->qd;
+    oa.stage2 = nullptr;
     oa.matid = c->matid;
     oa.n_cells = c->n_cells;
     for (int m = 0; m < 2; ++m) {
@@ -761,6 +850,7 @@ static int nh_apply(b200mf_nh *op, void *dst, const void *src, bool zero_dst) {
       oa.rho_alpha[m] = (T)ra[m];
     }
     rc = launch_cell_loop<T, N, Op>(c, (const T *)src, (T *)dst, oa);
+    if (rc == 0) rc = compress_add(c, dst);  // :620
     if (rc == 0 && c->n_constrained) {
       constrained_identity_kernel<T><<<nblocks(c->n_constrained, 256), 256, 0, c->stream>>>(c->n_constrained, c->constrained, (T *)dst, (const T *)src);
       g_launches.fetch_add(1);
@@ -797,9 +887,9 @@ extern "C" int b200mf_nh_qdata_host(b200mf_nh *op, int field, double *out) {
   double *tmp = nullptr;
   B2_CUDA(cudaMalloc(&tmp, n * sizeof(double)));
   if (c->dtype == B200MF_F64)
-    field_from_group_layout_kernel<double><<<nblocks(n, 256), 256, 0, c->stream>>>(c->N, c->cpg, c->L, QF_TENSOR2_COUNT, field, c->n_cells, (const double *)op->qd, tmp);
+    field_from_group_layout_kernel<double><<<nblocks(n, 256), 256, 0, c->stream>>>(c->N, c->cpg, c->L, table_stride_rt(c, QF_TENSOR2_COUNT), field, c->n_cells, (const double *)op->qd, tmp);
   else
-    field_from_group_layout_kernel<float><<<nblocks(n, 256), 256, 0, c->stream>>>(c->N, c->cpg, c->L, QF_TENSOR2_COUNT, field, c->n_cells, (const float *)op->qd, tmp);
+    field_from_group_layout_kernel<float><<<nblocks(n, 256), 256, 0, c->stream>>>(c->N, c->cpg, c->L, table_stride_rt(c, QF_TENSOR2_COUNT), field, c->n_cells, (const float *)op->qd, tmp);
   B2_LAUNCHED();
   B2_CUDA(cudaMemcpyAsync(out, tmp, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   B2_CUDA(cudaStreamSynchronize(c->stream));
@@ -807,27 +897,29 @@ extern "C" int b200mf_nh_qdata_host(b200mf_nh *op, int field, double *out) {
   return 0;
 }
 
-
 template <class MakeArgsAndLaunch>
 static int finish_diagonal(b200mf_ctx *c, void *diag, void *inv, unsigned long long *n_bad, MakeArgsAndLaunch &&launch) {
   B2_CUDA(cudaMemsetAsync(diag, 0, c->n_int * esize(c), c->stream));
   B2_CUDA(cudaMemsetAsync(n_bad, 0, sizeof(unsigned long long), c->stream));
   B2_TRY(launch());
+  B2_TRY(compress_add(c, diag));
   if (c->dtype == B200MF_F64) {
     if (c->n_constrained) {
       set_constrained_one_kernel<double><<<nblocks(c->n_constrained, 256), 256, 0, c->stream>>>(c->n_constrained, c->constrained, (double *)diag);
       B2_LAUNCHED();
     }
     // orphan entries (ghost slots no local cell touches) keep diag = 0 -> make them 1 as well
-    invert_diagonal_kernel<double><<<nblocks(c->n_nodes * c->NC, 256), 256, 0, c->stream>>>(c->n_nodes * c->NC, (const double *)diag, (double *)inv, n_bad);
+    invert_diagonal_kernel<double><<<nblocks(c->cstride * c->NC, 256), 256, 0, c->stream>>>(c->cstride * c->NC, c->cstride, c->n_nodes, (const double *)diag, (double *)inv, n_bad);
   } else {
     if (c->n_constrained) {
       set_constrained_one_kernel<float><<<nblocks(c->n_constrained, 256), 256, 0, c->stream>>>(c->n_constrained, c->constrained, (float *)diag);
       B2_LAUNCHED();
     }
-    invert_diagonal_kernel<float><<<nblocks(c->n_nodes * c->NC, 256), 256, 0, c->stream>>>(c->n_nodes * c->NC, (const float *)diag, (float *)inv, n_bad);
+    invert_diagonal_kernel<float><<<nblocks(c->cstride * c->NC, 256), 256, 0, c->stream>>>(c->cstride * c->NC, c->cstride, c->n_nodes, (const float *)diag, (float *)inv, n_bad);
   }
   B2_LAUNCHED();
+  B2_TRY(update_ghost_values(c, diag));  // mf_nh_operator.h:1056-1057
+  B2_TRY(update_ghost_values(c, inv));
   unsigned long long bad = 0;
   B2_CUDA(cudaMemcpyAsync(&bad, n_bad, sizeof bad, cudaMemcpyDeviceToHost, c->stream));
   B2_CUDA(cudaStreamSynchronize(c->stream));
@@ -852,7 +944,8 @@ extern "C" int b200mf_nh_compute_diagonal(b200mf_nh *op) {
     B2_DISPATCH(c, {
       using Op = NHTensor2Op<T, N>;
       typename Op::Args oa;
-      oa.qd = (const T *)op->qd;
+      oa.stage = (const T *)op->qd;
+      oa.stage2 = nullptr;
       oa.matid = c->matid;
       oa.n_cells = c->n_cells;
       for (int m = 0; m < 2; ++m) {
@@ -936,16 +1029,17 @@ extern "C" int b200mf_laplace_create(b200mf_laplace **out, b200mf_ctx *ctx, doub
   if (coef) {
     b200mf_ctx *c = ctx;
     const int N = c->N, N3 = N * N * N;
-    const size_t nel = (size_t)c->n_groups * N * c->L;
+    const int64_t gs = table_stride_rt(c, 1);
+    const size_t nel = (size_t)c->n_groups * gs;
     double *dn = nullptr;
     B2_CUDA(cudaMalloc(&dn, (size_t)c->n_cells * N3 * sizeof(double)));
     B2_CUDA(cudaMemcpy(dn, coef, (size_t)c->n_cells * N3 * sizeof(double), cudaMemcpyHostToDevice));
     B2_CUDA(cudaMalloc(&op->coef, nel * esize(c)));
     const int64_t padded = c->n_groups * c->cpg;
     if (c->dtype == B200MF_F64)
-      table_to_group_layout_kernel<double><<<nblocks(padded * N3, 256), 256>>>(N, c->cpg, c->L, 1, c->n_cells, padded, dn, (double *)op->coef, 0);
+      table_to_group_layout_kernel<double><<<nblocks(padded * N3, 256), 256>>>(N, c->cpg, c->L, 1, gs, c->n_cells, padded, dn, (double *)op->coef, 0);
     else
-      table_to_group_layout_kernel<float><<<nblocks(padded * N3, 256), 256>>>(N, c->cpg, c->L, 1, c->n_cells, padded, dn, (float *)op->coef, 0);
+      table_to_group_layout_kernel<float><<<nblocks(padded * N3, 256), 256>>>(N, c->cpg, c->L, 1, gs, c->n_cells, padded, dn, (float *)op->coef, 0);
     B2_LAUNCHED();
     B2_CUDA(cudaDeviceSynchronize());
     cudaFree(dn);
@@ -978,14 +1072,16 @@ static int laplace_apply(b200mf_laplace *op, void *dst, const void *src, bool ze
   if (dst == src) return set_error(B200MF_ERR_ARG, "vmult: dst aliases src");
   b200mf_ctx *c = op->ctx;
   if (zero_dst) B2_CUDA(cudaMemsetAsync(dst, 0, c->n_int * esize(c), c->stream));
+  B2_TRY(update_ghost_values(c, const_cast<void *>(src)));
   int rc = 0;
   B2_DISPATCH(c, {
     using Op = LaplaceOp<T, N>;
     typename Op::Args oa;
-    oa.mref = (const T *)c->mref;
-    oa.coef = (const T *)op->coef;
+    oa.stage = (const T *)c->mref;
+    oa.stage2 = (const T *)op->coef;
     oa.delta_t = (T)op->delta_t;
     rc = launch_cell_loop<T, N, Op>(c, (const T *)src, (T *)dst, oa);
+    if (rc == 0) rc = compress_add(c, dst);
     if (rc == 0 && c->n_constrained) {
       constrained_identity_kernel<T><<<nblocks(c->n_constrained, 256), 256, 0, c->stream>>>(c->n_constrained, c->constrained, (T *)dst, (const T *)src);
       g_launches.fetch_add(1);
@@ -1024,8 +1120,8 @@ extern "C" int b200mf_laplace_compute_diagonal(b200mf_laplace *op) {
     B2_DISPATCH(c, {
       using Op = LaplaceOp<T, N>;
       typename Op::Args oa;
-      oa.mref = (const T *)c->mref;
-      oa.coef = (const T *)op->coef;
+      oa.stage = (const T *)c->mref;
+      oa.stage2 = (const T *)op->coef;
       oa.delta_t = (T)op->delta_t;
       rc = launch_cell_loop<T, N, Op, true>(c, (const T *)nullptr, (T *)op->diag, oa);
     });

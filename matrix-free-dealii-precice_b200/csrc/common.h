@@ -10,6 +10,8 @@
 
 #include "../../include/b200mf.h"
 
+struct b200mf_ctx;
+
 namespace b200mf {
 
 extern thread_local std::string g_last_error;
@@ -43,12 +45,21 @@ struct Shape1D {
 };
 void compute_shape_1d(int p, Shape1D &out);
 
+// comm.cu
+void free_partitioner(b200mf_ctx *c);
+int update_ghost_values(b200mf_ctx *c, void *vec);
+int compress_add(b200mf_ctx *c, void *vec);
+int zero_ghosts(b200mf_ctx *c, void *vec);
+int allreduce_sum_f64(b200mf_ctx *c, double *dptr, int n);
+
 }  // namespace b200mf
+
+struct b200mf_partitioner;
 
 struct b200mf_ctx {
   int degree, N, NC, dtype;
   int64_t n_cells, n_groups, n_dofs, n_owned;  // caller's local vector size
-  int64_t n_nodes, n_int;                      // internal vector length (NC*n_nodes + orphans)
+  int64_t n_nodes, n_owned_nodes, cstride, n_int;  // internal vector: NC blocks of cstride (>= n_nodes) + orphans
   int cpg, L;                                  // cells per group, dense lanes per group
   cudaStream_t stream;
   int sm_count;
@@ -62,5 +73,6 @@ struct b200mf_ctx {
   void *stage;           // staging buffer, n_dofs elements of double
   size_t bytes;
   b200mf::Shape1D shape;
+  b200mf_partitioner *part;         // nullptr on a single rank
   std::vector<int64_t> *h_ext2int;  // caller index -> internal index, nullptr when identity
 };

@@ -25,11 +25,12 @@ struct MaterialConsts {  // material.h:78-94, 252-258
 // a4: tensor2 level, formulation 1, deformed frame (mf_nh_operator.h:945-974)
 template <typename T, int N>
 struct NHTensor2Op {
-  static constexpr int NC = 3, NF = QF_TENSOR2_COUNT, MIN_BLOCKS = 1;
+  static constexpr int NC = 3, NF = QF_TENSOR2_COUNT, NF_IN = QF_TENSOR2_COUNT, NF_IN2 = 0;
   static constexpr bool PLAIN = false, INTEGRATE = true;
-  using Ly = Layout<N, NC>;
+  using Ly = Layout<N, NC, sizeof(T) / 4>;
   struct Args {
-    const T *qd;
+    const T *stage;   // tensor2 table [group][NF][N][L]
+    const T *stage2;  // unused
     const uint8_t *matid;
     int64_t n_cells;
     T lam2[2];       // 2*lambda
@@ -44,22 +45,22 @@ struct NHTensor2Op {
     st.lam2 = m ? oa.lam2[1] : oa.lam2[0];
     st.rho_alpha = m ? oa.rho_alpha[1] : oa.rho_alpha[0];
   }
-  static __device__ __forceinline__ void quad(const Args &oa, const CellState &st, bool active, int64_t group, int iq,
-                                              int lane, const T (&v)[NC], const T (&G)[NC][3], T (&ov)[NC],
-                                              T (&oG)[NC][3]) {
+  static __device__ __forceinline__ void quad(const Args &, const CellState &st, bool active, const T *qs, const T *,
+                                              int64_t, int iq, int lane, const T (&v)[NC], const T (&G)[NC][3],
+                                              T (&ov)[NC], T (&oG)[NC][3]) {
     if (!active) {
 #pragma unroll
       for (int c = 0; c < NC; ++c) ov[c] = oG[c][0] = oG[c][1] = oG[c][2] = T(0);
       return;
     }
-    const T *q = oa.qd + qoff<N, Ly::L>(group, NF, 0, iq, lane);
-    constexpr size_t FS = (size_t)N * Ly::L;
+    const T *q = qs + iq * Ly::L + lane;
+    constexpr int FS = N * Ly::L;
     T K[9], Ts[6];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) K[i] = ld_stream(q + (QF_K + i) * FS);
-    const T w = ld_stream(q + QF_W * FS), c1 = ld_stream(q + QF_C1 * FS), c2 = ld_stream(q + QF_C2 * FS);
+    for (int i = 0; i < 9; ++i) K[i] = q[(QF_K + i) * FS];
+    const T w = q[QF_W * FS], c1 = q[QF_C1 * FS], c2 = q[QF_C2 * FS];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) Ts[i] = ld_stream(q + (QF_T + i) * FS);
+    for (int i = 0; i < 6; ++i) Ts[i] = q[(QF_T + i) * FS];
     const T Tm[3][3] = {{Ts[0], Ts[3], Ts[4]}, {Ts[3], Ts[1], Ts[5]}, {Ts[4], Ts[5], Ts[2]}};
     T g[3][3];  // grad_x v, get_gradient :954
 #pragma unroll
@@ -90,12 +91,13 @@ struct NHTensor2Op {
 // + deformed-frame metric (replaces MatrixFree::update_mapping(MappingQEulerian), mf_elasticity.h:955)
 template <typename T, int N>
 struct NHCacheTensor2Op {
-  static constexpr int NC = 3, NF = QF_TENSOR2_COUNT, MIN_BLOCKS = 1;
+  static constexpr int NC = 3, NF = QF_TENSOR2_COUNT, NF_IN = MF_COUNT, NF_IN2 = 0;
   static constexpr bool PLAIN = true, INTEGRATE = false;
-  using Ly = Layout<N, NC>;
+  using Ly = Layout<N, NC, sizeof(T) / 4>;
   struct Args {
-    const T *mref;  // [group][MF_COUNT][N][L]
-    T *qd;          // out
+    const T *stage;   // reference metric [group][MF_COUNT][N][L]
+    const T *stage2;  // unused
+    T *qd;            // out: tensor2 table
     const uint8_t *matid;
     int64_t n_cells;
     T mu[2], lambda[2];
@@ -112,12 +114,12 @@ struct NHCacheTensor2Op {
     st.mu = m ? oa.mu[1] : oa.mu[0];
     st.lambda = m ? oa.lambda[1] : oa.lambda[0];
   }
-  static __device__ __forceinline__ void quad(const Args &oa, const CellState &st, bool active, int64_t group, int iq,
-                                              int lane, const T (&)[NC], const T (&G)[NC][3], T (&)[NC],
-                                              T (&)[NC][3]) {
+  static __device__ __forceinline__ void quad(const Args &oa, const CellState &st, bool active, const T *qs, const T *,
+                                              int64_t group, int iq, int lane, const T (&)[NC], const T (&G)[NC][3],
+                                              T (&)[NC], T (&)[NC][3]) {
     if (!active) return;
     constexpr size_t FS = (size_t)N * Ly::L;
-    const T *m = oa.mref + qoff<N, Ly::L>(group, MF_COUNT, 0, iq, lane);
+    const T *m = qs + iq * Ly::L + lane;
     T Kr[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) Kr[i] = m[(MF_K + i) * FS];
@@ -141,7 +143,7 @@ struct NHCacheTensor2Op {
     const T detF = F[0][0] * Fi[0][0] + F[0][1] * Fi[1][0] + F[0][2] * Fi[2][0];
     if (st.real && !(detF > T(0))) atomicAdd(oa.n_bad, 1ull);  // :430-435
     const T idet = T(1) / detF;
-    T *q = oa.qd + qoff<N, Ly::L>(group, NF, 0, iq, lane);
+    T *q = oa.qd + (size_t)group * Ly::table_stride(NF) + iq * Ly::L + lane;
     // K_cur[e][f] = sum_m Finv[m][e] K_ref[m][f]   (invjac_cur = F^-T invjac_ref)
 #pragma unroll
     for (int e = 0; e < 3; ++e)
@@ -166,31 +168,31 @@ struct NHCacheTensor2Op {
 // a13: LaplaceOperator::do_operation_on_cell (heat_transfer.h:234-250): (M + dt*c*K) u
 template <typename T, int N>
 struct LaplaceOp {
-  static constexpr int NC = 1, MIN_BLOCKS = 1;
+  static constexpr int NC = 1, NF_IN = MF_COUNT, NF_IN2 = 1;
   static constexpr bool PLAIN = false, INTEGRATE = true;
-  using Ly = Layout<N, NC>;
+  using Ly = Layout<N, NC, sizeof(T) / 4>;
   struct Args {
-    const T *mref;  // [group][MF_COUNT][N][L]
-    const T *coef;  // [group][1][N][L] or nullptr (Coefficient::value == 1, heat_transfer.h:64-71)
+    const T *stage;   // reference metric [group][MF_COUNT][N][L]
+    const T *stage2;  // coefficient [group][1][N][L] or nullptr (Coefficient::value == 1, heat_transfer.h:64-71)
     T delta_t;
   };
   struct CellState {};
   static __device__ __forceinline__ void cell_begin(const Args &, int64_t, bool, CellState &) {}
-  static __device__ __forceinline__ void quad(const Args &oa, const CellState &, bool active, int64_t group, int iq,
-                                              int lane, const T (&v)[NC], const T (&G)[NC][3], T (&ov)[NC],
-                                              T (&oG)[NC][3]) {
+  static __device__ __forceinline__ void quad(const Args &oa, const CellState &, bool active, const T *qs, const T *qs2,
+                                              int64_t, int iq, int lane, const T (&v)[NC], const T (&G)[NC][3],
+                                              T (&ov)[NC], T (&oG)[NC][3]) {
     if (!active) {
       ov[0] = oG[0][0] = oG[0][1] = oG[0][2] = T(0);
       return;
     }
-    constexpr size_t FS = (size_t)N * Ly::L;
-    const T *m = oa.mref + qoff<N, Ly::L>(group, MF_COUNT, 0, iq, lane);
+    constexpr int FS = N * Ly::L;
+    const T *m = qs + iq * Ly::L + lane;
     T K[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) K[i] = ld_stream(m + (MF_K + i) * FS);
-    const T w = ld_stream(m + MF_W * FS);
+    for (int i = 0; i < 9; ++i) K[i] = m[(MF_K + i) * FS];
+    const T w = m[MF_W * FS];
     T k = oa.delta_t;
-    if (oa.coef != nullptr) k *= ld_stream(oa.coef + qoff<N, Ly::L>(group, 1, 0, iq, lane));  // :245-247
+    if (oa.stage2 != nullptr) k *= qs2[iq * Ly::L + lane];  // :245-247
     T g[3];
 #pragma unroll
     for (int e = 0; e < 3; ++e) g[e] = K[e * 3 + 0] * G[0][0] + K[e * 3 + 1] * G[0][1] + K[e * 3 + 2] * G[0][2];
