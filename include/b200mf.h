@@ -118,6 +118,34 @@ int b200mf_vec_upload_f64(b200mf_ctx *ctx, void *dvec, const double *host);   /*
 int b200mf_vec_download_f64(b200mf_ctx *ctx, double *host, const void *dvec);
 
 /* ------------------------------------------------------------------------
+ * Multi-GPU: one rank per GPU.  Replaces the MPI side of
+ * LinearAlgebra::distributed::Vector / Utilities::MPI::Partitioner:
+ * update_ghost_values (mf_nh_operator.h:610), compress(add) (:620),
+ * zero_out_ghost_values, and the allreduce inside l2_norm / operator*
+ * (mf_elasticity.h:1907, 1993).  Transport: NCCL over NVLink (libnccl is
+ * dlopen'ed at first use, so single-GPU users need no NCCL).
+ * ------------------------------------------------------------------------ */
+typedef struct b200mf_comm b200mf_comm;
+/* rank 0 fills a 128-byte id (ncclUniqueId) and broadcasts it to the other ranks by any host means (MPI_Bcast, a file,
+ * torch.distributed) before everyone calls b200mf_comm_create — the role of MPI_COMM_WORLD in src/solid.cc:30-31 */
+int b200mf_comm_unique_id(void *id128);
+int b200mf_comm_create(b200mf_comm **comm, int rank, int world, const void *id128);
+int b200mf_comm_destroy(b200mf_comm *comm);
+
+typedef struct { /* Utilities::MPI::Partitioner of MatrixFree::get_vector_partitioner(); caller numbering */
+  int n_neighbors;
+  const int *neighbor_ranks;     /* [n_neighbors] */
+  const int64_t *send_offsets;   /* [n_neighbors+1] into send_indices: import_indices per neighbour */
+  const uint32_t *send_indices;  /* locally owned entries the neighbour ghosts (import_indices) */
+  const int64_t *ghost_offsets;  /* [n_neighbors] first local index of the contiguous ghost range owned by the neighbour */
+  const int64_t *ghost_counts;   /* [n_neighbors] */
+} b200mf_partitioner_desc;
+int b200mf_ctx_set_partitioner(b200mf_ctx *ctx, b200mf_comm *comm, const b200mf_partitioner_desc *desc);
+int b200mf_vec_update_ghost_values(b200mf_ctx *ctx, void *dvec);   /* Vector::update_ghost_values */
+int b200mf_vec_compress_add(b200mf_ctx *ctx, void *dvec);          /* Vector::compress(VectorOperation::add) */
+int b200mf_vec_zero_out_ghost_values(b200mf_ctx *ctx, void *dvec); /* Vector::zero_out_ghost_values */
+
+/* ------------------------------------------------------------------------
  * NeoHookOperator (include/solid_mechanics/mf_nh_operator.h)
  * ------------------------------------------------------------------------ */
 typedef struct { /* Material_Compressible_Neo_Hook_One_Field ctor, include/solid_mechanics/material.h:78-94 */

@@ -29,6 +29,11 @@ class CtxDesc(C.Structure):
     ]
 
 
+class PartitionerDesc(C.Structure):
+    _fields_ = [("n_neighbors", C.c_int), ("neighbor_ranks", C.c_void_p), ("send_offsets", C.c_void_p),
+                ("send_indices", C.c_void_p), ("ghost_offsets", C.c_void_p), ("ghost_counts", C.c_void_p)]
+
+
 class Material(C.Structure):
     _fields_ = [("mu", C.c_double), ("nu", C.c_double), ("rho", C.c_double), ("alpha_1", C.c_double),
                 ("formulation", C.c_int)]
@@ -56,6 +61,13 @@ SIGNATURES = {
     "b200mf_vec_download": (_i32, [_vp, _vp, _vp]),
     "b200mf_vec_upload_f64": (_i32, [_vp, _vp, _vp]),
     "b200mf_vec_download_f64": (_i32, [_vp, _vp, _vp]),
+    "b200mf_comm_unique_id": (_i32, [_vp]),
+    "b200mf_comm_create": (_i32, [_PP, _i32, _i32, _vp]),
+    "b200mf_comm_destroy": (_i32, [_vp]),
+    "b200mf_ctx_set_partitioner": (_i32, [_vp, _vp, C.POINTER(PartitionerDesc)]),
+    "b200mf_vec_update_ghost_values": (_i32, [_vp, _vp]),
+    "b200mf_vec_compress_add": (_i32, [_vp, _vp]),
+    "b200mf_vec_zero_out_ghost_values": (_i32, [_vp, _vp]),
     "b200mf_nh_create": (_i32, [_PP, _vp, C.POINTER(Material), C.POINTER(Material)]),
     "b200mf_nh_destroy": (_i32, [_vp]),
     "b200mf_nh_initialize": (_i32, [_vp, _i32]),
