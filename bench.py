@@ -37,14 +37,24 @@ def algorithmic_bytes_per_cell(p, esize=8):
     return 2 * esize * 3 * p**3 + 4 * n**3 + 18 * esize * n**3
 
 
-def build_problem(p, ncell_dir, dtype="f64"):
+def build_problem(p, ncell_dir, dtype="f64", comm=None):
+    """One brick of ncell_dir^3 cells per rank (SURVEY.md §8d config 5: 1x1x1, 2x1x1, 2x2x1, 2x2x2 bricks);
+    shared faces are exchanged through the library's partitioner (update_ghost_values / compress(add))."""
     from b200mf import MatrixFree, NeoHookOperator
     from b200mf.mesh import StructuredMesh, synthetic_displacement
 
-    m = StructuredMesh((ncell_dir,) * 3, p)
-    m.clamp([(0, 0)], 3)
-    u = synthetic_displacement(m.node_coordinates(), 0.05)
-    mf = MatrixFree.from_mesh(m, 3, dtype=dtype)
+    if comm is not None and comm.world > 1:
+        from b200mf.partition import BrickPartition, weak_scaling_grid
+
+        m = BrickPartition(weak_scaling_grid(comm.world), ncell_dir, p, comm.rank)
+        m.clamp_global_face(0, 0)
+        u = synthetic_displacement(m.node_coordinates(), 0.05)
+        mf = MatrixFree.from_partition(m, comm, dtype=dtype)
+    else:
+        m = StructuredMesh((ncell_dir,) * 3, p)
+        m.clamp([(0, 0)], 3)
+        u = synthetic_displacement(m.node_coordinates(), 0.05)
+        mf = MatrixFree.from_mesh(m, 3, dtype=dtype)
     op = NeoHookOperator()
     op.set_material(mf, MAT)
     op.initialize(u, "tensor2")
@@ -213,10 +223,12 @@ def main():
     L = b200mf.load()
     nc = CELLS_PER_DIR[p] if args.cells is None else args.cells
     es = 8 if args.dtype == "f64" else 4
-    m, mf, op = build_problem(p, nc, args.dtype)
-    n = 3 * m.n_nodes
+    comm = b200mf.Communicator.from_torch_distributed() if world > 1 else None
+    m, mf, op = build_problem(p, nc, args.dtype, comm)
+    n = 3 * m.n_nodes  # local vector: owned + ghost entries
+    n_owned = m.n_owned if world > 1 else n
     src_h = np.random.default_rng(rank).uniform(-1, 1, n)
-    src_h[m.constrained_dofs(3)] = 0.0
+    src_h[m.constrained_dofs(3) if world == 1 else m.constrained_dofs()] = 0.0
     src, dst = DeviceVector(mf, src_h), DeviceVector(mf)
     stream = torch.cuda.current_stream()
     mf.set_stream(stream.cuda_stream)
@@ -244,7 +256,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     ms = total_ms / args.steps
-    dofs_total = n * world  # weak scaling: every rank owns a brick of the same size
+    dofs_total = n_owned  # global DoFs = sum of the owned entries of all ranks (weak scaling: one brick per rank)
+    if dist is not None:
+        t = torch.tensor([n_owned], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        dofs_total = int(t.item())
     value = dofs_total / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel (the cell loop; memset + constrained fix-up are the rest of the step)
@@ -254,7 +270,7 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    alg_bytes = algorithmic_bytes_per_cell(p, es) * m.n_cells
+    alg_bytes = algorithmic_bytes_per_cell(p, es) * m.n_cells  # per GPU (per launch of the cell kernel)
     achieved = alg_bytes / (ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",

@@ -20,6 +20,38 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+class Communicator:
+    """One rank per GPU (the role of MPI_COMM_WORLD, src/solid.cc:30-31): an NCCL communicator owned by the library.
+    The 128-byte unique id is created on rank 0 and handed to the other ranks by the host (here: torch.distributed)."""
+
+    def __init__(self, rank, world, unique_id: bytes):
+        self.rank, self.world = int(rank), int(world)
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        h = C.c_void_p()
+        _l.check(_l.load().b200mf_comm_create(C.byref(h), self.rank, self.world, buf))
+        self.h = h
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _l.check(_l.load().b200mf_comm_unique_id(buf))
+        return buf.raw
+
+    @classmethod
+    def from_torch_distributed(cls):
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(), dist.get_world_size()
+        box = [cls.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return cls(rank, world, box[0])
+
+    def destroy(self):
+        if getattr(self, "h", None):
+            _l.load().b200mf_comm_destroy(self.h)
+            self.h = None
+
+
 class MatrixFree:
     """Cell-batch data resident in HBM (index maps, constraint masks, metric)."""
 
@@ -77,6 +109,27 @@ class MatrixFree:
             kw.update(node_indices=mesh.cell_nodes)
         return cls(mesh.p, n_components, mesh.n_nodes * n_components, **kw)
 
+    @classmethod
+    def from_partition(cls, part, comm: "Communicator | None", dtype="f64"):
+        """Build rank-local data from a b200mf.partition.BrickPartition and attach the vector partitioner
+        (import indices / ghost ranges per neighbour)."""
+        con = np.flatnonzero(part.constrained_dofs()).astype(np.uint32)
+        mf = cls(part.p, part.ncomp, part.n_dofs, node_indices=part.cell_nodes, constrained_dofs=con,
+                 vertices=part.vertices, material_id=part.material_id, dtype=dtype, n_owned=part.n_owned)
+        if comm is not None and comm.world > 1:
+            mf.set_partitioner(comm, part.partitioner_arrays())
+        return mf
+
+    def set_partitioner(self, comm, arrays):
+        ranks = np.ascontiguousarray(arrays["ranks"], dtype=np.int32)
+        so = np.ascontiguousarray(arrays["send_offsets"], dtype=np.int64)
+        si = np.ascontiguousarray(arrays["send_indices"], dtype=np.uint32)
+        go = np.ascontiguousarray(arrays["ghost_offsets"], dtype=np.int64)
+        gc = np.ascontiguousarray(arrays["ghost_counts"], dtype=np.int64)
+        d = _l.PartitionerDesc(len(ranks), _ptr(ranks), _ptr(so), _ptr(si), _ptr(go), _ptr(gc))
+        _l.check(_l.load().b200mf_ctx_set_partitioner(self.h, comm.h, C.byref(d)))
+        self.comm = comm
+
     def set_stream(self, cuda_stream):
         _l.check(_l.load().b200mf_ctx_set_stream(self.h, C.c_void_p(cuda_stream)))
 
@@ -117,6 +170,15 @@ class DeviceVector:
         out = np.empty(self.mf.n_dofs, dtype=np.float64)
         _l.check(_l.load().b200mf_vec_download_f64(self.mf.h, _ptr(out), self.ptr))
         return out
+
+    def update_ghost_values(self):
+        _l.check(_l.load().b200mf_vec_update_ghost_values(self.mf.h, self.ptr))
+
+    def compress_add(self):
+        _l.check(_l.load().b200mf_vec_compress_add(self.mf.h, self.ptr))
+
+    def zero_out_ghost_values(self):
+        _l.check(_l.load().b200mf_vec_zero_out_ghost_values(self.mf.h, self.ptr))
 
     def __del__(self):
         if getattr(self, "ptr", None) and getattr(self.mf, "h", None):

@@ -283,7 +283,7 @@ __global__ void invert_diagonal_kernel(int64_t n, int64_t cstride, int64_t n_nod
                                        unsigned long long *n_bad) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    if (i % cstride >= n_nodes) {  // padding slot
+    if (i % cstride >= n_nodes) {  // padding slot, or a ghost entry (filled by update_ghost_values afterwards, :1056-1057)
       inv[i] = T(0);
       return;
     }
@@ -909,13 +909,13 @@ static int finish_diagonal(b200mf_ctx *c, void *diag, void *inv, unsigned long l
       B2_LAUNCHED();
     }
     // orphan entries (ghost slots no local cell touches) keep diag = 0 -> make them 1 as well
-    invert_diagonal_kernel<double><<<nblocks(c->cstride * c->NC, 256), 256, 0, c->stream>>>(c->cstride * c->NC, c->cstride, c->n_nodes, (const double *)diag, (double *)inv, n_bad);
+    invert_diagonal_kernel<double><<<nblocks(c->cstride * c->NC, 256), 256, 0, c->stream>>>(c->cstride * c->NC, c->cstride, c->n_owned_nodes, (const double *)diag, (double *)inv, n_bad);
   } else {
     if (c->n_constrained) {
       set_constrained_one_kernel<float><<<nblocks(c->n_constrained, 256), 256, 0, c->stream>>>(c->n_constrained, c->constrained, (float *)diag);
       B2_LAUNCHED();
     }
-    invert_diagonal_kernel<float><<<nblocks(c->cstride * c->NC, 256), 256, 0, c->stream>>>(c->cstride * c->NC, c->cstride, c->n_nodes, (const float *)diag, (float *)inv, n_bad);
+    invert_diagonal_kernel<float><<<nblocks(c->cstride * c->NC, 256), 256, 0, c->stream>>>(c->cstride * c->NC, c->cstride, c->n_owned_nodes, (const float *)diag, (float *)inv, n_bad);
   }
   B2_LAUNCHED();
   B2_TRY(update_ghost_values(c, diag));  // mf_nh_operator.h:1056-1057
