@@ -8,7 +8,7 @@
 #include <numeric>
 
 #include "common.h"
-#include "ops.cuh"
+#include "kernels.h"
 
 namespace b200mf {
 
@@ -128,27 +128,28 @@ void compute_shape_1d(int p, Shape1D &out) {
   for (int i = 0; i < n; ++i) out.nodes[i] = (double)nd[i];
 }
 
-static int upload_shape_constants() {
-  static bool done = false;
-  if (done) return 0;
+// host copies of the 1-D matrices every kernel translation unit uploads into its own __constant__ bank (launch.cuh)
+void shape_tables(const double **hd_out, const float **hf_out) {
   static double hd[MAXN + 1][2][MAXN * MAXN];
   static float hf[MAXN + 1][2][MAXN * MAXN];
-  memset(hd, 0, sizeof hd);
-  for (int N = 2; N <= MAXN; ++N) {
-    Shape1D s;
-    compute_shape_1d(N - 1, s);
-    for (int i = 0; i < N * N; ++i) {
-      hd[N][0][i] = s.S[i];
-      hd[N][1][i] = s.C[i];
+  static bool done = false;
+  if (!done) {
+    memset(hd, 0, sizeof hd);
+    for (int N = 2; N <= MAXN; ++N) {
+      Shape1D s;
+      compute_shape_1d(N - 1, s);
+      for (int i = 0; i < N * N; ++i) {
+        hd[N][0][i] = s.S[i];
+        hd[N][1][i] = s.C[i];
+      }
     }
+    for (int N = 0; N <= MAXN; ++N)
+      for (int m = 0; m < 2; ++m)
+        for (int i = 0; i < MAXN * MAXN; ++i) hf[N][m][i] = (float)hd[N][m][i];
+    done = true;
   }
-  for (int N = 0; N <= MAXN; ++N)
-    for (int m = 0; m < 2; ++m)
-      for (int i = 0; i < MAXN * MAXN; ++i) hf[N][m][i] = (float)hd[N][m][i];
-  B2_CUDA(cudaMemcpyToSymbol(c_shape_d, hd, sizeof hd));
-  B2_CUDA(cudaMemcpyToSymbol(c_shape_f, hf, sizeof hf));
-  done = true;
-  return 0;
+  *hd_out = &hd[0][0][0];
+  *hf_out = &hf[0][0][0];
 }
 
 // ---------------------------------------------------------------------------
@@ -301,90 +302,6 @@ __global__ void jacobi_kernel(int64_t n, T *__restrict__ dst, const T *__restric
 
 static inline unsigned nblocks(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
-// ---------------------------------------------------------------------------
-// launch of the templated cell loop
-// tuning: groups (warps) per block and the __launch_bounds__ minimum blocks per SM (register cap)
-static int g_tune_gpb = 0, g_tune_minb = 0;  // 0 = default; set by b200mf_set_tuning (experiments)
-
-template <typename T, int N, class Op, bool DIAG, int GPB, int MINB>
-static int launch_variant(const b200mf_ctx *ctx, const T *src, T *dst, const typename Op::Args &oa) {
-  using Ly = Layout<N, Op::NC, sizeof(T) / 4>;
-  auto kern = cell_loop_kernel<T, N, Op, GPB, DIAG, MINB>;
-  const size_t smem = (size_t)GPB * KernelSmem<T, N, Op>::GROUP_BYTES;
-  static int occ = 0;  // per instantiation
-  if (occ == 0) {
-    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // occupancy the registers allow with the largest carve-out, then give shared memory exactly what
-    // those blocks need and leave the rest to L1 (the DoF gather re-reads sectors: L1 hits matter)
-    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    int occ_max = 0;
-    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_max, kern, Ly::TPG * GPB, smem));
-    if (occ_max < 1) return set_error(B200MF_ERR_CUDA, "cell kernel does not fit on an SM (N=%d, %zu B shared)", N, smem);
-    int pct = (int)((occ_max * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
-    pct = std::min(100, std::max(1, pct));
-    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Ly::TPG * GPB, smem));
-    if (occ < 1) occ = occ_max;
-  }
-  CellArgs<T> A;
-  A.n_groups = ctx->n_groups;
-  A.nidx = ctx->nidx;
-  A.src = src;
-  A.dst = dst;
-  A.cstride = ctx->cstride;
-  const int64_t want = (ctx->n_groups + GPB - 1) / GPB;
-  const int64_t cap = (int64_t)ctx->sm_count * occ;
-  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min(want, cap));
-  kern<<<grid, Ly::TPG * GPB, smem, ctx->stream>>>(A, oa);
-  B2_LAUNCHED();
-  return 0;
-}
-
-template <typename T, int N, class Op, bool DIAG = false>
-static int launch_cell_loop(const b200mf_ctx *ctx, const T *src, T *dst, const typename Op::Args &oa) {
-  using Ly = Layout<N, Op::NC, sizeof(T) / 4>;
-  if constexpr (!Ly::WARP_MODE) {
-    return launch_variant<T, N, Op, DIAG, 1, 1>(ctx, src, dst, oa);
-  } else {
-#ifdef B2_EXPERIMENT
-    if constexpr (!DIAG && Op::INTEGRATE && Op::NC == 3 && std::is_same<T, double>::value && N >= 3 && N <= 5) {
-      const int key = g_tune_gpb * 10 + g_tune_minb;
-      switch (key) {
-        case 11: return launch_variant<T, N, Op, DIAG, 1, 1>(ctx, src, dst, oa);
-        case 31: return launch_variant<T, N, Op, DIAG, 3, 1>(ctx, src, dst, oa);
-        case 61: return launch_variant<T, N, Op, DIAG, 6, 1>(ctx, src, dst, oa);
-        case 21: return launch_variant<T, N, Op, DIAG, 2, 1>(ctx, src, dst, oa);
-        case 26: return launch_variant<T, N, Op, DIAG, 2, 6>(ctx, src, dst, oa);
-        case 41: return launch_variant<T, N, Op, DIAG, 4, 1>(ctx, src, dst, oa);
-        case 43: return launch_variant<T, N, Op, DIAG, 4, 3>(ctx, src, dst, oa);
-        case 81: return launch_variant<T, N, Op, DIAG, 8, 1>(ctx, src, dst, oa);
-        default: break;
-      }
-    }
-#endif
-    // warps per block from the B200 sweep (profiles/r01_sweep_*.jsonl): shared memory (cell buffers + staged
-    // table) bounds the resident warps, small blocks pack an SM best; N = 5 prefers 4-warp blocks
-    constexpr int GPB = (N == 5) ? 4 : (N == 2 ? 4 : 1);
-    return launch_variant<T, N, Op, DIAG, GPB, 1>(ctx, src, dst, oa);
-  }
-}
-
-#define B2_DISPATCH_N(N_, T_, ...)                                                  \
-  switch (N_) {                                                                      \
-    case 2: { constexpr int N = 2; using T = T_; __VA_ARGS__; } break;                      \
-    case 3: { constexpr int N = 3; using T = T_; __VA_ARGS__; } break;                      \
-    case 4: { constexpr int N = 4; using T = T_; __VA_ARGS__; } break;                      \
-    case 5: { constexpr int N = 5; using T = T_; __VA_ARGS__; } break;                      \
-    case 6: { constexpr int N = 6; using T = T_; __VA_ARGS__; } break;                      \
-    case 7: { constexpr int N = 7; using T = T_; __VA_ARGS__; } break;                      \
-    default: rc = set_error(B200MF_ERR_ARG, "unsupported degree %d", (N_) - 1);      \
-  }
-#define B2_DISPATCH(ctx_, ...)                                                      \
-  do {                                                                               \
-    if ((ctx_)->dtype == B200MF_F64) { B2_DISPATCH_N((ctx_)->N, double, __VA_ARGS__) }      \
-    else { B2_DISPATCH_N((ctx_)->N, float, __VA_ARGS__) }                                   \
-  } while (0)
-
 static inline size_t esize(const b200mf_ctx *c) { return c->dtype == B200MF_F64 ? 8 : 4; }
 // elements between groups of a [group][NF][N][L] table (== Layout::table_stride)
 static inline int64_t table_stride_rt(const b200mf_ctx *c, int NF) {
@@ -400,11 +317,6 @@ using namespace b200mf;
 extern "C" const char *b200mf_last_error(void) { return g_last_error.c_str(); }
 extern "C" int64_t b200mf_launch_count(void) { return g_launches.load(); }
 extern "C" int b200mf_version(void) { return 100; }
-extern "C" int b200mf_set_tuning(int groups_per_block, int min_blocks_per_sm) {
-  g_tune_gpb = groups_per_block;
-  g_tune_minb = min_blocks_per_sm;
-  return 0;
-}
 
 // ===========================================================================
 // ABI: context
@@ -421,7 +333,6 @@ extern "C" int b200mf_ctx_create(b200mf_ctx **out, const b200mf_ctx_desc *d) {
   if (d->n_cells < 0 || d->n_dofs <= 0 || d->n_owned < 0 || d->n_owned > d->n_dofs) return set_error(B200MF_ERR_ARG, "bad sizes");
   if (!d->vertices && !(d->inverse_jacobian && d->jxw)) return set_error(B200MF_ERR_ARG, "need vertices or inverse_jacobian+jxw");
   if (d->n_constrained > 0 && !d->constrained_dofs) return set_error(B200MF_ERR_ARG, "constrained_dofs is null");
-  B2_TRY(upload_shape_constants());
 
   std::unique_ptr<b200mf_ctx> c(new b200mf_ctx());
   memset(c.get(), 0, sizeof(b200mf_ctx));
@@ -714,10 +625,14 @@ extern "C" int b200mf_vec_download_f64(b200mf_ctx *c, double *host, const void *
 struct b200mf_nh {
   b200mf_ctx *ctx;
   b200mf_material mat[2];
-  int caching;       // requested level (API parity); the device table is the tensor2 layout
+  int caching;  // requested MF caching level
+  int variant;  // NHVariant the kernels run
   bool initialized, cached, have_diag;
-  void *qd;          // T [group][NF][N][L]
-  size_t qd_bytes;
+  void *qd;   // staged table of the deformed-frame variants, T [group][NF][N][L]
+  void *qd2;  // scalar_referential: cached_scalar table
+  void *big;  // tensor4 / tensor4_ns tables
+  void *pos;  // scalar_referential: cell-local displacement
+  size_t table_bytes;
   unsigned long long *n_bad;
   void *diag, *inv_diag;
   void *tmp_src, *tmp_dst;  // for the *_host entry points
@@ -733,22 +648,36 @@ static void derived(const b200mf_material &m, double &kappa, double &c_1, double
 extern "C" int b200mf_nh_create(b200mf_nh **out, b200mf_ctx *ctx, const b200mf_material *mat, const b200mf_material *incl) {
   if (!out || !ctx || !mat) return set_error(B200MF_ERR_ARG, "null argument");
   if (ctx->NC != 3) return set_error(B200MF_ERR_ARG, "NeoHookOperator needs a 3-component context");
-  if (mat->formulation != 0 && mat->formulation != 1) return set_error(B200MF_ERR_ARG, "formulation must be 0 or 1");
-  if (!(mat->nu < 0.5 && mat->nu >= -1.0)) return set_error(B200MF_ERR_ARG, "Poisson ratio outside [-1,0.5) (material.h:88-89)");
+  const b200mf_material *ms[2] = {mat, incl ? incl : mat};
+  for (const b200mf_material *m : ms) {
+    if (m->formulation != 0 && m->formulation != 1) return set_error(B200MF_ERR_ARG, "Unknown material formulation");  // :405-406
+    if (!(m->nu < 0.5 && m->nu >= -1.0)) return set_error(B200MF_ERR_ARG, "Poisson ratio outside [-1,0.5) (material.h:88-89)");
+  }
+  if (ms[0]->formulation != ms[1]->formulation)
+    return set_error(B200MF_ERR_ARG, "material and material_inclusion must use the same formulation");
   std::unique_ptr<b200mf_nh> op(new b200mf_nh());
   memset(op.get(), 0, sizeof(b200mf_nh));
   op->ctx = ctx;
-  op->mat[0] = *mat;
-  op->mat[1] = incl ? *incl : *mat;
+  op->mat[0] = *ms[0];
+  op->mat[1] = *ms[1];
   op->caching = -1;
   B2_CUDA(cudaMalloc(&op->n_bad, sizeof(unsigned long long)));
   *out = op.release();
   return 0;
 }
 
+static void nh_free_tables(b200mf_nh *op) {
+  cudaFree(op->qd);
+  cudaFree(op->qd2);
+  cudaFree(op->big);
+  cudaFree(op->pos);
+  op->qd = op->qd2 = op->big = op->pos = nullptr;
+  op->table_bytes = 0;
+}
+
 extern "C" int b200mf_nh_destroy(b200mf_nh *op) {
   if (!op) return 0;
-  cudaFree(op->qd);
+  nh_free_tables(op);
   cudaFree(op->n_bad);
   cudaFree(op->diag);
   cudaFree(op->inv_diag);
@@ -763,20 +692,77 @@ extern "C" int b200mf_nh_initialize(b200mf_nh *op, int caching) {
   if (caching < B200MF_CACHE_SCALAR_REFERENTIAL || caching > B200MF_CACHE_TENSOR4_NS)
     return set_error(B200MF_ERR_ARG, "Unknown caching");  // mf_nh_operator.h:385
   if (op->mat[0].formulation == 0 && caching != B200MF_CACHE_TENSOR2)
-    return set_error(B200MF_ERR_ARG, "formulation 0 requires tensor2 caching (mf_nh_operator.h:419-424)");
-  if (caching != B200MF_CACHE_TENSOR2 || op->mat[0].formulation != 1)
-    return set_error(B200MF_ERR_ARG, "caching level %d / formulation %d not built yet", caching, op->mat[0].formulation);
+    return set_error(B200MF_ERR_ARG, "formulation 0 requires tensor2 caching (mf_nh_operator.h:421, 706)");
   b200mf_ctx *c = op->ctx;
   op->caching = caching;
-  const size_t nel = (size_t)c->n_groups * table_stride_rt(c, QF_TENSOR2_COUNT);
-  if (op->qd) cudaFree(op->qd);
-  op->qd_bytes = nel * esize(c);
-  B2_CUDA(cudaMalloc(&op->qd, op->qd_bytes));
-  B2_CUDA(cudaMemsetAsync(op->qd, 0, op->qd_bytes, c->stream));
+  op->variant = op->mat[0].formulation == 0            ? NHV_FORM0
+                : caching == B200MF_CACHE_TENSOR2      ? NHV_TENSOR2
+                : caching == B200MF_CACHE_TENSOR4      ? NHV_TENSOR4
+                : caching == B200MF_CACHE_TENSOR4_NS   ? NHV_TENSOR4_NS
+                                                       : NHV_SCALAR_REF;
+  nh_free_tables(op);
+  auto alloc = [&](void **p, int nf) -> int {
+    const size_t bytes = (size_t)c->n_groups * table_stride_rt(c, nf) * esize(c);
+    B2_CUDA(cudaMalloc(p, std::max<size_t>(bytes, 16)));
+    B2_CUDA(cudaMemsetAsync(*p, 0, bytes, c->stream));
+    op->table_bytes += bytes;
+    return 0;
+  };
+  const int v = op->variant;
+  if (nhv_deformed(v)) B2_TRY(alloc(&op->qd, nhv_staged_fields(v)));
+  if (nhv_big_fields(v)) B2_TRY(alloc(&op->big, nhv_big_fields(v)));
+  if (v == NHV_SCALAR_REF) {
+    B2_TRY(alloc(&op->qd2, 1));
+    B2_TRY(alloc(&op->pos, 3));
+  }
   op->initialized = true;
   op->cached = false;
   op->have_diag = false;
   return 0;
+}
+
+template <typename T>
+static NHArgs<T> nh_args(const b200mf_nh *op) {
+  const b200mf_ctx *c = op->ctx;
+  NHArgs<T> oa;
+  oa.stage = (const T *)(nhv_deformed(op->variant) ? op->qd : c->mref);
+  oa.stage2 = (const T *)op->qd2;
+  oa.big = (const T *)op->big;
+  oa.pos = (const T *)op->pos;
+  oa.matid = c->matid;
+  oa.n_cells = c->n_cells;
+  for (int m = 0; m < 2; ++m) {
+    double kappa, c_1, lambda, ra;
+    derived(op->mat[m], kappa, c_1, lambda, ra);
+    oa.mu[m] = (T)op->mat[m].mu;
+    oa.lambda[m] = (T)lambda;
+    oa.rho_alpha[m] = (T)ra;
+    oa.kappa[m] = (T)kappa;
+    oa.c_1[m] = (T)c_1;
+  }
+  return oa;
+}
+
+template <typename T>
+static int nh_cache_t(b200mf_nh *op, const void *disp) {
+  b200mf_ctx *c = op->ctx;
+  NHCacheArgs<T> oa;
+  oa.stage = (const T *)c->mref;
+  oa.stage2 = nullptr;
+  oa.qd = (T *)op->qd;
+  oa.qd2 = (T *)op->qd2;
+  oa.big = (T *)op->big;
+  oa.pos = (T *)op->pos;
+  oa.matid = c->matid;
+  oa.n_cells = c->n_cells;
+  for (int m = 0; m < 2; ++m) {
+    double kappa, c_1, lambda, ra;
+    derived(op->mat[m], kappa, c_1, lambda, ra);
+    oa.mu[m] = (T)op->mat[m].mu;
+    oa.lambda[m] = (T)lambda;
+  }
+  oa.n_bad = op->n_bad;
+  return run_nh_cache<T>(c, op->variant, (const T *)disp, oa);
 }
 
 extern "C" int b200mf_nh_cache(b200mf_nh *op, const void *disp, int64_t *n_bad_out) {
@@ -785,24 +771,7 @@ extern "C" int b200mf_nh_cache(b200mf_nh *op, const void *disp, int64_t *n_bad_o
   b200mf_ctx *c = op->ctx;
   B2_CUDA(cudaMemsetAsync(op->n_bad, 0, sizeof(unsigned long long), c->stream));
   B2_TRY(update_ghost_values(c, const_cast<void *>(disp)));  // cache() reads ghosted displacement
-  double kappa[2], c_1[2], lambda[2], ra[2];
-  for (int m = 0; m < 2; ++m) derived(op->mat[m], kappa[m], c_1[m], lambda[m], ra[m]);
-  int rc = 0;
-  B2_DISPATCH(c, {
-    using Op = NHCacheTensor2Op<T, N>;
-    typename Op::Args oa;
-    oa.stage = (const T *)c->mref;
-    oa.stage2 = nullptr;
-    oa.qd = (T *)op->qd;
-    oa.matid = c->matid;
-    oa.n_cells = c->n_cells;
-    for (int m = 0; m < 2; ++m) {
-      oa.mu[m] = (T)op->mat[m].mu;
-      oa.lambda[m] = (T)lambda[m];
-    }
-    oa.n_bad = op->n_bad;
-    rc = launch_cell_loop<T, N, Op>(c, (const T *)disp, (T *)nullptr, oa);
-  });
+  int rc = c->dtype == B200MF_F64 ? nh_cache_t<double>(op, disp) : nh_cache_t<float>(op, disp);
   B2_TRY(rc);
   unsigned long long bad = 0;
   B2_CUDA(cudaMemcpyAsync(&bad, op->n_bad, sizeof bad, cudaMemcpyDeviceToHost, c->stream));
@@ -828,6 +797,23 @@ extern "C" int b200mf_nh_cache_host(b200mf_nh *op, const double *disp, int64_t *
   return b200mf_nh_cache(op, op->tmp_src, n_bad_out);
 }
 
+template <typename T>
+static int constrained_identity(b200mf_ctx *c, void *dst, const void *src) {  // :623-624
+  if (c->n_constrained) {
+    constrained_identity_kernel<T><<<nblocks(c->n_constrained, 256), 256, 0, c->stream>>>(c->n_constrained, c->constrained, (T *)dst, (const T *)src);
+    B2_LAUNCHED();
+  }
+  return 0;
+}
+
+template <typename T>
+static int nh_apply_t(b200mf_nh *op, void *dst, const void *src) {
+  b200mf_ctx *c = op->ctx;
+  B2_TRY(run_nh<T>(c, op->variant, (const T *)src, (T *)dst, nh_args<T>(op), 0, c->n_groups, c->stream));
+  B2_TRY(compress_add(c, dst));  // :620
+  return constrained_identity<T>(c, dst, src);
+}
+
 static int nh_apply(b200mf_nh *op, void *dst, const void *src, bool zero_dst) {
   if (!op || !dst || !src) return set_error(B200MF_ERR_ARG, "null argument");
   if (dst == src) return set_error(B200MF_ERR_ARG, "vmult: dst aliases src");
@@ -835,27 +821,7 @@ static int nh_apply(b200mf_nh *op, void *dst, const void *src, bool zero_dst) {
   b200mf_ctx *c = op->ctx;
   if (zero_dst) B2_CUDA(cudaMemsetAsync(dst, 0, c->n_int * esize(c), c->stream));  // vmult: dst = 0, :548
   B2_TRY(update_ghost_values(c, const_cast<void *>(src)));                          // :610
-  double kappa[2], c_1[2], lambda[2], ra[2];
-  for (int m = 0; m < 2; ++m) derived(op->mat[m], kappa[m], c_1[m], lambda[m], ra[m]);
-  int rc = 0;
-  B2_DISPATCH(c, {
-    using Op = NHTensor2Op<T, N>;
-    typename Op::Args oa;
-    oa.stage = (const T *)op->qd;
-    oa.stage2 = nullptr;
-    oa.matid = c->matid;
-    oa.n_cells = c->n_cells;
-    for (int m = 0; m < 2; ++m) {
-      oa.lam2[m] = (T)(2.0 * lambda[m]);
-      oa.rho_alpha[m] = (T)ra[m];
-    }
-    rc = launch_cell_loop<T, N, Op>(c, (const T *)src, (T *)dst, oa);
-    if (rc == 0) rc = compress_add(c, dst);  // :620
-    if (rc == 0 && c->n_constrained) {
-      constrained_identity_kernel<T><<<nblocks(c->n_constrained, 256), 256, 0, c->stream>>>(c->n_constrained, c->constrained, (T *)dst, (const T *)src);
-      g_launches.fetch_add(1);
-    }
-  });
+  int rc = c->dtype == B200MF_F64 ? nh_apply_t<double>(op, dst, src) : nh_apply_t<float>(op, dst, src);
   B2_TRY(rc);
   B2_CUDA(cudaGetLastError());
   return 0;
@@ -875,21 +841,35 @@ extern "C" int b200mf_nh_vmult_host(b200mf_nh *op, double *dst, const double *sr
 }
 
 extern "C" int64_t b200mf_nh_m(const b200mf_nh *op) { return op ? op->ctx->n_dofs : -1; }
-extern "C" size_t b200mf_nh_memory_consumption(const b200mf_nh *op) { return op ? op->qd_bytes : 0; }
-extern "C" int b200mf_nh_n_qfields(const b200mf_nh *op) { return op && op->initialized ? QF_TENSOR2_COUNT : 0; }
+extern "C" size_t b200mf_nh_memory_consumption(const b200mf_nh *op) { return op ? op->table_bytes : 0; }
+// number of fields b200mf_nh_qdata_host can return: staged table (deformed variants) or c (scalar_referential), then the big table
+extern "C" int b200mf_nh_n_qfields(const b200mf_nh *op) {
+  if (!op || !op->initialized) return 0;
+  const int v = op->variant;
+  return (nhv_deformed(v) ? nhv_staged_fields(v) : v == NHV_SCALAR_REF ? 1 : 0) + nhv_big_fields(v);
+}
 
 extern "C" int b200mf_nh_qdata_host(b200mf_nh *op, int field, double *out) {
   if (!op || !out) return set_error(B200MF_ERR_ARG, "null argument");
   if (!op->cached) return set_error(B200MF_ERR_STATE, "qdata before cache()");
-  if (field < 0 || field >= QF_TENSOR2_COUNT) return set_error(B200MF_ERR_ARG, "bad field");
+  if (field < 0 || field >= b200mf_nh_n_qfields(op)) return set_error(B200MF_ERR_ARG, "bad field");
   b200mf_ctx *c = op->ctx;
+  const int v = op->variant;
+  const int ns = nhv_deformed(v) ? nhv_staged_fields(v) : v == NHV_SCALAR_REF ? 1 : 0;
+  const void *tab = nhv_deformed(v) ? op->qd : op->qd2;
+  int nf = ns;
+  if (field >= ns) {
+    tab = op->big;
+    nf = nhv_big_fields(v);
+    field -= ns;
+  }
   const int64_t n = c->n_cells * c->N * c->N * c->N;
   double *tmp = nullptr;
   B2_CUDA(cudaMalloc(&tmp, n * sizeof(double)));
   if (c->dtype == B200MF_F64)
-    field_from_group_layout_kernel<double><<<nblocks(n, 256), 256, 0, c->stream>>>(c->N, c->cpg, c->L, table_stride_rt(c, QF_TENSOR2_COUNT), field, c->n_cells, (const double *)op->qd, tmp);
+    field_from_group_layout_kernel<double><<<nblocks(n, 256), 256, 0, c->stream>>>(c->N, c->cpg, c->L, table_stride_rt(c, nf), field, c->n_cells, (const double *)tab, tmp);
   else
-    field_from_group_layout_kernel<float><<<nblocks(n, 256), 256, 0, c->stream>>>(c->N, c->cpg, c->L, table_stride_rt(c, QF_TENSOR2_COUNT), field, c->n_cells, (const float *)op->qd, tmp);
+    field_from_group_layout_kernel<float><<<nblocks(n, 256), 256, 0, c->stream>>>(c->N, c->cpg, c->L, table_stride_rt(c, nf), field, c->n_cells, (const float *)tab, tmp);
   B2_LAUNCHED();
   B2_CUDA(cudaMemcpyAsync(out, tmp, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   B2_CUDA(cudaStreamSynchronize(c->stream));
@@ -937,23 +917,9 @@ extern "C" int b200mf_nh_compute_diagonal(b200mf_nh *op) {
     B2_CUDA(cudaMalloc(&op->inv_diag, c->n_int * esize(c)));
     B2_CUDA(cudaMemsetAsync(op->inv_diag, 0, c->n_int * esize(c), c->stream));
   }
-  double kappa[2], c_1[2], lambda[2], ra[2];
-  for (int m = 0; m < 2; ++m) derived(op->mat[m], kappa[m], c_1[m], lambda[m], ra[m]);
   int rc0 = finish_diagonal(c, op->diag, op->inv_diag, op->n_bad, [&]() {
-    int rc = 0;
-    B2_DISPATCH(c, {
-      using Op = NHTensor2Op<T, N>;
-      typename Op::Args oa;
-      oa.stage = (const T *)op->qd;
-      oa.stage2 = nullptr;
-      oa.matid = c->matid;
-      oa.n_cells = c->n_cells;
-      for (int m = 0; m < 2; ++m) {
-        oa.lam2[m] = (T)(2.0 * lambda[m]);
-        oa.rho_alpha[m] = (T)ra[m];
-      }
-      rc = launch_cell_loop<T, N, Op, true>(c, (const T *)nullptr, (T *)op->diag, oa);
-    });
+    int rc = c->dtype == B200MF_F64 ? run_nh_diag<double>(c, op->variant, (double *)op->diag, nh_args<double>(op))
+                                    : run_nh_diag<float>(c, op->variant, (float *)op->diag, nh_args<float>(op));
     return rc;
   });
   B2_TRY(rc0);
@@ -1067,26 +1033,29 @@ extern "C" int b200mf_laplace_set_delta_t(b200mf_laplace *op, double dt) {
   return 0;
 }
 
+template <typename T>
+static LaplaceArgs<T> laplace_args(const b200mf_laplace *op) {
+  LaplaceArgs<T> oa;
+  oa.stage = (const T *)op->ctx->mref;
+  oa.stage2 = (const T *)op->coef;
+  oa.delta_t = (T)op->delta_t;
+  return oa;
+}
+template <typename T>
+static int laplace_apply_t(b200mf_laplace *op, void *dst, const void *src) {
+  b200mf_ctx *c = op->ctx;
+  B2_TRY(run_laplace<T>(c, false, (const T *)src, (T *)dst, laplace_args<T>(op), 0, c->n_groups, c->stream));
+  B2_TRY(compress_add(c, dst));
+  return constrained_identity<T>(c, dst, src);
+}
+
 static int laplace_apply(b200mf_laplace *op, void *dst, const void *src, bool zero_dst) {
   if (!op || !dst || !src) return set_error(B200MF_ERR_ARG, "null argument");
   if (dst == src) return set_error(B200MF_ERR_ARG, "vmult: dst aliases src");
   b200mf_ctx *c = op->ctx;
   if (zero_dst) B2_CUDA(cudaMemsetAsync(dst, 0, c->n_int * esize(c), c->stream));
   B2_TRY(update_ghost_values(c, const_cast<void *>(src)));
-  int rc = 0;
-  B2_DISPATCH(c, {
-    using Op = LaplaceOp<T, N>;
-    typename Op::Args oa;
-    oa.stage = (const T *)c->mref;
-    oa.stage2 = (const T *)op->coef;
-    oa.delta_t = (T)op->delta_t;
-    rc = launch_cell_loop<T, N, Op>(c, (const T *)src, (T *)dst, oa);
-    if (rc == 0) rc = compress_add(c, dst);
-    if (rc == 0 && c->n_constrained) {
-      constrained_identity_kernel<T><<<nblocks(c->n_constrained, 256), 256, 0, c->stream>>>(c->n_constrained, c->constrained, (T *)dst, (const T *)src);
-      g_launches.fetch_add(1);
-    }
-  });
+  int rc = c->dtype == B200MF_F64 ? laplace_apply_t<double>(op, dst, src) : laplace_apply_t<float>(op, dst, src);
   B2_TRY(rc);
   B2_CUDA(cudaGetLastError());
   return 0;
@@ -1116,15 +1085,8 @@ extern "C" int b200mf_laplace_compute_diagonal(b200mf_laplace *op) {
     B2_CUDA(cudaMalloc(&op->n_bad, sizeof(unsigned long long)));
   }
   int rc0 = finish_diagonal(c, op->diag, op->inv_diag, op->n_bad, [&]() {
-    int rc = 0;
-    B2_DISPATCH(c, {
-      using Op = LaplaceOp<T, N>;
-      typename Op::Args oa;
-      oa.stage = (const T *)c->mref;
-      oa.stage2 = (const T *)op->coef;
-      oa.delta_t = (T)op->delta_t;
-      rc = launch_cell_loop<T, N, Op, true>(c, (const T *)nullptr, (T *)op->diag, oa);
-    });
+    int rc = c->dtype == B200MF_F64 ? run_laplace<double>(c, true, nullptr, (double *)op->diag, laplace_args<double>(op), 0, c->n_groups, c->stream)
+                                    : run_laplace<float>(c, true, nullptr, (float *)op->diag, laplace_args<float>(op), 0, c->n_groups, c->stream);
     return rc;
   });
   B2_TRY(rc0);

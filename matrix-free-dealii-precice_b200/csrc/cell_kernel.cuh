@@ -138,7 +138,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 
 template <typename T>
 struct CellArgs {
-  int64_t n_groups;
+  int64_t group_begin, n_groups;  // groups [group_begin, n_groups)
   const uint32_t *nidx;  // [group][k][lane], flags in bits 29..31
   const T *src;
   T *dst;
@@ -177,9 +177,10 @@ __device__ __forceinline__ void sweep_C(const T (&in)[N], T (&out)[N]) {
 //   struct Args { const T *stage, *stage2; ... }   stage2 may be null at run time
 //   struct CellState;                    per-thread per-cell state (e.g. material constants)
 //   static void cell_begin(args, cell, valid, CellState&)
-//   static void quad(args, state, active, qs, qs2, group, iq, lane, v[NC], G[NC][3], ov[NC], oG[NC][3])
+//   static void quad(args, state, active, qs, qs2, scr, group, iq, lane, v[NC], G[NC][3], ov[NC], oG[NC][3])
 //       qs / qs2: shared-memory copies of this group's tables, field f of q-point (iq, lane) at
-//       qs[(f*N + iq)*L + lane]
+//       qs[(f*N + iq)*L + lane]; scr: NF_SCRATCH fields of per-group scratch in the same layout
+//   static constexpr bool PRE, STORE_DOFS; int NF_SCRATCH  (see the pass loop)
 //
 // DIAG = true turns the loop into MatrixFreeTools::compute_diagonal: the cell
 // operator is applied to every local unit vector and entry i of the result is kept.
@@ -189,7 +190,8 @@ struct KernelSmem {
   static constexpr size_t BUF_BYTES = round_up((size_t)Ly::GROUP_ELEMS * sizeof(T), 16);
   static constexpr size_t ST1_BYTES = Ly::table_stride(Op::NF_IN) * sizeof(T);
   static constexpr size_t ST2_BYTES = Op::NF_IN2 ? Ly::table_stride(Op::NF_IN2) * sizeof(T) : 0;
-  static constexpr size_t GROUP_BYTES = BUF_BYTES + ST1_BYTES + ST2_BYTES + 16;  // + mbarrier
+  static constexpr size_t SCR_BYTES = Op::NF_SCRATCH ? Ly::table_stride(Op::NF_SCRATCH) * sizeof(T) : 0;  // pre-pass -> main pass
+  static constexpr size_t GROUP_BYTES = BUF_BYTES + ST1_BYTES + ST2_BYTES + SCR_BYTES + 16;  // + mbarrier
 };
 
 template <typename T, int N, class Op, int GPB, bool DIAG = false, int MINB = 1>
@@ -218,7 +220,8 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
   T *bufC = bufB + NC * CSTR;
   T *qs = reinterpret_cast<T *>(gbase + KS_::BUF_BYTES);
   T *qs2 = reinterpret_cast<T *>(gbase + KS_::BUF_BYTES + KS_::ST1_BYTES);
-  uint64_t *mbar = reinterpret_cast<uint64_t *>(gbase + KS_::BUF_BYTES + KS_::ST1_BYTES + KS_::ST2_BYTES);
+  T *scr = reinterpret_cast<T *>(gbase + KS_::BUF_BYTES + KS_::ST1_BYTES + KS_::ST2_BYTES);
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(gbase + KS_::BUF_BYTES + KS_::ST1_BYTES + KS_::ST2_BYTES + KS_::SCR_BYTES);
 
   if (lane == 0) mbar_init(mbar, 1);
   group_sync<WM>();
@@ -264,7 +267,7 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
   const int oX = b * KS + a * JS;  // + i    : (j=a, k=b) column along x
 
   const int64_t gstep = (int64_t)gridDim.x * GPB;
-  int64_t group = (int64_t)blockIdx.x * GPB + gib;
+  int64_t group = A.group_begin + (int64_t)blockIdx.x * GPB + gib;
   unsigned parity = 0;
   uint32_t nid[N], nid_next[N];
   T u[NC][N];
@@ -289,9 +292,14 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
 #pragma unroll
         for (int k = 0; k < N; ++k) dacc[c][k] = T(0);
     }
+    if constexpr (Op::STORE_DOFS) Op::store_dofs(oa, group, lane, active, u);
     constexpr int NPASS = DIAG ? NC * Ly::N3 : 1;
+    // Op::PRE: one extra evaluation-only pass (pass -1) over a second cell-local field (Op::load_pre) whose
+    // quadrature-point results (Op::quad_pre) stay in shared memory for the main pass(es)
+    constexpr int FIRST = Op::PRE ? -1 : 0;
 #pragma unroll 1
-    for (int pass = 0; pass < NPASS; ++pass) {
+    for (int pass = FIRST; pass < NPASS; ++pass) {
+      const bool pre = Op::PRE && pass < 0;
       const int pc = pass / Ly::N3, pk = (pass / N2) % N, pt = pass % N2;  // unit vector (component, k, column)
       // ---- phase 1 (Z orientation): z sweep of the gathered values ----------
       if (DIAG) {
@@ -303,12 +311,18 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         T o[N];
-        sweep_S<T, N, false>(u[c], o);
+        if (pre) {
+          T up[N];
+          Op::load_pre(oa, group, lane, active, c, up);
+          sweep_S<T, N, false>(up, o);
+        } else {
+          sweep_S<T, N, false>(u[c], o);
+        }
 #pragma unroll
         for (int k = 0; k < N; ++k)
           if (active) bufA[c * CSTR + k * KS + oZ] = o[k];
       }
-      if (pass == 0 && has_next) load_nid(gnext, nid_next);
+      if (pass == FIRST && has_next) load_nid(gnext, nid_next);
       group_sync<WM>();
       // ---- phase 2 (Y orientation) -------------------------------------------
 #pragma unroll
@@ -335,7 +349,7 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
         for (int i = 0; i < N; ++i)
           if (active) bufA[c * CSTR + oX + i] = val[c][i];
       }
-      if (pass == 0) mbar_wait(mbar, parity);  // this group's tables have landed in shared memory
+      if (pass == FIRST) mbar_wait(mbar, parity);  // this group's tables have landed in shared memory
       group_sync<WM>();
       // ---- phase 4: quadrature loop ------------------------------------------
       T acc[NC][N];
@@ -359,7 +373,11 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
           G[c][2] = gz;
           v[c] = val[c][iq];
         }
-        Op::quad(oa, st, active, qs, qs2, group, iq, lane, v, G, ov, oG);
+        if (pre) {
+          Op::quad_pre(oa, st, active, qs, scr, group, iq, lane, G);
+          continue;
+        }
+        Op::quad(oa, st, active, qs, qs2, scr, group, iq, lane, v, G, ov, oG);
         if (Op::INTEGRATE) {
 #pragma unroll
           for (int c = 0; c < NC; ++c) {
@@ -379,7 +397,7 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
           stage(gnext);
         }
       }
-      if (Op::INTEGRATE) {
+      if (Op::INTEGRATE && !pre) {
         // issue the next group's gather now; it completes under the transpose half below
         T u_next[NC][N];
         if (!DIAG && has_next) gather(nid_next, u_next);

@@ -1,0 +1,90 @@
+// Launch of the templated cell loop (included by the kernel translation units only).
+#pragma once
+#include <algorithm>
+
+#include "kernels.h"
+
+namespace b200mf {
+
+// every translation unit owns a copy of the __constant__ 1-D matrices (cell_kernel.cuh)
+static int ensure_shape_constants() {
+  static bool done = false;
+  if (done) return 0;
+  const double *hd;
+  const float *hf;
+  shape_tables(&hd, &hf);
+  B2_CUDA(cudaMemcpyToSymbol(c_shape_d, hd, sizeof(c_shape_d)));
+  B2_CUDA(cudaMemcpyToSymbol(c_shape_f, hf, sizeof(c_shape_f)));
+  done = true;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// launch of the templated cell loop
+
+template <typename T, int N, class Op, bool DIAG, int GPB, int MINB>
+static int launch_variant(const b200mf_ctx *ctx, const T *src, T *dst, const typename Op::Args &oa, int64_t g0, int64_t g1,
+                          cudaStream_t stream) {
+  using Ly = Layout<N, Op::NC, sizeof(T) / 4>;
+  auto kern = cell_loop_kernel<T, N, Op, GPB, DIAG, MINB>;
+  const size_t smem = (size_t)GPB * KernelSmem<T, N, Op>::GROUP_BYTES;
+  static int occ = 0;  // per instantiation
+  B2_TRY(ensure_shape_constants());
+  if (occ == 0) {
+    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // occupancy the registers allow with the largest carve-out, then give shared memory exactly what
+    // those blocks need and leave the rest to L1 (the DoF gather re-reads sectors: L1 hits matter)
+    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int occ_max = 0;
+    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_max, kern, Ly::TPG * GPB, smem));
+    if (occ_max < 1) return set_error(B200MF_ERR_CUDA, "cell kernel does not fit on an SM (N=%d, %zu B shared)", N, smem);
+    int pct = (int)((occ_max * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+    pct = std::min(100, std::max(1, pct));
+    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Ly::TPG * GPB, smem));
+    if (occ < 1) occ = occ_max;
+  }
+  if (g1 <= g0) return 0;
+  CellArgs<T> A;
+  A.group_begin = g0;
+  A.n_groups = g1;
+  A.nidx = ctx->nidx;
+  A.src = src;
+  A.dst = dst;
+  A.cstride = ctx->cstride;
+  const int64_t want = (g1 - g0 + GPB - 1) / GPB;
+  const int64_t cap = (int64_t)ctx->sm_count * occ;
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min(want, cap));
+  kern<<<grid, Ly::TPG * GPB, smem, stream>>>(A, oa);
+  B2_LAUNCHED();
+  return 0;
+}
+
+template <typename T, int N, class Op, bool DIAG = false>
+static int launch_cell_loop(const b200mf_ctx *ctx, const T *src, T *dst, const typename Op::Args &oa, int64_t g0 = 0, int64_t g1 = -1,
+                            cudaStream_t stream = nullptr) {
+  using Ly = Layout<N, Op::NC, sizeof(T) / 4>;
+  if (g1 < 0) g1 = ctx->n_groups;
+  if (!stream) stream = ctx->stream;
+  if constexpr (!Ly::WARP_MODE) {
+    return launch_variant<T, N, Op, DIAG, 1, 1>(ctx, src, dst, oa, g0, g1, stream);
+  } else {
+    // warps per block from the B200 sweep (profiles/r01_sweep_*.jsonl): shared memory (cell buffers + staged
+    // table) bounds the resident warps, small blocks pack an SM best; N = 5 prefers 4-warp blocks
+    constexpr int GPB = (N == 5) ? 4 : (N == 2 ? 4 : 1);
+    return launch_variant<T, N, Op, DIAG, GPB, 1>(ctx, src, dst, oa, g0, g1, stream);
+  }
+}
+
+#define B2_DISPATCH_N(N_, T_, ...)                                                  \
+  switch (N_) {                                                                      \
+    case 2: { constexpr int N = 2; using T = T_; __VA_ARGS__; } break;                      \
+    case 3: { constexpr int N = 3; using T = T_; __VA_ARGS__; } break;                      \
+    case 4: { constexpr int N = 4; using T = T_; __VA_ARGS__; } break;                      \
+    case 5: { constexpr int N = 5; using T = T_; __VA_ARGS__; } break;                      \
+    case 6: { constexpr int N = 6; using T = T_; __VA_ARGS__; } break;                      \
+    case 7: { constexpr int N = 7; using T = T_; __VA_ARGS__; } break;                      \
+    default: rc = set_error(B200MF_ERR_ARG, "unsupported degree %d", (N_) - 1);      \
+  }
+
+}  // namespace b200mf

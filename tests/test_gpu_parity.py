@@ -24,13 +24,69 @@ def oracle_nh(m, u, level="tensor2", formulation=1, mu_inclusion=None):
     return op
 
 
-def gpu_nh(m, u, dtype="f64", full_dof_map=False, inclusion=None, explicit_metric=None):
+def gpu_nh(m, u, dtype="f64", full_dof_map=False, inclusion=None, explicit_metric=None, level="tensor2", formulation=1):
     mf = MatrixFree.from_mesh(m, 3, dtype=dtype, full_dof_map=full_dof_map, explicit_metric=explicit_metric)
     op = NeoHookOperator()
-    op.set_material(mf, MATD, inclusion)
-    op.initialize(u, "tensor2")
+    mat = dict(MATD, formulation=formulation)
+    if inclusion is not None:
+        inclusion = dict(inclusion, formulation=formulation)
+    op.set_material(mf, mat, inclusion)
+    op.initialize(u, level)
     op.cache()
     return mf, op
+
+
+# (MF caching level, material formulation): every branch of do_operation_on_cell (mf_nh_operator.h:701-1015)
+VARIANTS = [("scalar_referential", 1), ("tensor2", 1), ("tensor4", 1), ("tensor4_ns", 1), ("tensor2", 0)]
+
+
+@pytest.mark.parametrize("level,formulation", VARIANTS)
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6])
+def test_nh_vmult_all_caching_levels(p, level, formulation):
+    """Every cache level / formulation against the oracle's restatement of the same branch, plus the
+    reference's own evidence that the four levels are one operator (identical goldens)."""
+    m = make_mesh(p, NCELLS[p])
+    m.material_id[1::4] = 1
+    u = displacement(m)
+    incl = dict(MATD, mu=100 * MATD["mu"])
+    src = np.random.default_rng(p).uniform(-1, 1, 3 * m.n_nodes)
+    ref = np.zeros_like(src)
+    oracle_nh(m, u, level, formulation, mu_inclusion=incl["mu"]).vmult(ref, src)
+    mf, op = gpu_nh(m, u, level=level, formulation=formulation, inclusion=incl)
+    s, d = DeviceVector(mf, src), DeviceVector(mf)
+    op.vmult(d, s)
+    out = d.download()
+    assert rel(out, ref) < TOL64
+    if formulation == 1 and level != "tensor2":
+        ref2 = np.zeros_like(src)
+        oracle_nh(m, u, "tensor2", 1, mu_inclusion=incl["mu"]).vmult(ref2, src)
+        assert rel(out, ref2) < 1e-11
+    if p <= 2:
+        op.compute_diagonal()
+        assert rel(op.get_matrix_diagonal(), oracle_nh(m, u, level, formulation, mu_inclusion=incl["mu"]).compute_diagonal()) < TOL64
+
+
+@pytest.mark.parametrize("level,formulation", VARIANTS)
+def test_nh_vmult_all_caching_levels_fp32(level, formulation):
+    p = 3
+    m = make_mesh(p, NCELLS[p])
+    u = displacement(m)
+    src = np.random.default_rng(p).uniform(-1, 1, 3 * m.n_nodes)
+    ref = np.zeros_like(src)
+    oracle_nh(m, u, level, formulation).vmult(ref, src)
+    mf, op = gpu_nh(m, u, dtype="f32", level=level, formulation=formulation)
+    out = np.zeros_like(src)
+    op.vmult(out, src)
+    assert rel(out, ref) < TOL32
+
+
+def test_formulation0_requires_tensor2():
+    m = make_mesh(2, (2, 2, 2))
+    mf = MatrixFree.from_mesh(m, 3)
+    op = NeoHookOperator()
+    op.set_material(mf, dict(MATD, formulation=0))
+    with pytest.raises(B200mfError, match="formulation 0 requires tensor2"):
+        op.initialize(displacement(m), "tensor4")
 
 
 @pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6])
