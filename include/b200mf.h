@@ -201,6 +201,95 @@ int b200mf_laplace_compute_diagonal(b200mf_laplace *op); /* :205-230 */
 int b200mf_laplace_diagonal(b200mf_laplace *op, const void **diag_dvec, const void **inv_diag_dvec);
 int b200mf_laplace_diagonal_host(b200mf_laplace *op, double *diag_host, double *inv_diag_host);
 
+b200mf_ctx *b200mf_nh_ctx(b200mf_nh *op);           /* the MatrixFree the operator was built on (data_in_use, :213) */
+b200mf_ctx *b200mf_laplace_ctx(b200mf_laplace *op); /* MatrixFreeOperators::Base::get_matrix_free */
+
+/* ------------------------------------------------------------------------
+ * Vector algebra on device vectors: the LinearAlgebra::distributed::Vector members the solvers and the
+ * Newton loop call (l2_norm mf_elasticity.h:1907, 1993, 2061; operator* / sadd / = inside SolverCG).
+ * Reductions run over owned entries and are summed over ranks.
+ * ------------------------------------------------------------------------ */
+int b200mf_vec_dot(b200mf_ctx *ctx, const void *a_dvec, const void *b_dvec, double *out);
+int b200mf_vec_l2_norm(b200mf_ctx *ctx, const void *a_dvec, double *out);
+int b200mf_vec_sadd(b200mf_ctx *ctx, void *y_dvec, double s, double a, const void *x_dvec); /* y = s*y + a*x */
+int b200mf_vec_set_zero(b200mf_ctx *ctx, void *y_dvec);
+/* copy between two contexts built on the same mesh and numbering but different number types
+ * (double system vector <-> float level vector: MGTransferMatrixFree::copy_to_mg / copy_from_mg,
+ * level displacement mf_elasticity.h:314, 920-922) */
+int b200mf_vec_convert(b200mf_ctx *dst_ctx, void *dst_dvec, b200mf_ctx *src_ctx, const void *src_dvec);
+
+/* ------------------------------------------------------------------------
+ * PreconditionChebyshev<LevelMatrixType, LevelVectorType> with the operator's inverse diagonal as inner
+ * preconditioner (mf_elasticity.h:371-372, 1149-1180; heat_transfer.h:764-788).  Algorithm: SURVEY.md A.5.
+ * ------------------------------------------------------------------------ */
+typedef struct b200mf_chebyshev b200mf_chebyshev;
+typedef struct { /* PreconditionChebyshev::AdditionalData */
+  int degree;              /* >= 1, or -1 = numbers::invalid_unsigned_int: solver mode (mf_elasticity.h:1160-1161) */
+  double smoothing_range;  /* > 1: [lambda_max/range, lambda_max]; <= 1 in solver mode: target reduction (:1158-1159) */
+  int eig_cg_n_iterations; /* CG iterations of the eigenvalue estimate; 0: use max_eigenvalue (:1162-1165, 1173-1174) */
+  double eig_cg_residual;  /* kept for interface parity (deal.II >= 9.6 runs a fixed iteration count to 1e-10) */
+  double max_eigenvalue;
+  int64_t first_global_index; /* global index of this rank's first owned DoF (deterministic start vector) */
+  int64_t n_global_dofs;      /* global problem size for its mean value; 0 = local owned size */
+} b200mf_chebyshev_data;
+int b200mf_chebyshev_create_nh(b200mf_chebyshev **cheb, b200mf_nh *op, const b200mf_chebyshev_data *data);
+int b200mf_chebyshev_create_laplace(b200mf_chebyshev **cheb, b200mf_laplace *op, const b200mf_chebyshev_data *data);
+int b200mf_chebyshev_destroy(b200mf_chebyshev *cheb);
+/* estimate_eigenvalues(): (re)runs the CG/Lanczos estimate — the reference does so for every level at every Newton
+ * step (setup_gmg(false), mf_elasticity.h:1352); out pointers may be NULL */
+int b200mf_chebyshev_estimate_eigenvalues(b200mf_chebyshev *cheb, double *min_eigenvalue, double *max_eigenvalue, int *cg_iterations,
+                                          int *degree);
+int b200mf_chebyshev_vmult(b200mf_chebyshev *cheb, void *dst_dvec, const void *src_dvec); /* zero initial guess: degree-1 matvecs */
+int b200mf_chebyshev_step(b200mf_chebyshev *cheb, void *dst_dvec, const void *src_dvec);  /* dst is the initial guess: degree matvecs */
+
+/* ------------------------------------------------------------------------
+ * MGTransferMatrixFree<3,float> between two uniformly refined levels (mf_elasticity.h:863-877, 881-929;
+ * heat_transfer.h:761-762).  children: [n_coarse_cells][8] cell indices on the fine context, child (cx,cy,cz)
+ * at cx + 2 cy + 4 cz (the order of the caller's cell arrays).
+ * ------------------------------------------------------------------------ */
+typedef struct b200mf_mg_transfer b200mf_mg_transfer;
+int b200mf_mg_transfer_create(b200mf_mg_transfer **t, b200mf_ctx *coarse, b200mf_ctx *fine, const int64_t *children);
+int b200mf_mg_transfer_destroy(b200mf_mg_transfer *t);
+int b200mf_mg_transfer_prolongate(b200mf_mg_transfer *t, void *fine_dst, const void *coarse_src);
+int b200mf_mg_transfer_prolongate_and_add(b200mf_mg_transfer *t, void *fine_dst, const void *coarse_src);
+int b200mf_mg_transfer_restrict_and_add(b200mf_mg_transfer *t, void *coarse_dst, const void *fine_src);
+int b200mf_mg_transfer_interpolate(b200mf_mg_transfer *t, void *coarse_dst, const void *fine_src); /* one step of interpolate_to_mg */
+
+/* ------------------------------------------------------------------------
+ * Multigrid<LevelVectorType> V-cycle wrapped as PreconditionMG (mf_elasticity.h:1209-1224, 1272-1276):
+ * level l > 0: Chebyshev pre-smoothing (vmult), residual, restrict_and_add, recursion, prolongate_and_add,
+ * Chebyshev post-smoothing (step); level 0: smoothers[0] applied as solver (MGCoarseGridApplySmoother, :1180).
+ * ------------------------------------------------------------------------ */
+typedef struct b200mf_mg b200mf_mg;
+int b200mf_mg_create(b200mf_mg **mg, int n_levels, b200mf_chebyshev *const *smoothers /*[n_levels]*/,
+                     b200mf_mg_transfer *const *transfers /*[n_levels-1]*/, b200mf_ctx *system_ctx);
+int b200mf_mg_destroy(b200mf_mg *mg);
+int b200mf_mg_vmult(b200mf_mg *mg, void *dst_dvec, const void *src_dvec); /* system-context vectors (copy_to_mg / copy_from_mg inside) */
+
+/* ------------------------------------------------------------------------
+ * SolverCG<VectorType> (mf_elasticity.h:2024-2051; heat_transfer.h:724-737, 810-811), SURVEY.md A.6
+ * ------------------------------------------------------------------------ */
+typedef enum { B200MF_PRECOND_NONE = 0, B200MF_PRECOND_JACOBI = 1, B200MF_PRECOND_MG = 2 } b200mf_precond;
+typedef struct b200mf_cg b200mf_cg;
+typedef struct {
+  double tolerance;    /* absolute: tol_lin * ||rhs|| (mf_elasticity.h:1993, 2018-2021) */
+  int max_iterations;  /* SolverControl max steps (:2016) */
+  int preconditioner;  /* b200mf_precond */
+  double jacobi_omega; /* PreconditionJacobi relaxation (:2028-2030) */
+  b200mf_mg *mg;       /* PreconditionMG (:2048) */
+  int x_is_zero;       /* skip the start-up matvec (the solid solver zeroes newton_update, :1990) */
+} b200mf_cg_control;
+typedef struct {
+  int iterations; /* SolverControl::last_step() */
+  double residual, initial_residual;
+  int converged;
+  double min_eigenvalue, max_eigenvalue; /* Lanczos estimates (condition-number slot, :2000-2010) */
+} b200mf_cg_result;
+int b200mf_cg_create_nh(b200mf_cg **solver, b200mf_nh *op);
+int b200mf_cg_create_laplace(b200mf_cg **solver, b200mf_laplace *op);
+int b200mf_cg_destroy(b200mf_cg *solver);
+int b200mf_cg_solve(b200mf_cg *solver, void *x_dvec, const void *b_dvec, const b200mf_cg_control *control, b200mf_cg_result *result);
+
 #ifdef __cplusplus
 }
 #endif

@@ -2,3 +2,4 @@
 the reference's operator interface over libb200mf.so).  No CPU fallback."""
 from .lib import B200mfError, load  # noqa: F401
 from .operators import Communicator, DeviceVector, LaplaceOperator, MatrixFree, NeoHookOperator  # noqa: F401
+from .solvers import MGTransferMatrixFree, PreconditionChebyshev, PreconditionMG, SolverCG  # noqa: F401,E402

@@ -39,6 +39,22 @@ class Material(C.Structure):
                 ("formulation", C.c_int)]
 
 
+class ChebyshevData(C.Structure):
+    _fields_ = [("degree", C.c_int), ("smoothing_range", C.c_double), ("eig_cg_n_iterations", C.c_int),
+                ("eig_cg_residual", C.c_double), ("max_eigenvalue", C.c_double), ("first_global_index", C.c_int64),
+                ("n_global_dofs", C.c_int64)]
+
+
+class CGControl(C.Structure):
+    _fields_ = [("tolerance", C.c_double), ("max_iterations", C.c_int), ("preconditioner", C.c_int),
+                ("jacobi_omega", C.c_double), ("mg", C.c_void_p), ("x_is_zero", C.c_int)]
+
+
+class CGResult(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("residual", C.c_double), ("initial_residual", C.c_double),
+                ("converged", C.c_int), ("min_eigenvalue", C.c_double), ("max_eigenvalue", C.c_double)]
+
+
 _lib = None
 
 _vp, _i64, _i32, _dbl = C.c_void_p, C.c_int64, C.c_int, C.c_double
@@ -97,6 +113,32 @@ SIGNATURES = {
     "b200mf_laplace_compute_diagonal": (_i32, [_vp]),
     "b200mf_laplace_diagonal": (_i32, [_vp, _PP, _PP]),
     "b200mf_laplace_diagonal_host": (_i32, [_vp, _vp, _vp]),
+    "b200mf_nh_ctx": (_vp, [_vp]),
+    "b200mf_laplace_ctx": (_vp, [_vp]),
+    "b200mf_vec_dot": (_i32, [_vp, _vp, _vp, C.POINTER(_dbl)]),
+    "b200mf_vec_l2_norm": (_i32, [_vp, _vp, C.POINTER(_dbl)]),
+    "b200mf_vec_sadd": (_i32, [_vp, _vp, _dbl, _dbl, _vp]),
+    "b200mf_vec_set_zero": (_i32, [_vp, _vp]),
+    "b200mf_vec_convert": (_i32, [_vp, _vp, _vp, _vp]),
+    "b200mf_chebyshev_create_nh": (_i32, [_PP, _vp, C.POINTER(ChebyshevData)]),
+    "b200mf_chebyshev_create_laplace": (_i32, [_PP, _vp, C.POINTER(ChebyshevData)]),
+    "b200mf_chebyshev_destroy": (_i32, [_vp]),
+    "b200mf_chebyshev_estimate_eigenvalues": (_i32, [_vp, C.POINTER(_dbl), C.POINTER(_dbl), C.POINTER(_i32), C.POINTER(_i32)]),
+    "b200mf_chebyshev_vmult": (_i32, [_vp, _vp, _vp]),
+    "b200mf_chebyshev_step": (_i32, [_vp, _vp, _vp]),
+    "b200mf_mg_transfer_create": (_i32, [_PP, _vp, _vp, _vp]),
+    "b200mf_mg_transfer_destroy": (_i32, [_vp]),
+    "b200mf_mg_transfer_prolongate": (_i32, [_vp, _vp, _vp]),
+    "b200mf_mg_transfer_prolongate_and_add": (_i32, [_vp, _vp, _vp]),
+    "b200mf_mg_transfer_restrict_and_add": (_i32, [_vp, _vp, _vp]),
+    "b200mf_mg_transfer_interpolate": (_i32, [_vp, _vp, _vp]),
+    "b200mf_mg_create": (_i32, [_PP, _i32, _PP, _PP, _vp]),
+    "b200mf_mg_destroy": (_i32, [_vp]),
+    "b200mf_mg_vmult": (_i32, [_vp, _vp, _vp]),
+    "b200mf_cg_create_nh": (_i32, [_PP, _vp]),
+    "b200mf_cg_create_laplace": (_i32, [_PP, _vp]),
+    "b200mf_cg_destroy": (_i32, [_vp]),
+    "b200mf_cg_solve": (_i32, [_vp, _vp, _vp, C.POINTER(CGControl), C.POINTER(CGResult)]),
 }
 
 

@@ -189,6 +189,23 @@ class StructuredMesh:
                               self.lower, self.upper, periodic_x=self.periodic_x)
 
 
+def children_of(coarse_mesh):
+    """[n_coarse_cells, 8] cell indices of the uniformly refined mesh (child (cx,cy,cz) at cx + 2 cy + 4 cz), the
+    parent/child relation `refine_global` produces (mf_elasticity.h:638) — input of b200mf_mg_transfer_create."""
+    nc = coarse_mesh.ncells
+    dim = len(nc)
+    ijk = coarse_mesh.cell_ijk
+    out = np.zeros((coarse_mesh.n_cells, 1 << dim), dtype=np.int64)
+    for ch in range(1 << dim):
+        idx = np.zeros(coarse_mesh.n_cells, dtype=np.int64)
+        stride = 1
+        for d in range(dim):
+            idx += (2 * ijk[:, d] + ((ch >> d) & 1)) * stride
+            stride *= 2 * nc[d]
+        out[:, ch] = idx
+    return out
+
+
 def cylinder_shell_mapping(length, r_in, r_out, scale=1.0):
     """Unit box (s,t,r) -> cylinder shell: axis along x, angle from s.  Matches
     the shape of GridGenerator::cylinder_shell used by

@@ -174,6 +174,28 @@ class DeviceVector:
     def update_ghost_values(self):
         _l.check(_l.load().b200mf_vec_update_ghost_values(self.mf.h, self.ptr))
 
+    # LinearAlgebra::distributed::Vector algebra (owned entries, summed over ranks)
+    def dot(self, other):
+        v = C.c_double()
+        _l.check(_l.load().b200mf_vec_dot(self.mf.h, self.ptr, other.ptr, C.byref(v)))
+        return v.value
+
+    def l2_norm(self):
+        v = C.c_double()
+        _l.check(_l.load().b200mf_vec_l2_norm(self.mf.h, self.ptr, C.byref(v)))
+        return v.value
+
+    def sadd(self, s, a, x):
+        """self = s*self + a*x"""
+        _l.check(_l.load().b200mf_vec_sadd(self.mf.h, self.ptr, float(s), float(a), x.ptr))
+
+    def set_zero(self):
+        _l.check(_l.load().b200mf_vec_set_zero(self.mf.h, self.ptr))
+
+    def copy_from(self, other):
+        """same mesh, possibly another number type (double system <-> float level)"""
+        _l.check(_l.load().b200mf_vec_convert(self.mf.h, self.ptr, other.mf.h, other.ptr))
+
     def compress_add(self):
         _l.check(_l.load().b200mf_vec_compress_add(self.mf.h, self.ptr))
 

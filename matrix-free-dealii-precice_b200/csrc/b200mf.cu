@@ -463,6 +463,8 @@ extern "C" int b200mf_ctx_create(b200mf_ctx **out, const b200mf_ctx_desc *d) {
           nidx[((size_t)g * N + k) * L + cw * N2 + ji] = node | ((uint32_t)nflags[node] << 29);
         }
     }
+    c->h_cell_nodes = new std::vector<uint32_t>(node_of_cell.size());
+    for (size_t i = 0; i < node_of_cell.size(); ++i) (*c->h_cell_nodes)[i] = node_of_cell[i] | ((uint32_t)nflags[node_of_cell[i]] << 29);
     B2_CUDA(cudaMalloc(&c->nidx, nidx.size() * sizeof(uint32_t)));
     B2_CUDA(cudaMemcpy(c->nidx, nidx.data(), nidx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     c->bytes += nidx.size() * sizeof(uint32_t);
@@ -544,6 +546,7 @@ extern "C" int b200mf_ctx_destroy(b200mf_ctx *c) {
   cudaFree(c->stage);
   free_partitioner(c);
   delete c->h_ext2int;
+  delete c->h_cell_nodes;
   delete c;
   return 0;
 }
@@ -840,6 +843,7 @@ extern "C" int b200mf_nh_vmult_host(b200mf_nh *op, double *dst, const double *sr
   return b200mf_vec_download_f64(op->ctx, dst, op->tmp_dst);
 }
 
+extern "C" b200mf_ctx *b200mf_nh_ctx(b200mf_nh *op) { return op ? op->ctx : nullptr; }
 extern "C" int64_t b200mf_nh_m(const b200mf_nh *op) { return op ? op->ctx->n_dofs : -1; }
 extern "C" size_t b200mf_nh_memory_consumption(const b200mf_nh *op) { return op ? op->table_bytes : 0; }
 // number of fields b200mf_nh_qdata_host can return: staged table (deformed variants) or c (scalar_referential), then the big table
@@ -1026,6 +1030,7 @@ extern "C" int b200mf_laplace_destroy(b200mf_laplace *op) {
   return 0;
 }
 
+extern "C" b200mf_ctx *b200mf_laplace_ctx(b200mf_laplace *op) { return op ? op->ctx : nullptr; }
 extern "C" int b200mf_laplace_set_delta_t(b200mf_laplace *op, double dt) {
   if (!op) return set_error(B200MF_ERR_ARG, "null op");
   op->delta_t = dt;

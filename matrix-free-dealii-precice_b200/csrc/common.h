@@ -75,4 +75,5 @@ struct b200mf_ctx {
   b200mf::Shape1D shape;
   b200mf_partitioner *part;         // nullptr on a single rank
   std::vector<int64_t> *h_ext2int;  // caller index -> internal index, nullptr when identity
+  std::vector<uint32_t> *h_cell_nodes;  // [n_cells][N^3] node | constrained flags (bits 29..31), caller's cell order (MG transfer set-up)
 };
