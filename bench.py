@@ -30,14 +30,20 @@ MAT = dict(mu=0.5e6, nu=0.4, rho=1000.0, alpha_1=1.0 / (0.25 * 0.01**2), formula
 METRIC = "nh_tangent_vmult_dofs_per_s"
 
 
-def algorithmic_bytes_per_cell(p, esize=8):
+# q-point values the kernel of each variant streams per quadrature point (csrc/ops.cuh): metric (9+1) plus
+#   tensor2: c1, c2, symmetric tau/J (6)            scalar_referential: c + 3 cached displacement values
+#   tensor4: c2, tau/J (6), 6x6 tensor (36)         tensor4_ns: 81      form0: J^(-1/3), F (9)
+QPOINT_VALUES = {"tensor2": 18, "scalar_referential": 14, "tensor4": 53, "tensor4_ns": 91, "form0": 20}
+
+
+def algorithmic_bytes_per_cell(p, esize=8, variant="tensor2"):
     """src read + dst write per unique DoF, one uint32 per node, and the q-point
-    table the kernel actually streams: deformed metric (9+1) + c1, c2, symmetric tau/J (6) = 18 values."""
+    table the kernel of this variant actually streams."""
     n = p + 1
-    return 2 * esize * 3 * p**3 + 4 * n**3 + 18 * esize * n**3
+    return 2 * esize * 3 * p**3 + 4 * n**3 + QPOINT_VALUES[variant] * esize * n**3
 
 
-def build_problem(p, ncell_dir, dtype="f64", comm=None):
+def build_problem(p, ncell_dir, dtype="f64", comm=None, caching="tensor2", formulation=1):
     """One brick of ncell_dir^3 cells per rank (SURVEY.md §8d config 5: 1x1x1, 2x1x1, 2x2x1, 2x2x2 bricks);
     shared faces are exchanged through the library's partitioner (update_ghost_values / compress(add))."""
     from b200mf import MatrixFree, NeoHookOperator
@@ -56,8 +62,8 @@ def build_problem(p, ncell_dir, dtype="f64", comm=None):
         u = synthetic_displacement(m.node_coordinates(), 0.05)
         mf = MatrixFree.from_mesh(m, 3, dtype=dtype)
     op = NeoHookOperator()
-    op.set_material(mf, MAT)
-    op.initialize(u, "tensor2")
+    op.set_material(mf, dict(MAT, formulation=formulation))
+    op.initialize(u, caching)
     op.cache()
     return m, mf, op
 
@@ -178,9 +184,9 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(p, nc, ngpus):
-    return {"workload": f"neo-Hookean tangent vmult, tensor2 caching, Q{p}, box {nc}^3 cells per GPU",
-            "degree": p, "cells_per_gpu": nc**3, "dofs_per_gpu": 3 * (nc * p + 1) ** 3, "caching": "tensor2",
+def workload_config(p, nc, ngpus, caching="tensor2", formulation=1):
+    return {"workload": f"neo-Hookean tangent vmult, {caching} caching, formulation {formulation}, Q{p}, box {nc}^3 cells per GPU",
+            "degree": p, "cells_per_gpu": nc**3, "dofs_per_gpu": 3 * (nc * p + 1) ** 3, "caching": caching,
             "parallelism": f"dd{ngpus}", "l2": "vectors+tables per step >> 126 MB L2 (no flush needed)"}
 
 
@@ -197,6 +203,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--sweep", action="store_true", help="also report Q1..Q6 device-resident rates")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--caching", default="tensor2", choices=["scalar_referential", "tensor2", "tensor4", "tensor4_ns"])
+    ap.add_argument("--formulation", type=int, default=1, choices=[0, 1])
     args = ap.parse_args()
     p = args.degree
     if args.cpu_cells is None:
@@ -224,7 +232,8 @@ def main():
     nc = CELLS_PER_DIR[p] if args.cells is None else args.cells
     es = 8 if args.dtype == "f64" else 4
     comm = b200mf.Communicator.from_torch_distributed() if world > 1 else None
-    m, mf, op = build_problem(p, nc, args.dtype, comm)
+    variant = "form0" if args.formulation == 0 else args.caching
+    m, mf, op = build_problem(p, nc, args.dtype, comm, args.caching, args.formulation)
     n = 3 * m.n_nodes  # local vector: owned + ghost entries
     n_owned = m.n_owned if world > 1 else n
     src_h = np.random.default_rng(rank).uniform(-1, 1, n)
@@ -270,11 +279,11 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    alg_bytes = algorithmic_bytes_per_cell(p, es) * m.n_cells  # per GPU (per launch of the cell kernel)
+    alg_bytes = algorithmic_bytes_per_cell(p, es, variant) * m.n_cells  # per GPU (per launch of the cell kernel)
     achieved = alg_bytes / (ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
-                "algorithmic_bytes_per_dof": algorithmic_bytes_per_cell(p, es) / (3 * p**3),
+                "algorithmic_bytes_per_dof": algorithmic_bytes_per_cell(p, es, variant) / (3 * p**3),
                 "timed": "whole vmult step (memset + cell loop + constrained fix-up), CUDA events"}
 
     # ---- e2e: host buffers through the C-ABI host entry point ----------------------------------
@@ -305,7 +314,7 @@ def main():
         sweep = {}
         del src, dst, op, mf
         for q in range(1, 7):
-            mq, mfq, opq = build_problem(q, CELLS_PER_DIR[q], args.dtype)
+            mq, mfq, opq = build_problem(q, CELLS_PER_DIR[q], args.dtype, None, args.caching, args.formulation)
             nq = 3 * mq.n_nodes
             s, d = DeviceVector(mfq, np.random.default_rng(q).uniform(-1, 1, nq)), DeviceVector(mfq)
             for _ in range(3):
@@ -318,7 +327,7 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             msq = e0.elapsed_time(e1) / 10
-            gb = algorithmic_bytes_per_cell(q, es) * mq.n_cells / (msq * 1e-3) / 1e9
+            gb = algorithmic_bytes_per_cell(q, es, variant) * mq.n_cells / (msq * 1e-3) / 1e9
             sweep[f"Q{q}"] = {"dofs": nq, "ms": msq, "dofs_per_s": nq / (msq * 1e-3), "GB/s": gb, "frac": gb / peak}
             del s, d, opq, mfq
 
@@ -332,7 +341,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "DoFs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
-            "data": "synthetic", "config": workload_config(p, nc, world), "roofline": roofline, "cpu_baseline": cpu,
+            "data": "synthetic", "config": workload_config(p, nc, world, args.caching, args.formulation), "roofline": roofline, "cpu_baseline": cpu,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(),
         }
         if sweep:

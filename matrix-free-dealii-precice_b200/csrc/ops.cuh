@@ -53,11 +53,12 @@ template <typename T>
 __device__ __forceinline__ void nh_cell_begin(const NHArgs<T> &oa, int64_t cell, bool valid, NHCell<T> &st) {
   int m = 0;
   if (oa.matid != nullptr && valid && cell < oa.n_cells) m = oa.matid[cell] != 0;  // :402-404, :656-658
-  st.mu = oa.mu[m];
-  st.lambda = oa.lambda[m];
-  st.rho_alpha = oa.rho_alpha[m];
-  st.kappa = oa.kappa[m];
-  st.c_1 = oa.c_1[m];
+  // selects, not dynamic indexing: indexing kernel parameters by a run-time value forces a local-memory copy
+  st.mu = m ? oa.mu[1] : oa.mu[0];
+  st.lambda = m ? oa.lambda[1] : oa.lambda[0];
+  st.rho_alpha = m ? oa.rho_alpha[1] : oa.rho_alpha[0];
+  st.kappa = m ? oa.kappa[1] : oa.kappa[0];
+  st.c_1 = m ? oa.c_1[1] : oa.c_1[0];
 }
 
 template <typename T>
@@ -313,8 +314,8 @@ struct NHCacheOp {
     int m = 0;
     st.real = valid && cell < oa.n_cells;
     if (oa.matid != nullptr && st.real) m = oa.matid[cell] != 0;  // :402-404
-    st.mu = oa.mu[m];
-    st.lambda = oa.lambda[m];
+    st.mu = m ? oa.mu[1] : oa.mu[0];
+    st.lambda = m ? oa.lambda[1] : oa.lambda[0];
   }
   // :416-418: keep the cell-local displacement so that vmult needs no indirect read of it
   static __device__ __forceinline__ void store_dofs(const Args &oa, int64_t group, int lane, bool active, const T (&u)[NC][N]) {
