@@ -6,7 +6,7 @@
  * PARITY PIN STATUS: the reference has no operator-level golden vectors
  * (SURVEY.md §8c).  This file is validated against oracle/np_oracle.py (dense,
  * no sum factorisation) to <= 1e-13 and through it against the 2-D Q1
- * Turek-Hron end-to-end goldens of /root/reference/tests/solid.
+ * Turek-Hron end-to-end goldens of /root/reference/tests/solid (tests/test_golden_turek.py).
  *
  * Reference lines restated (relative to /root/reference):
  *   include/solid_mechanics/mf_nh_operator.h:392-523   cache()

@@ -9,7 +9,8 @@ PARITY PIN STATUS: the reference holds no operator-level golden vectors
 (all cache levels agree, symmetry, finite differences of the residual,
 scipy-assembled Laplace matrices) and (b) end-to-end against the reference's
 only goldens, the 2-D Q1 Turek-Hron runs (tests/solid/*/*_serial.output),
-through oracle/np_solver.py.  deal.II semantics (FE_Q on Gauss-Lobatto points,
+through oracle/solid_driver.py + oracle/solver_oracle.py (tests/test_golden_turek.py:
+all six goldens reproduced — displacement to 6 digits, Newton 4/4, CG 29/24/701).  deal.II semantics (FE_Q on Gauss-Lobatto points,
 Gauss quadrature, lexicographic component-major cell layout, Jacobian
 conventions) are restated from its documentation: SURVEY.md Appendix A.
 

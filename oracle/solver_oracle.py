@@ -10,8 +10,10 @@ from deal.II's documented behaviour and anchored on
   MGTransferMatrixFree    mf_elasticity.h:863-877, 920-922; heat_transfer.h:761-762
   Multigrid/PreconditionMG mf_elasticity.h:1209-1224, 1272-1276
 
-Parity status: the end-to-end goldens of the reference (average CG iterations 29/24/701, tests/solid/*/*.output:19)
-are 2-D Q1 runs through preCICE; see DESIGN.md for what is and is not pinned.
+Parity status: PINNED against the reference's end-to-end goldens — oracle/solid_driver.py drives these classes through
+the 2-D Q1 Turek-Hron runs and reproduces the average CG iterations per Newton step of all six cases (29 for the four
+cache levels with GMG-Chebyshev, 24 for formulation 0, 701 with Jacobi; tests/solid/*/*_serial.output:19) —
+tests/test_golden_turek.py.
 """
 from __future__ import annotations
 
