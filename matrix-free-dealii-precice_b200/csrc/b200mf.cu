@@ -130,8 +130,8 @@ void compute_shape_1d(int p, Shape1D &out) {
 
 // host copies of the 1-D matrices every kernel translation unit uploads into its own __constant__ bank (launch.cuh)
 void shape_tables(const double **hd_out, const float **hf_out) {
-  static double hd[MAXN + 1][2][MAXN * MAXN];
-  static float hf[MAXN + 1][2][MAXN * MAXN];
+  static double hd[MAXN + 1][3][MAXN * MAXN];
+  static float hf[MAXN + 1][3][MAXN * MAXN];
   static bool done = false;
   if (!done) {
     memset(hd, 0, sizeof hd);
@@ -141,10 +141,11 @@ void shape_tables(const double **hd_out, const float **hf_out) {
       for (int i = 0; i < N * N; ++i) {
         hd[N][0][i] = s.S[i];
         hd[N][1][i] = s.C[i];
+        hd[N][2][i] = s.D[i];  // derivative of the nodal basis at the Gauss points (= C S)
       }
     }
     for (int N = 0; N <= MAXN; ++N)
-      for (int m = 0; m < 2; ++m)
+      for (int m = 0; m < 3; ++m)
         for (int i = 0; i < MAXN * MAXN; ++i) hf[N][m][i] = (float)hd[N][m][i];
     done = true;
   }
@@ -170,7 +171,7 @@ __global__ void metric_from_vertices_kernel(int N, int cpg, int L, int64_t gstri
   const int q = (int)(idx % N3);
   const int iq = q % N, jq = (q / N) % N, kq = q / N2;
   const int64_t group = cell / cpg;
-  const int lane = (int)(cell % cpg) * N2 + kq * N + jq;
+  const int lane = (int)(cell % cpg) * N2 + jq * N + iq;  // column thread (cell, j, i) owns the q-points (i, j, kq)
   double Ki[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, jxw = 0.0;
   if (cell < n_cells) {
     const double *v = vtx + cell * 24;
@@ -204,7 +205,7 @@ __global__ void metric_from_vertices_kernel(int N, int cpg, int L, int64_t gstri
     jxw = det * qp.wq[iq] * qp.wq[jq] * qp.wq[kq];
   }
   const size_t FS = (size_t)N * L;
-  T *o = mref + (size_t)group * gstride + (size_t)iq * L + lane;
+  T *o = mref + (size_t)group * gstride + (size_t)kq * L + lane;
   for (int i = 0; i < 9; ++i) o[(MF_K + i) * FS] = (T)Ki[i];
   o[MF_W * FS] = (T)jxw;
 }
@@ -220,9 +221,9 @@ __global__ void table_to_group_layout_kernel(int N, int cpg, int L, int nf, int6
   const int q = (int)(idx % N3);
   const int iq = q % N, jq = (q / N) % N, kq = q / N2;
   const int64_t group = cell / cpg;
-  const int lane = (int)(cell % cpg) * N2 + kq * N + jq;
+  const int lane = (int)(cell % cpg) * N2 + jq * N + iq;  // column thread (cell, j, i) owns the q-points (i, j, kq)
   const size_t FS = (size_t)N * L;
-  T *o = out + (size_t)group * gstride + (size_t)iq * L + lane;
+  T *o = out + (size_t)group * gstride + (size_t)kq * L + lane;
   for (int f = 0; f < nf; ++f) {
     double v;
     if (cell < n_cells)
@@ -244,8 +245,8 @@ __global__ void field_from_group_layout_kernel(int N, int cpg, int L, int64_t gs
   const int q = (int)(idx % N3);
   const int iq = q % N, jq = (q / N) % N, kq = q / N2;
   const int64_t group = cell / cpg;
-  const int lane = (int)(cell % cpg) * N2 + kq * N + jq;
-  out[idx] = (double)in[(size_t)group * gstride + ((size_t)field * N + iq) * L + lane];
+  const int lane = (int)(cell % cpg) * N2 + jq * N + iq;  // column thread (cell, j, i) owns the q-points (i, j, kq)
+  out[idx] = (double)in[(size_t)group * gstride + ((size_t)field * N + kq) * L + lane];
 }
 
 template <typename TO, typename TI>

@@ -9,28 +9,32 @@
 // i.e. reinit / read_dof_values / evaluate / quadrature loop / integrate /
 // distribute_local_to_global.
 //
-// Design (B200-first, not a translation of deal.II's SIMD-over-cells loop):
-//  * one thread owns one 1-D "column" of a cell: N = p+1 values per component in
-//    registers, N^2 threads per cell.  Sweeps along the register direction use
-//    the 1-D matrices as compile-time constant-bank operands (DFMA R,R,c[..],R:
-//    no load instruction), the other two directions are reached by transposing
-//    through shared memory (2N smem accesses per N^2 FMAs instead of the N^2 of
-//    the thread-per-point scheme: B200 has 4x the HBM bytes per SM-clock of
-//    V100/A100 but the same 128 B/clk shared-memory port, so the classic scheme
-//    is shared-memory bound long before HBM is).
-//  * for N^2 <= 32 a cell never straddles a warp: floor(32/N^2) cells per warp
-//    ("group") and every barrier is a __syncwarp; N^2 > 32 uses one 64-thread
-//    block per cell and __syncthreads.
-//  * all per-cell tables are stored per group in the exact lane order the
-//    kernel reads them ([group][field][x-index][lane]); a group's table is one
-//    contiguous block that the TMA unit (cp.async.bulk + mbarrier) copies into
-//    shared memory one group ahead of the arithmetic, and the DoF gather of the
-//    next group is issued into registers before the transpose half of the
-//    current one: HBM latency is off the critical path (the first profile,
-//    profiles/r01_v1_*, showed 60 % of the stalls on the long scoreboard).
-//  * vectors are stored in component blocks (DoF (node,c) at c*cstride+node): a
-//    row of N nodes of one component is one contiguous run, which halves the
-//    sectors per gather / red.global.add compared with interleaved components.
+// Design (B200-first, not a translation of deal.II's SIMD-over-cells loop).  The first two
+// versions of this kernel (profiles/r01_v1_*, r01_v2_*) were bound by the shared-memory / L1
+// data pipe (l1tex__data_pipe_lsu_wavefronts 82-87 % at 47-65 % of DRAM): B200 has 4x the HBM
+// bytes per SM-clock of V100/A100 but the same 128 B/clk shared-memory port.  This version
+// (v3) therefore minimises shared-memory wavefronts per cell:
+//  * two thread roles inside a group of cells.  A COLUMN thread (i, j) owns the z-column of
+//    one cell: it gathers the nodal values (coalesced along i), applies the z sweep in
+//    registers, later runs the quadrature-point physics for its N points and the z part of
+//    the integration, and scatters.  A PLANE task (component c, z-plane kq) owns one x-y
+//    plane of one component: N^2 values in registers, x and y sweeps and the x/y collocation
+//    derivatives without touching shared memory.
+//  * per component 16 N^3 element accesses of shared memory per cell instead of (11 + 4N) N^3
+//    (N = 4: -41 %, N = 7: -59 %): z-swept nodal planes (column -> plane), values + d/dx + d/dy
+//    at the quadrature points (plane -> column), and the same two hops back.  d/dz is a register
+//    sweep of the column thread.  All 1-D matrices are compile-time constant-bank operands
+//    (DFMA R, R, c[..], R: no load instruction).
+//  * for N^2 <= 32 a cell never straddles a warp: floor(32/N^2) cells per warp ("group") and
+//    every barrier is a __syncwarp; N^2 > 32 uses one 64-thread block per cell.
+//  * all per-cell tables are stored per group in the exact lane order the column threads read
+//    them ([group][field][kq][lane], lane = (cell, j, i)); a group's table is one contiguous
+//    block that the TMA unit (cp.async.bulk + mbarrier) copies into shared memory one group
+//    ahead of the arithmetic, and the DoF gather of the next group is issued into registers
+//    before the integration half of the current one: HBM latency is off the critical path.
+//  * vectors are stored in component blocks (DoF (node, c) at c*cstride + node): a row of N
+//    nodes of one component is one contiguous run (half the sectors per gather / red.global.add
+//    of interleaved components).
 //  * F, tau and the linearised stress live only in registers.
 #pragma once
 #include <cuda_runtime.h>
@@ -44,9 +48,9 @@ constexpr uint32_t NODE_MASK = (1u << 29) - 1u;
 __host__ __device__ constexpr uint32_t node_flag(int c) { return 1u << (29 + c); }
 constexpr uint32_t NODE_ALL_CONSTRAINED = 7u << 29;
 
-// [N][0: S[q][i] = l_i(xi_q), 1: C[q][r] = collocation derivative on the Gauss points][q*N + i]
-static __constant__ double c_shape_d[MAXN + 1][2][MAXN * MAXN];
-static __constant__ float c_shape_f[MAXN + 1][2][MAXN * MAXN];
+// [N][0: S[q][i] = l_i(xi_q), 1: C[q][r] = collocation derivative on the Gauss points, 2: D = C S][q*N + i]
+static __constant__ double c_shape_d[MAXN + 1][3][MAXN * MAXN];
+static __constant__ float c_shape_f[MAXN + 1][3][MAXN * MAXN];
 
 template <typename T, int N>
 struct Shape;
@@ -54,34 +58,26 @@ template <int N>
 struct Shape<double, N> {
   static __device__ __forceinline__ double S(int q, int i) { return c_shape_d[N][0][q * N + i]; }
   static __device__ __forceinline__ double C(int q, int r) { return c_shape_d[N][1][q * N + r]; }
+  static __device__ __forceinline__ double D(int q, int i) { return c_shape_d[N][2][q * N + i]; }
 };
 template <int N>
 struct Shape<float, N> {
   static __device__ __forceinline__ float S(int q, int i) { return c_shape_f[N][0][q * N + i]; }
   static __device__ __forceinline__ float C(int q, int r) { return c_shape_f[N][1][q * N + r]; }
+  static __device__ __forceinline__ float D(int q, int i) { return c_shape_f[N][2][q * N + i]; }
 };
 
 // ---------------------------------------------------------------------------
-// Thread / shared-memory layout.  Strides from tools/smem_layout_search.py (64-bit accesses are served
-// per half-warp over 16 8-byte banks: confirmed by the ncu source page, profiles/r01_*: only the
-// Z-orientation accesses of even N pay 2x, 7.8% excess wavefronts in total).
-template <int WORDS, int N>
-struct SmemPad;  // JS, KPAD (KS = N*JS + KPAD), CELLPAD for 3 components / 1 component
-#define B2_PAD(W, N_, JS_, KP_, C3_, C1_) \
-  template <> struct SmemPad<W, N_> { static constexpr int JS = JS_, KPAD = KP_, CPAD3 = C3_, CPAD1 = C1_; };
-B2_PAD(2, 2, 3, 0, 0, 0)
-B2_PAD(2, 3, 3, 0, 8, 10)
-B2_PAD(2, 4, 5, 0, 0, 0)
-B2_PAD(2, 5, 5, 0, 0, 0)
-B2_PAD(2, 6, 7, 0, 0, 0)
-B2_PAD(2, 7, 7, 0, 0, 0)
-B2_PAD(1, 2, 3, 0, 0, 0)
-B2_PAD(1, 3, 3, 0, 8, 10)
-B2_PAD(1, 4, 5, 0, 0, 0)
-B2_PAD(1, 5, 5, 0, 0, 0)
-B2_PAD(1, 6, 7, 0, 0, 0)
-B2_PAD(1, 7, 7, 0, 0, 0)
-#undef B2_PAD
+// Shared-memory layout.  Two plane buffers per group with nested strides (plane stride PL, element j*N + i):
+//   bufZ plane (cw, c, kq)    at cw*ZCELL + c*ZCOMP + kq*PL,             ZCOMP = N*PL + CCZ, ZCELL = NC*ZCOMP + CZ
+//   bufQ plane (cw, c, f, kq) at cw*QCELL + c*QCOMP + f*QFIELD + kq*PL,  QFIELD = N*PL + FQ, QCOMP = 3*QFIELD + CCQ, QCELL = NC*QCOMP + CQ
+// Pads from tools/smem_layout_search2.py (64-bit accesses are served per half-warp over 16 8-byte banks).
+template <int WORDS, int NC, int N>
+struct SmemPad3;
+#define B2_PAD3(W, NC_, N_, PL_, CZ_, CCZ_, CQ_, CCQ_, FQ_) \
+  template <> struct SmemPad3<W, NC_, N_> { static constexpr int PL = PL_, CZ = CZ_, CCZ = CCZ_, CQ = CQ_, CCQ = CCQ_, FQ = FQ_; };
+#include "smem_pads.inc"
+#undef B2_PAD3
 
 __host__ __device__ constexpr size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
 
@@ -90,15 +86,18 @@ struct Layout {
   static constexpr int N2 = N * N, N3 = N * N * N;
   static constexpr bool WARP_MODE = (N2 <= 32);
   static constexpr int CPG = WARP_MODE ? 32 / N2 : 1;                 // cells per group
-  static constexpr int L = CPG * N2;                                  // dense lanes per group
+  static constexpr int L = CPG * N2;                                  // column threads (dense lanes) per group
   static constexpr int TPG = WARP_MODE ? 32 : ((N2 + 31) / 32) * 32;  // threads per group
-  static constexpr int JS = SmemPad<WORDS, N>::JS;
-  static constexpr int KS = N * JS + SmemPad<WORDS, N>::KPAD;
-  static constexpr int CSTR = N * KS;  // one component of one buffer
-  static constexpr int NBUF = 3;
-  static constexpr int CELLPAD = (NC == 3) ? SmemPad<WORDS, N>::CPAD3 : SmemPad<WORDS, N>::CPAD1;
-  static constexpr int CELL = NBUF * NC * CSTR + CELLPAD;
-  static constexpr int GROUP_ELEMS = CPG * CELL;
+  static constexpr int NT = CPG * NC * N;                             // plane tasks per group
+  using P = SmemPad3<WORDS, NC, N>;
+  static constexpr int PL = P::PL;
+  static constexpr int ZCOMP = N * PL + P::CCZ, ZCELL = NC * ZCOMP + P::CZ;
+  static constexpr int QFIELD = N * PL + P::FQ, QCOMP = 3 * QFIELD + P::CCQ, QCELL = NC * QCOMP + P::CQ;
+  static constexpr int ZSIZE = CPG * ZCELL;
+  static constexpr int QSIZE = CPG * QCELL;
+  static constexpr int GROUP_ELEMS = ZSIZE + QSIZE;
+  __host__ __device__ static constexpr int zplane(int cw, int c, int kq) { return cw * ZCELL + c * ZCOMP + kq * PL; }
+  __host__ __device__ static constexpr int qplane(int cw, int c, int f, int kq) { return cw * QCELL + c * QCOMP + f * QFIELD + kq * PL; }
   // elements between consecutive groups of a [group][NF][N][L] table (16-byte multiple for cp.async.bulk)
   __host__ __device__ static constexpr size_t table_stride(int NF) { return round_up((size_t)NF * N * L, 16 / (4 * WORDS)); }
 };
@@ -139,7 +138,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 template <typename T>
 struct CellArgs {
   int64_t group_begin, n_groups;  // groups [group_begin, n_groups)
-  const uint32_t *nidx;  // [group][k][lane], flags in bits 29..31
+  const uint32_t *nidx;           // [group][k][lane], flags in bits 29..31
   const T *src;
   T *dst;
   int64_t cstride;  // vector layout: DoF (node, c) lives at c*cstride + node ("component blocks")
@@ -172,15 +171,19 @@ __device__ __forceinline__ void sweep_C(const T (&in)[N], T (&out)[N]) {
 // Op concept:
 //   static constexpr int  NC;            components
 //   static constexpr bool PLAIN;         read_dof_values_plain (ignore constraints)
-//   static constexpr bool INTEGRATE;     run the transpose half and scatter
+//   static constexpr bool INTEGRATE;     run the integration half and scatter
+//   static constexpr bool PRE;           one extra evaluation-only pass (pass -1) over a second cell-local field
+//                                        (Op::load_pre) whose q-point results (Op::quad_pre) stay in shared memory
+//   static constexpr bool STORE_DOFS;    Op::store_dofs gets the gathered cell-local values
 //   static constexpr int  NF_IN, NF_IN2; fields of the (up to two) input tables staged through shared memory
+//   static constexpr int  NF_SCRATCH;    fields of per-group scratch (pre-pass -> main pass)
 //   struct Args { const T *stage, *stage2; ... }   stage2 may be null at run time
-//   struct CellState;                    per-thread per-cell state (e.g. material constants)
+//   struct CellState;                    per-thread per-cell state (material constants)
 //   static void cell_begin(args, cell, valid, CellState&)
-//   static void quad(args, state, active, qs, qs2, scr, group, iq, lane, v[NC], G[NC][3], ov[NC], oG[NC][3])
-//       qs / qs2: shared-memory copies of this group's tables, field f of q-point (iq, lane) at
-//       qs[(f*N + iq)*L + lane]; scr: NF_SCRATCH fields of per-group scratch in the same layout
-//   static constexpr bool PRE, STORE_DOFS; int NF_SCRATCH  (see the pass loop)
+//   static void quad(args, state, active, qs, qs2, scr, group, kq, lane, v[NC], G[NC][3], ov[NC], oG[NC][3])
+//       the column thread `lane` = (cell, j, i) handles the q-points (i, j, kq), kq = 0..N-1;
+//       qs / qs2 / scr: shared-memory tables, field f of q-point (kq, lane) at qs[(f*N + kq)*L + lane];
+//       G[c][d] = d u_c / d xi_d (reference gradient), oG likewise for the test-function side
 //
 // DIAG = true turns the loop into MatrixFreeTools::compute_diagonal: the cell
 // operator is applied to every local unit vector and entry i of the result is kept.
@@ -191,7 +194,7 @@ struct KernelSmem {
   static constexpr size_t ST1_BYTES = Ly::table_stride(Op::NF_IN) * sizeof(T);
   static constexpr size_t ST2_BYTES = Op::NF_IN2 ? Ly::table_stride(Op::NF_IN2) * sizeof(T) : 0;
   static constexpr size_t SCR_BYTES = Op::NF_SCRATCH ? Ly::table_stride(Op::NF_SCRATCH) * sizeof(T) : 0;  // pre-pass -> main pass
-  static constexpr size_t GROUP_BYTES = BUF_BYTES + ST1_BYTES + ST2_BYTES + SCR_BYTES + 16;  // + mbarrier
+  static constexpr size_t GROUP_BYTES = BUF_BYTES + ST1_BYTES + ST2_BYTES + SCR_BYTES + 16;                // + mbarrier
 };
 
 template <typename T, int N, class Op, int GPB, bool DIAG = false, int MINB = 1>
@@ -201,7 +204,7 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
   using Ly = Layout<N, NC, sizeof(T) / 4>;
   using Sh = Shape<T, N>;
   using KS_ = KernelSmem<T, N, Op>;
-  constexpr int N2 = Ly::N2, JS = Ly::JS, KS = Ly::KS, CSTR = Ly::CSTR, L = Ly::L;
+  constexpr int N2 = Ly::N2, L = Ly::L, PL = Ly::PL, NT = Ly::NT;
   constexpr bool WM = Ly::WARP_MODE;
   static_assert(WM || GPB == 1, "block mode runs one group per block");
 
@@ -209,15 +212,13 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
 
   const int gib = threadIdx.x / Ly::TPG;
   const int lane = threadIdx.x % Ly::TPG;
-  const bool active = lane < L;
+  const bool active = lane < L;           // column thread
   const int cw = active ? lane / N2 : 0;
-  const int t = active ? lane % N2 : 0;
-  const int a = t % N, b = t / N;
+  const int ji = active ? lane % N2 : 0;  // j*N + i
 
   unsigned char *gbase = smem_raw + (size_t)gib * KS_::GROUP_BYTES;
-  T *bufA = reinterpret_cast<T *>(gbase) + (size_t)cw * Ly::CELL;
-  T *bufB = bufA + NC * CSTR;
-  T *bufC = bufB + NC * CSTR;
+  T *bufZ = reinterpret_cast<T *>(gbase);
+  T *bufQ = bufZ + Ly::ZSIZE;
   T *qs = reinterpret_cast<T *>(gbase + KS_::BUF_BYTES);
   T *qs2 = reinterpret_cast<T *>(gbase + KS_::BUF_BYTES + KS_::ST1_BYTES);
   T *scr = reinterpret_cast<T *>(gbase + KS_::BUF_BYTES + KS_::ST1_BYTES + KS_::ST2_BYTES);
@@ -251,20 +252,11 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
     }
   };
 
-  // per-thread rows/columns of the collocation derivative for the two
-  // directions that are contracted straight out of shared memory
-  T cy[N], cz[N], cyT[N], czT[N];
-#pragma unroll
-  for (int m = 0; m < N; ++m) {
-    cy[m] = Sh::C(a, m);
-    cz[m] = Sh::C(b, m);
-    cyT[m] = Sh::C(m, a);
-    czT[m] = Sh::C(m, b);
-  }
-
-  const int oZ = b * JS + a;       // + k*KS : (i=a, j=b) column along z
-  const int oY = b * KS + a;       // + j*JS : (i=a, k=b) column along y
-  const int oX = b * KS + a * JS;  // + i    : (j=a, k=b) column along x
+  // column-thread offsets into the plane buffers
+  const int zoff = Ly::zplane(cw, 0, 0) + ji;
+  const int qoff = Ly::qplane(cw, 0, 0, 0) + ji;
+  auto zidx = [&](int c, int kq) { return zoff + c * Ly::ZCOMP + kq * PL; };
+  auto qidx = [&](int c, int f, int kq) { return qoff + c * Ly::QCOMP + f * Ly::QFIELD + kq * PL; };
 
   const int64_t gstep = (int64_t)gridDim.x * GPB;
   int64_t group = A.group_begin + (int64_t)blockIdx.x * GPB + gib;
@@ -294,19 +286,17 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
     }
     if constexpr (Op::STORE_DOFS) Op::store_dofs(oa, group, lane, active, u);
     constexpr int NPASS = DIAG ? NC * Ly::N3 : 1;
-    // Op::PRE: one extra evaluation-only pass (pass -1) over a second cell-local field (Op::load_pre) whose
-    // quadrature-point results (Op::quad_pre) stay in shared memory for the main pass(es)
     constexpr int FIRST = Op::PRE ? -1 : 0;
 #pragma unroll 1
     for (int pass = FIRST; pass < NPASS; ++pass) {
       const bool pre = Op::PRE && pass < 0;
       const int pc = pass / Ly::N3, pk = (pass / N2) % N, pt = pass % N2;  // unit vector (component, k, column)
-      // ---- phase 1 (Z orientation): z sweep of the gathered values ----------
+      // ---- F1 (column): z sweep of the nodal column, planes to bufZ ---------------------------
       if (DIAG) {
 #pragma unroll
         for (int k = 0; k < N; ++k)
 #pragma unroll
-          for (int c = 0; c < NC; ++c) u[c][k] = (!(nid[k] & node_flag(c)) && c == pc && k == pk && t == pt) ? T(1) : T(0);
+          for (int c = 0; c < NC; ++c) u[c][k] = (!(nid[k] & node_flag(c)) && c == pc && k == pk && ji == pt) ? T(1) : T(0);
       }
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
@@ -319,77 +309,110 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
           sweep_S<T, N, false>(u[c], o);
         }
 #pragma unroll
-        for (int k = 0; k < N; ++k)
-          if (active) bufA[c * CSTR + k * KS + oZ] = o[k];
+        for (int kq = 0; kq < N; ++kq)
+          if (active) bufZ[zidx(c, kq)] = o[kq];
       }
       if (pass == FIRST && has_next) load_nid(gnext, nid_next);
       group_sync<WM>();
-      // ---- phase 2 (Y orientation) -------------------------------------------
+      // ---- F2 (plane tasks): x, y sweeps; values, d/dx, d/dy at the q-points of the plane ------
+#pragma unroll 1
+      for (int t0 = 0; t0 < NT; t0 += Ly::TPG) {
+        const int t = t0 + lane;
+        if (t < NT) {
+          const int tcw = t / (NC * N), tc = (t / N) % NC, tk = t % N;
+          const T *zp = bufZ + Ly::zplane(tcw, tc, tk);
+          T a[N][N];  // a[j][i]
 #pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        T col[N], o[N];
+          for (int j = 0; j < N; ++j)
 #pragma unroll
-        for (int j = 0; j < N; ++j) col[j] = bufA[c * CSTR + j * JS + oY];
-        sweep_S<T, N, false>(col, o);
+            for (int i = 0; i < N; ++i) a[j][i] = zp[j * N + i];
+          T b[N][N];  // x sweep: b[j][qx]
 #pragma unroll
-        for (int j = 0; j < N; ++j)
-          if (active) bufB[c * CSTR + j * JS + oY] = o[j];
-      }
-      group_sync<WM>();
-      // ---- phase 3 (X orientation): values + x derivative at quadrature points
-      T val[NC][N], gx[NC][N];
+          for (int j = 0; j < N; ++j) sweep_S<T, N, false>(a[j], b[j]);
+          // y sweep: a[qy][qx]
 #pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        T col[N];
+          for (int qx = 0; qx < N; ++qx) {
+            T col[N], o[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) col[i] = bufB[c * CSTR + oX + i];
-        sweep_S<T, N, false>(col, val[c]);
-        sweep_C<T, N>(val[c], gx[c]);
+            for (int j = 0; j < N; ++j) col[j] = b[j][qx];
+            sweep_S<T, N, false>(col, o);
 #pragma unroll
-        for (int i = 0; i < N; ++i)
-          if (active) bufA[c * CSTR + oX + i] = val[c][i];
+            for (int qy = 0; qy < N; ++qy) a[qy][qx] = o[qy];
+          }
+          T *qv = bufQ + Ly::qplane(tcw, tc, 0, tk), *qx_ = bufQ + Ly::qplane(tcw, tc, 1, tk), *qy_ = bufQ + Ly::qplane(tcw, tc, 2, tk);
+#pragma unroll
+          for (int qy = 0; qy < N; ++qy) {
+            T gx[N];
+            sweep_C<T, N>(a[qy], gx);
+#pragma unroll
+            for (int qx = 0; qx < N; ++qx) {
+              qv[qy * N + qx] = a[qy][qx];
+              qx_[qy * N + qx] = gx[qx];
+            }
+          }
+#pragma unroll
+          for (int qx = 0; qx < N; ++qx) {
+            T col[N], gy[N];
+#pragma unroll
+            for (int qy = 0; qy < N; ++qy) col[qy] = a[qy][qx];
+            sweep_C<T, N>(col, gy);
+#pragma unroll
+            for (int qy = 0; qy < N; ++qy) qy_[qy * N + qx] = gy[qy];
+          }
+        }
       }
       if (pass == FIRST) mbar_wait(mbar, parity);  // this group's tables have landed in shared memory
       group_sync<WM>();
-      // ---- phase 4: quadrature loop ------------------------------------------
-      T acc[NC][N];
-#pragma unroll
-      for (int c = 0; c < NC; ++c)
-#pragma unroll
-        for (int i = 0; i < N; ++i) acc[c][i] = T(0);
-#pragma unroll
-      for (int iq = 0; iq < N; ++iq) {
-        T G[NC][3], v[NC], ov[NC], oG[NC][3];
+      // ---- F3 (column): d/dz in registers, quadrature loop, z part of the integration ---------
+      T racc[NC][N];  // values + z-derivative terms of the test side, at the q-points of the column
+      {
+        T val[NC][N], gz[NC][N];
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-          T gy = T(0), gz = T(0);
 #pragma unroll
-          for (int m = 0; m < N; ++m) {
-            gy += cy[m] * bufA[c * CSTR + b * KS + m * JS + iq];
-            gz += cz[m] * bufA[c * CSTR + m * KS + a * JS + iq];
+          for (int kq = 0; kq < N; ++kq) {
+            val[c][kq] = bufQ[qidx(c, 0, kq)];
+            racc[c][kq] = T(0);
           }
-          G[c][0] = gx[c][iq];
-          G[c][1] = gy;
-          G[c][2] = gz;
-          v[c] = val[c][iq];
+          sweep_C<T, N>(val[c], gz[c]);
         }
-        if (pre) {
-          Op::quad_pre(oa, st, active, qs, scr, group, iq, lane, G);
-          continue;
-        }
-        Op::quad(oa, st, active, qs, qs2, scr, group, iq, lane, v, G, ov, oG);
-        if (Op::INTEGRATE) {
+#pragma unroll
+        for (int kq = 0; kq < N; ++kq) {
+          T G[NC][3], v[NC], ov[NC], oG[NC][3];
 #pragma unroll
           for (int c = 0; c < NC; ++c) {
+            v[c] = val[c][kq];
+            G[c][0] = bufQ[qidx(c, 1, kq)];
+            G[c][1] = bufQ[qidx(c, 2, kq)];
+            G[c][2] = gz[c][kq];
+          }
+          if (pre) {
+            Op::quad_pre(oa, st, active, qs, scr, group, kq, lane, G);
+            continue;
+          }
+          Op::quad(oa, st, active, qs, qs2, scr, group, kq, lane, v, G, ov, oG);
+          if (Op::INTEGRATE) {
 #pragma unroll
-            for (int i = 0; i < N; ++i) acc[c][i] += Sh::C(iq, i) * oG[c][0];
-            acc[c][iq] += ov[c];
-            if (active) bufB[c * CSTR + oX + iq] = oG[c][1];
-            if (active) bufC[c * CSTR + oX + iq] = oG[c][2];
+            for (int c = 0; c < NC; ++c) {
+#pragma unroll
+              for (int m = 0; m < N; ++m) racc[c][m] += Sh::C(kq, m) * oG[c][2];
+              racc[c][kq] += ov[c];
+              if (active) {
+                bufQ[qidx(c, 1, kq)] = oG[c][0];
+                bufQ[qidx(c, 2, kq)] = oG[c][1];
+              }
+            }
           }
         }
       }
-      group_sync<WM>();  // everyone is done with bufA (values) and with the staged tables
+      if (Op::INTEGRATE && !pre) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+          for (int kq = 0; kq < N; ++kq)
+            if (active) bufQ[qidx(c, 0, kq)] = racc[c][kq];
+      }
+      group_sync<WM>();  // q-point results are in bufQ; everyone is done with the staged tables
       if (pass == NPASS - 1) {
         parity ^= 1u;
         if (has_next) {
@@ -398,52 +421,67 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
         }
       }
       if (Op::INTEGRATE && !pre) {
-        // issue the next group's gather now; it completes under the transpose half below
+        // issue the next group's gather now; it completes under the integration half below
         T u_next[NC][N];
         if (!DIAG && has_next) gather(nid_next, u_next);
-        // ---- phase 5: y/z derivative transposes, x sweep back ------------------
+        // ---- B2 (plane tasks): transposed x/y derivative and x, y sweeps ------------------------
+#pragma unroll 1
+        for (int t0 = 0; t0 < NT; t0 += Ly::TPG) {
+          const int t = t0 + lane;
+          if (t < NT) {
+            const int tcw = t / (NC * N), tc = (t / N) % NC, tk = t % N;
+            const T *qv = bufQ + Ly::qplane(tcw, tc, 0, tk), *qx_ = bufQ + Ly::qplane(tcw, tc, 1, tk), *qy_ = bufQ + Ly::qplane(tcw, tc, 2, tk);
+            T a[N][N];  // a[qy][qx]
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
+            for (int qy = 0; qy < N; ++qy) {
+              T gx[N];
 #pragma unroll
-          for (int iq = 0; iq < N; ++iq) {
-            T s = acc[c][iq];
+              for (int qx = 0; qx < N; ++qx) {
+                a[qy][qx] = qv[qy * N + qx];
+                gx[qx] = qx_[qy * N + qx];
+              }
 #pragma unroll
-            for (int m = 0; m < N; ++m) {
-              s += cyT[m] * bufB[c * CSTR + b * KS + m * JS + iq];
-              s += czT[m] * bufC[c * CSTR + m * KS + a * JS + iq];
+              for (int qx = 0; qx < N; ++qx)
+#pragma unroll
+                for (int m = 0; m < N; ++m) a[qy][qx] += Sh::C(m, qx) * gx[m];
             }
-            acc[c][iq] = s;
+#pragma unroll
+            for (int qx = 0; qx < N; ++qx) {
+              T gy[N];
+#pragma unroll
+              for (int qy = 0; qy < N; ++qy) gy[qy] = qy_[qy * N + qx];
+#pragma unroll
+              for (int qy = 0; qy < N; ++qy)
+#pragma unroll
+                for (int m = 0; m < N; ++m) a[qy][qx] += Sh::C(m, qy) * gy[m];
+            }
+            T b[N][N];  // x sweep back: b[qy][i]
+#pragma unroll
+            for (int qy = 0; qy < N; ++qy) sweep_S<T, N, true>(a[qy], b[qy]);
+            T *zp = bufZ + Ly::zplane(tcw, tc, tk);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+              T col[N], o[N];
+#pragma unroll
+              for (int qy = 0; qy < N; ++qy) col[qy] = b[qy][i];
+              sweep_S<T, N, true>(col, o);
+#pragma unroll
+              for (int j = 0; j < N; ++j) zp[j * N + i] = o[j];
+            }
           }
-          T o[N];
-          sweep_S<T, N, true>(acc[c], o);
-#pragma unroll
-          for (int i = 0; i < N; ++i)
-            if (active) bufA[c * CSTR + oX + i] = o[i];
         }
         group_sync<WM>();
-        // ---- phase 6 (Y) -------------------------------------------------------
+        // ---- B1 (column): z sweep back + scatter-add -------------------------------------------
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           T col[N], o[N];
 #pragma unroll
-          for (int j = 0; j < N; ++j) col[j] = bufA[c * CSTR + j * JS + oY];
-          sweep_S<T, N, true>(col, o);
-#pragma unroll
-          for (int j = 0; j < N; ++j)
-            if (active) bufB[c * CSTR + j * JS + oY] = o[j];
-        }
-        group_sync<WM>();
-        // ---- phase 7 (Z): z sweep back + scatter-add ---------------------------
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          T col[N], o[N];
-#pragma unroll
-          for (int k = 0; k < N; ++k) col[k] = bufB[c * CSTR + k * KS + oZ];
+          for (int kq = 0; kq < N; ++kq) col[kq] = bufZ[zidx(c, kq)];
           sweep_S<T, N, true>(col, o);
 #pragma unroll
           for (int k = 0; k < N; ++k) {
             if (DIAG)
-              dacc[c][k] += (c == pc && k == pk && t == pt) ? o[k] : T(0);
+              dacc[c][k] += (c == pc && k == pk && ji == pt) ? o[k] : T(0);
             else if (!(nid[k] & node_flag(c)))
               atomicAdd(A.dst + (size_t)c * A.cstride + (nid[k] & NODE_MASK), o[k]);
           }
@@ -454,7 +492,7 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
 #pragma unroll
             for (int k = 0; k < N; ++k) u[c][k] = u_next[c][k];
         }
-        // the next pass's / group's first barrier orders these bufB reads before its phase-2 writes
+        group_sync<WM>();  // bufZ is free for the next pass / group
       }
     }  // pass
     if (DIAG) {

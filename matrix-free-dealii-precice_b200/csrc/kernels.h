@@ -6,7 +6,7 @@
 
 namespace b200mf {
 
-void shape_tables(const double **hd, const float **hf);  // [MAXN+1][2][MAXN*MAXN], b200mf.cu
+void shape_tables(const double **hd, const float **hf);  // [MAXN+1][3][MAXN*MAXN], b200mf.cu
 
 // cell-group range [g0, g1) on `stream`
 template <typename T>

@@ -261,6 +261,26 @@ def test_laplace_fp32():
     assert rel(out, ref) < TOL32
 
 
+# enough cells that every persistent block walks several cell groups: exercises the software pipeline
+# (TMA staging of the next group's tables, register prefetch of its DoFs) that small meshes never reach
+PIPE_CELLS = {1: (40, 40, 36), 2: (20, 20, 20), 3: (24, 20, 16), 4: (12, 12, 10), 5: (10, 8, 8), 6: (8, 8, 8)}
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6])
+def test_nh_vmult_many_groups_per_block(p):
+    m = make_mesh(p, PIPE_CELLS[p])
+    u = displacement(m)
+    src = np.random.default_rng(p).uniform(-1, 1, 3 * m.n_nodes)
+    ref = np.zeros_like(src)
+    level = "scalar_referential" if p % 2 else "tensor2"
+    oracle_nh(m, u, level).vmult(ref, src)
+    mf, op = gpu_nh(m, u, level=level)
+    s, d = DeviceVector(mf, src), DeviceVector(mf)
+    for _ in range(2):
+        op.vmult(d, s)
+        assert rel(d.download(), ref) < TOL64
+
+
 def test_error_behaviour():
     m = make_mesh(2, (2, 2, 2))
     mf = MatrixFree.from_mesh(m, 3)
