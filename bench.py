@@ -36,6 +36,11 @@ METRIC = "nh_tangent_vmult_dofs_per_s"
 QPOINT_VALUES = {"tensor2": 18, "scalar_referential": 14, "tensor4": 53, "tensor4_ns": 91, "form0": 20}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the cell-loop kernel from the committed
+# `ncu --set full` captures (profiles/r01_v3_ncu_summary.md), keyed by (degree, variant, dtype) at the default mesh
+NCU_TRAFFIC = {}
+
+
 def algorithmic_bytes_per_cell(p, esize=8, variant="tensor2"):
     """src read + dst write per unique DoF, one uint32 per node, and the q-point
     table the kernel of this variant actually streams."""
@@ -69,54 +74,70 @@ def build_problem(p, ncell_dir, dtype="f64", comm=None, caching="tensor2", formu
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region (NVML from a thread, ~1 ms period;
+    the timed region of the default run is only tens of ms, too short for `nvidia-smi -lms`)."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.index, self.stop, self.thread, self.h, self.max_mhz = [], index, False, None, None, None
+        try:
+            import pynvml
+
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a list of indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[index])
+                except Exception:
+                    phys = index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def _sample(self):
+        nv = self.nv
+        mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        try:
+            bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+            bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        return mhz, bits
+
+    def _run(self):
+        while not self.stop:
+            try:
+                self.rows.append(self._sample())
+            except Exception:
+                break
+            time.sleep(0.001)
 
     def __enter__(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+        if self.h is not None:
+            self.thread = threading.Thread(target=self._run, daemon=True)
             self.thread.start()
-        except Exception:
-            self.proc = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
     def __exit__(self, *a):
-        if self.proc:
-            time.sleep(0.15)
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
+        self.stop = True
+        if self.thread:
+            self.thread.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], 0.0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        sm = [r[0] for r in self.rows]
+        bits = 0
         for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
-                for nm, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+            bits |= r[1]
+        reasons = sorted(k for k, m in self.REASONS.items() if bits & m)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(sm), "how": "NVML clock + clocks-event-reasons polled every ~1 ms inside the timed region"}
 
 
-def cpu_oracle_rate(p, ncell_dir, min_seconds=10.0, max_reps=50):
+def cpu_oracle_rate(p, ncell_dir, min_seconds=10.0, max_reps=100000):
     """DoFs/s of the CPU oracle port (oracle/mf_oracle.c, OpenMP over cells, all host threads)."""
     from b200mf.mesh import StructuredMesh, synthetic_displacement
     from oracle import c_oracle as CO
@@ -208,7 +229,7 @@ def main():
     args = ap.parse_args()
     p = args.degree
     if args.cpu_cells is None:
-        args.cpu_cells = {1: 64, 2: 40, 3: 28, 4: 20, 5: 16, 6: 14}[p]
+        args.cpu_cells = {1: 128, 2: 64, 3: 48, 4: 36, 5: 28, 6: 24}[p]
     if args.impl == "reference":
         return run_reference(args)
 
@@ -251,6 +272,7 @@ def main():
         op.vmult(dst, src)
     barrier()
     launches0 = L.b200mf_launch_count()
+    mf.time_kernels(True)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     with ClockSampler(local_rank) as clocks:
         ev[0].record(stream)
@@ -259,6 +281,9 @@ def main():
             ev[i + 1].record(stream)
         barrier()
     launches = L.b200mf_launch_count() - launches0
+    kernel_ms_total, kernel_launches = mf.kernel_time()
+    mf.time_kernels(False)
+    kernel_ms = kernel_ms_total / max(kernel_launches, 1)
     total_ms = ev[0].elapsed_time(ev[-1])
     if dist is not None:
         t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
@@ -280,11 +305,16 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     alg_bytes = algorithmic_bytes_per_cell(p, es, variant) * m.n_cells  # per GPU (per launch of the cell kernel)
-    achieved = alg_bytes / (ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": f"cell_loop_kernel<{'double' if es == 8 else 'float'}, {p + 1}, NHOp<{variant}>>",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": NCU_TRAFFIC.get((p, variant, args.dtype)) if args.cells is None else None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
+                "algorithmic_bytes_per_launch": alg_bytes,
                 "algorithmic_bytes_per_dof": algorithmic_bytes_per_cell(p, es, variant) / (3 * p**3),
-                "timed": "whole vmult step (memset + cell loop + constrained fix-up), CUDA events"}
+                "kernel_ms": kernel_ms, "kernel_launches_timed": int(kernel_launches), "kernel_share_of_step": kernel_ms / ms,
+                "frac_whole_step": alg_bytes / (ms * 1e-3) / 1e9 / peak,
+                "timed": "cell-loop kernel alone, CUDA events on its stream inside the timed region (one launch per step)"}
 
     # ---- e2e: host buffers through the C-ABI host entry point ----------------------------------
     e2e = None

@@ -101,6 +101,10 @@ int b200mf_ctx_destroy(b200mf_ctx *ctx);
 /* all work of this context (and of operators built on it) is enqueued on `cuda_stream` (cudaStream_t; NULL = default) */
 int b200mf_ctx_set_stream(b200mf_ctx *ctx, void *cuda_stream);
 int b200mf_ctx_synchronize(b200mf_ctx *ctx);
+/* measurement aid: with on != 0 every cell-loop launch is bracketed by CUDA events on the launching stream;
+ * b200mf_ctx_kernel_time synchronises and returns their summed duration and the number of launches since `on` */
+int b200mf_ctx_time_kernels(b200mf_ctx *ctx, int on);
+int b200mf_ctx_kernel_time(b200mf_ctx *ctx, double *total_ms, int64_t *n_launches);
 int64_t b200mf_ctx_n_dofs(const b200mf_ctx *ctx);
 size_t b200mf_ctx_memory_consumption(const b200mf_ctx *ctx); /* MatrixFree::memory_consumption, mf_elasticity.h:982-990 */
 

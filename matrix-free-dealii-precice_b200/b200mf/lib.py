@@ -69,6 +69,8 @@ SIGNATURES = {
     "b200mf_ctx_destroy": (_i32, [_vp]),
     "b200mf_ctx_set_stream": (_i32, [_vp, _vp]),
     "b200mf_ctx_synchronize": (_i32, [_vp]),
+    "b200mf_ctx_time_kernels": (_i32, [_vp, _i32]),
+    "b200mf_ctx_kernel_time": (_i32, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "b200mf_ctx_n_dofs": (_i64, [_vp]),
     "b200mf_ctx_memory_consumption": (C.c_size_t, [_vp]),
     "b200mf_vec_create": (_i32, [_vp, _PP]),

@@ -136,6 +136,16 @@ class MatrixFree:
     def synchronize(self):
         _l.check(_l.load().b200mf_ctx_synchronize(self.h))
 
+    def time_kernels(self, on=True):
+        """Bracket every cell-loop launch with CUDA events on the launching stream (bench.py roofline)."""
+        _l.check(_l.load().b200mf_ctx_time_kernels(self.h, int(on)))
+
+    def kernel_time(self):
+        """(summed ms, launches) of the cell-loop kernels since time_kernels(True)."""
+        ms, n = C.c_double(0), C.c_int64(0)
+        _l.check(_l.load().b200mf_ctx_kernel_time(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def memory_consumption(self):
         return _l.load().b200mf_ctx_memory_consumption(self.h)
 

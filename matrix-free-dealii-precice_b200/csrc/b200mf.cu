@@ -548,6 +548,10 @@ extern "C" int b200mf_ctx_destroy(b200mf_ctx *c) {
   free_partitioner(c);
   delete c->h_ext2int;
   delete c->h_cell_nodes;
+  if (c->kernel_events) {
+    for (cudaEvent_t e : *c->kernel_events) cudaEventDestroy(e);
+    delete c->kernel_events;
+  }
   delete c;
   return 0;
 }
@@ -562,6 +566,42 @@ extern "C" int b200mf_ctx_synchronize(b200mf_ctx *c) {
   B2_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }
+// Measurement aid (bench.py roofline): CUDA events on the launching stream around every cell-loop launch.
+extern "C" int b200mf_ctx_time_kernels(b200mf_ctx *c, int on) {
+  if (!c) return set_error(B200MF_ERR_ARG, "null ctx");
+  if (c->kernel_events) {
+    for (cudaEvent_t e : *c->kernel_events) cudaEventDestroy(e);
+    delete c->kernel_events;
+    c->kernel_events = nullptr;
+  }
+  if (on) c->kernel_events = new std::vector<cudaEvent_t>();
+  return 0;
+}
+extern "C" int b200mf_ctx_kernel_time(b200mf_ctx *c, double *total_ms, int64_t *n_launches) {
+  if (!c || !total_ms || !n_launches) return set_error(B200MF_ERR_ARG, "null argument");
+  *total_ms = 0;
+  *n_launches = 0;
+  if (!c->kernel_events) return 0;
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  for (size_t i = 0; i + 1 < c->kernel_events->size(); i += 2) {
+    float ms = 0;
+    B2_CUDA(cudaEventSynchronize((*c->kernel_events)[i + 1]));
+    B2_CUDA(cudaEventElapsedTime(&ms, (*c->kernel_events)[i], (*c->kernel_events)[i + 1]));
+    *total_ms += ms;
+    ++*n_launches;
+  }
+  return 0;
+}
+namespace b200mf {
+int kernel_event(b200mf_ctx *c, cudaStream_t s) {
+  if (!c->kernel_events) return 0;
+  cudaEvent_t e;
+  B2_CUDA(cudaEventCreate(&e));
+  B2_CUDA(cudaEventRecord(e, s));
+  c->kernel_events->push_back(e);
+  return 0;
+}
+}  // namespace b200mf
 extern "C" int64_t b200mf_ctx_n_dofs(const b200mf_ctx *c) { return c ? c->n_dofs : -1; }
 extern "C" size_t b200mf_ctx_memory_consumption(const b200mf_ctx *c) { return c ? c->bytes : 0; }
 

@@ -185,12 +185,20 @@ __device__ __forceinline__ void sweep_C(const T (&in)[N], T (&out)[N]) {
 //       qs / qs2 / scr: shared-memory tables, field f of q-point (kq, lane) at qs[(f*N + kq)*L + lane];
 //       G[c][d] = d u_c / d xi_d (reference gradient), oG likewise for the test-function side
 //
-// DIAG = true turns the loop into MatrixFreeTools::compute_diagonal: the cell
-// operator is applied to every local unit vector and entry i of the result is kept.
-template <typename T, int N, class Op>
+// DIAG = true computes what MatrixFreeTools::compute_diagonal computes - entry i of the cell
+// operator applied to the local unit vector e_i - without the 3 N^3 operator applications per cell it costs
+// in deal.II.  The q-point operation is a linear map (value, d/dxi_1..3) -> (value, d/dxi_1..3); for the unit
+// vector of component c only its 4x4 block Q_c(q) matters (obtained generically from four Op::quad calls on
+// unit inputs), and
+//     diag_i = sum_q sum_{a,b} Q_c(q)[a][b] Phi_a(q,i) Phi_b(q,i),   Phi_0 = S S S, Phi_1 = D S S, Phi_2 = S D S, Phi_3 = S S D
+// factorises direction by direction into sweeps with the entry-wise products S.S, S.D, D.D of the 1-D
+// matrices: 10 symmetric terms collapse to 6 fields after the z sweep, 3 after y, 1 after x.
+template <typename T, int N, class Op, bool DIAG = false>
 struct KernelSmem {
   using Ly = Layout<N, Op::NC, sizeof(T) / 4>;
-  static constexpr size_t BUF_BYTES = round_up((size_t)Ly::GROUP_ELEMS * sizeof(T), 16);
+  static constexpr int DIAG_ELEMS = Ly::CPG * 6 * Ly::N3;  // diagonal pass: 6 coefficient fields per cell (see below)
+  static constexpr int BUF_ELEMS = (DIAG && DIAG_ELEMS > Ly::GROUP_ELEMS) ? DIAG_ELEMS : Ly::GROUP_ELEMS;
+  static constexpr size_t BUF_BYTES = round_up((size_t)BUF_ELEMS * sizeof(T), 16);
   static constexpr size_t ST1_BYTES = Ly::table_stride(Op::NF_IN) * sizeof(T);
   static constexpr size_t ST2_BYTES = Op::NF_IN2 ? Ly::table_stride(Op::NF_IN2) * sizeof(T) : 0;
   static constexpr size_t SCR_BYTES = Op::NF_SCRATCH ? Ly::table_stride(Op::NF_SCRATCH) * sizeof(T) : 0;  // pre-pass -> main pass
@@ -203,7 +211,7 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
   constexpr int NC = Op::NC;
   using Ly = Layout<N, NC, sizeof(T) / 4>;
   using Sh = Shape<T, N>;
-  using KS_ = KernelSmem<T, N, Op>;
+  using KS_ = KernelSmem<T, N, Op, DIAG>;
   constexpr int N2 = Ly::N2, L = Ly::L, PL = Ly::PL, NT = Ly::NT;
   constexpr bool WM = Ly::WARP_MODE;
   static_assert(WM || GPB == 1, "block mode runs one group per block");
@@ -258,6 +266,18 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
   auto zidx = [&](int c, int kq) { return zoff + c * Ly::ZCOMP + kq * PL; };
   auto qidx = [&](int c, int f, int kq) { return qoff + c * Ly::QCOMP + f * Ly::QFIELD + kq * PL; };
 
+  // diagonal pass: this thread's columns of S and D (row index q) for its j (y sweep) and i (x sweep)
+  T sy[DIAG ? N : 1], dy[DIAG ? N : 1], sx[DIAG ? N : 1], dx[DIAG ? N : 1];
+  if constexpr (DIAG) {
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+      sy[q] = Sh::S(q, ji / N);
+      dy[q] = Sh::D(q, ji / N);
+      sx[q] = Sh::S(q, ji % N);
+      dx[q] = Sh::D(q, ji % N);
+    }
+  }
+
   const int64_t gstep = (int64_t)gridDim.x * GPB;
   int64_t group = A.group_begin + (int64_t)blockIdx.x * GPB + gib;
   unsigned parity = 0;
@@ -277,27 +297,124 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
     typename Op::CellState st;
     Op::cell_begin(oa, group * Ly::CPG + cw, active, st);
 
-    T dacc[NC][N];
-    if (DIAG) {
-#pragma unroll
-      for (int c = 0; c < NC; ++c)
-#pragma unroll
-        for (int k = 0; k < N; ++k) dacc[c][k] = T(0);
-    }
     if constexpr (Op::STORE_DOFS) Op::store_dofs(oa, group, lane, active, u);
-    constexpr int NPASS = DIAG ? NC * Ly::N3 : 1;
+    constexpr int NPASS = 1;
     constexpr int FIRST = Op::PRE ? -1 : 0;
 #pragma unroll 1
     for (int pass = FIRST; pass < NPASS; ++pass) {
       const bool pre = Op::PRE && pass < 0;
-      const int pc = pass / Ly::N3, pk = (pass / N2) % N, pt = pass % N2;  // unit vector (component, k, column)
-      // ---- F1 (column): z sweep of the nodal column, planes to bufZ ---------------------------
-      if (DIAG) {
+      if constexpr (DIAG) {
+        if (!pre) {
+          // ---- diagonal pass ---------------------------------------------------------------------
+          if (pass == FIRST) {
+            if (has_next) load_nid(gnext, nid_next);
+            mbar_wait(mbar, parity);
+          }
+          T *db = bufZ + cw * (6 * Ly::N3);  // [field][k3][j][i] of this thread's cell
+          const int tj = ji / N, ti = ji % N;
+#pragma unroll 1
+          for (int c = 0; c < NC; ++c) {
+            T zc[6][N];
 #pragma unroll
-        for (int k = 0; k < N; ++k)
+            for (int f = 0; f < 6; ++f)
 #pragma unroll
-          for (int c = 0; c < NC; ++c) u[c][k] = (!(nid[k] & node_flag(c)) && c == pc && k == pk && ji == pt) ? T(1) : T(0);
+              for (int k = 0; k < N; ++k) zc[f][k] = T(0);
+#pragma unroll 1
+            for (int kq = 0; kq < N; ++kq) {
+              T Q[4][4];  // Q[a][b]: output a (value, d/dxi_1..3 of the test side) for unit input b
+#pragma unroll
+              for (int b = 0; b < 4; ++b) {
+                T v[NC], G[NC][3], ov[NC], oG[NC][3];
+#pragma unroll
+                for (int cc = 0; cc < NC; ++cc) {
+                  v[cc] = (cc == c && b == 0) ? T(1) : T(0);
+#pragma unroll
+                  for (int d = 0; d < 3; ++d) G[cc][d] = (cc == c && b == d + 1) ? T(1) : T(0);
+                }
+                Op::quad(oa, st, active, qs, qs2, scr, group, kq, lane, v, G, ov, oG);
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                  T o = T(0);
+#pragma unroll
+                  for (int cc = 0; cc < NC; ++cc) o += (cc == c) ? (a == 0 ? ov[cc] : oG[cc][a - 1]) : T(0);
+                  Q[a][b] = o;
+                }
+              }
+#pragma unroll
+              for (int k = 0; k < N; ++k) {
+                const T sv = Sh::S(kq, k), dv = Sh::D(kq, k);
+                const T ss = sv * sv, sd = sv * dv, dd = dv * dv;
+                zc[0][k] += ss * Q[0][0] + dd * Q[3][3] + sd * (Q[0][3] + Q[3][0]);
+                zc[1][k] += ss * (Q[0][1] + Q[1][0]) + sd * (Q[1][3] + Q[3][1]);
+                zc[2][k] += ss * (Q[0][2] + Q[2][0]) + sd * (Q[2][3] + Q[3][2]);
+                zc[3][k] += ss * Q[1][1];
+                zc[4][k] += ss * Q[2][2];
+                zc[5][k] += ss * (Q[1][2] + Q[2][1]);
+              }
+            }
+            if (active) {
+#pragma unroll
+              for (int f = 0; f < 6; ++f)
+#pragma unroll
+                for (int k = 0; k < N; ++k) db[(f * N + k) * N2 + ji] = zc[f][k];
+            }
+            group_sync<WM>();
+            // y sweep: thread (k2 = tj, i) contracts over q2; x types left: 0 S.S, 1 S.D, 2 D.D
+            T yc[3][N];
+#pragma unroll
+            for (int k = 0; k < N; ++k) yc[0][k] = yc[1][k] = yc[2][k] = T(0);
+            if (active) {
+#pragma unroll
+              for (int q2 = 0; q2 < N; ++q2) {
+                const T sv = sy[q2], dv = dy[q2];
+                const T ss = sv * sv, sd = sv * dv, dd = dv * dv;
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                  const T *z = db + k * N2 + q2 * N + ti;
+                  yc[0][k] += ss * z[0 * Ly::N3] + sd * z[2 * Ly::N3] + dd * z[4 * Ly::N3];
+                  yc[1][k] += ss * z[1 * Ly::N3] + sd * z[5 * Ly::N3];
+                  yc[2][k] += ss * z[3 * Ly::N3];
+                }
+              }
+            }
+            group_sync<WM>();
+            if (active) {
+#pragma unroll
+              for (int f = 0; f < 3; ++f)
+#pragma unroll
+                for (int k = 0; k < N; ++k) db[(f * N + k) * N2 + ji] = yc[f][k];
+            }
+            group_sync<WM>();
+            // x sweep: thread (k2, k1 = ti) contracts over q1, then adds its N diagonal entries of component c
+            if (active) {
+              T out[N];
+#pragma unroll
+              for (int k = 0; k < N; ++k) out[k] = T(0);
+#pragma unroll
+              for (int q1 = 0; q1 < N; ++q1) {
+                const T sv = sx[q1], dv = dx[q1];
+                const T ss = sv * sv, sd = sv * dv, dd = dv * dv;
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                  const T *y = db + k * N2 + tj * N + q1;
+                  out[k] += ss * y[0 * Ly::N3] + sd * y[1 * Ly::N3] + dd * y[2 * Ly::N3];
+                }
+              }
+#pragma unroll
+              for (int k = 0; k < N; ++k)
+                if (!(nid[k] & (1u << (29 + c)))) atomicAdd(A.dst + (size_t)c * A.cstride + (nid[k] & NODE_MASK), out[k]);
+            }
+            group_sync<WM>();
+          }
+          parity ^= 1u;
+          if (has_next) {
+            fence_proxy_async();
+            stage(gnext);
+          }
+          continue;
+        }
       }
+      // ---- F1 (column): z sweep of the nodal column, planes to bufZ ---------------------------
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         T o[N];
@@ -480,9 +597,7 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
           sweep_S<T, N, true>(col, o);
 #pragma unroll
           for (int k = 0; k < N; ++k) {
-            if (DIAG)
-              dacc[c][k] += (c == pc && k == pk && ji == pt) ? o[k] : T(0);
-            else if (!(nid[k] & node_flag(c)))
+            if (!(nid[k] & node_flag(c)))
               atomicAdd(A.dst + (size_t)c * A.cstride + (nid[k] & NODE_MASK), o[k]);
           }
         }
@@ -495,13 +610,6 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
         group_sync<WM>();  // bufZ is free for the next pass / group
       }
     }  // pass
-    if (DIAG) {
-#pragma unroll
-      for (int c = 0; c < NC; ++c)
-#pragma unroll
-        for (int k = 0; k < N; ++k)
-          if (!(nid[k] & node_flag(c))) atomicAdd(A.dst + (size_t)c * A.cstride + (nid[k] & NODE_MASK), dacc[c][k]);
-    }
     if (!Op::INTEGRATE && has_next) gather(nid_next, u);  // evaluation-only ops (cache): plain prefetch
 #pragma unroll
     for (int k = 0; k < N; ++k) nid[k] = nid_next[k];

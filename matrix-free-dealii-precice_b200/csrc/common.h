@@ -45,6 +45,8 @@ struct Shape1D {
 };
 void compute_shape_1d(int p, Shape1D &out);
 
+int kernel_event(b200mf_ctx *c, cudaStream_t s);  // b200mf.cu
+
 // comm.cu
 void free_partitioner(b200mf_ctx *c);
 int update_ghost_values(b200mf_ctx *c, void *vec);
@@ -75,5 +77,6 @@ struct b200mf_ctx {
   b200mf::Shape1D shape;
   b200mf_partitioner *part;         // nullptr on a single rank
   std::vector<int64_t> *h_ext2int;  // caller index -> internal index, nullptr when identity
+  std::vector<cudaEvent_t> *kernel_events;  // non-null: event pairs recorded around every cell-loop launch (b200mf_ctx_time_kernels)
   std::vector<uint32_t> *h_cell_nodes;  // [n_cells][N^3] node | constrained flags (bits 29..31), caller's cell order (MG transfer set-up)
 };

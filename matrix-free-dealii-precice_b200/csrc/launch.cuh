@@ -27,7 +27,7 @@ static int launch_variant(const b200mf_ctx *ctx, const T *src, T *dst, const typ
                           cudaStream_t stream) {
   using Ly = Layout<N, Op::NC, sizeof(T) / 4>;
   auto kern = cell_loop_kernel<T, N, Op, GPB, DIAG, MINB>;
-  const size_t smem = (size_t)GPB * KernelSmem<T, N, Op>::GROUP_BYTES;
+  const size_t smem = (size_t)GPB * KernelSmem<T, N, Op, DIAG>::GROUP_BYTES;
   static int occ = 0;  // per instantiation
   B2_TRY(ensure_shape_constants());
   if (occ == 0) {
@@ -55,8 +55,10 @@ static int launch_variant(const b200mf_ctx *ctx, const T *src, T *dst, const typ
   const int64_t want = (g1 - g0 + GPB - 1) / GPB;
   const int64_t cap = (int64_t)ctx->sm_count * occ;
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min(want, cap));
+  B2_TRY(kernel_event(const_cast<b200mf_ctx *>(ctx), stream));
   kern<<<grid, Ly::TPG * GPB, smem, stream>>>(A, oa);
   B2_LAUNCHED();
+  B2_TRY(kernel_event(const_cast<b200mf_ctx *>(ctx), stream));
   return 0;
 }
 

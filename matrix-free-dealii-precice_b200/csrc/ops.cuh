@@ -29,7 +29,7 @@ enum { QF4_C2 = 10, QF4_T = 11, QF_TENSOR4_COUNT = 17 };
 enum { MF_K = 0, MF_W = 9, MF_COUNT = 10 };
 
 __host__ __device__ constexpr int nhv_staged_fields(int v) {
-  return v == NHV_TENSOR2 ? QF_TENSOR2_COUNT : v == NHV_FORM0 ? QF_FORM0_COUNT : v == NHV_TENSOR4 ? QF_TENSOR4_COUNT : MF_COUNT;
+  return v == NHV_TENSOR2 ? (int)QF_TENSOR2_COUNT : v == NHV_FORM0 ? (int)QF_FORM0_COUNT : v == NHV_TENSOR4 ? (int)QF_TENSOR4_COUNT : (int)MF_COUNT;
 }
 __host__ __device__ constexpr int nhv_big_fields(int v) { return v == NHV_TENSOR4 ? 36 : v == NHV_TENSOR4_NS ? 81 : 0; }
 __host__ __device__ constexpr bool nhv_deformed(int v) { return v == NHV_TENSOR2 || v == NHV_FORM0 || v == NHV_TENSOR4; }
