@@ -283,7 +283,7 @@ def main():
     launches = L.b200mf_launch_count() - launches0
     kernel_ms_total, kernel_launches = mf.kernel_time()
     mf.time_kernels(False)
-    kernel_ms = kernel_ms_total / max(kernel_launches, 1)
+    kernel_ms = kernel_ms_total / args.steps  # all cell-loop launches of one step (1 on one rank; interior/boundary/interior when partitioned)
     total_ms = ev[0].elapsed_time(ev[-1])
     if dist is not None:
         t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
@@ -314,7 +314,31 @@ def main():
                 "algorithmic_bytes_per_dof": algorithmic_bytes_per_cell(p, es, variant) / (3 * p**3),
                 "kernel_ms": kernel_ms, "kernel_launches_timed": int(kernel_launches), "kernel_share_of_step": kernel_ms / ms,
                 "frac_whole_step": alg_bytes / (ms * 1e-3) / 1e9 / peak,
-                "timed": "cell-loop kernel alone, CUDA events on its stream inside the timed region (one launch per step)"}
+                "timed": "cell-loop kernel alone, CUDA events on its stream inside the timed region "
+                         f"({kernel_launches // max(args.steps, 1)} launch(es) per step)"}
+
+    # ---- N > 1: how much of the two ghost exchanges is exposed -----------
+    exchange = None
+    if world > 1:
+        def timed(mode, k=10):
+            mf.set_overlap(mode)
+            for _ in range(3):
+                op.vmult(dst, src)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(k):
+                op.vmult(dst, src)
+            e1.record(stream)
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1) / k], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        t_serial, t_none = timed(0), timed(-1)
+        mf.set_overlap(1)
+        exchange = {"ms_overlapped": ms, "ms_serial_exchange": t_serial, "ms_no_exchange": t_none,
+                    "exposed_ms": ms - t_none, "exposed_ms_without_overlap": t_serial - t_none}
 
     # ---- e2e: host buffers through the C-ABI host entry point ----------------------------------
     e2e = None
@@ -374,6 +398,8 @@ def main():
             "data": "synthetic", "config": workload_config(p, nc, world, args.caching, args.formulation), "roofline": roofline, "cpu_baseline": cpu,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(),
         }
+        if exchange:
+            line["ghost_exchange"] = exchange
         if sweep:
             line["sweep"] = sweep
         print(json.dumps(line), flush=True)

@@ -105,6 +105,12 @@ int b200mf_ctx_synchronize(b200mf_ctx *ctx);
  * b200mf_ctx_kernel_time synchronises and returns their summed duration and the number of launches since `on` */
 int b200mf_ctx_time_kernels(b200mf_ctx *ctx, int on);
 int b200mf_ctx_kernel_time(b200mf_ctx *ctx, double *total_ms, int64_t *n_launches);
+/* multi-rank contexts: 1 (default) hides update_ghost_values / compress(add) of vmult behind the interior cells on a
+ * second stream, 0 runs exchange -> cells -> exchange on one stream as the reference does (mf_nh_operator.h:598-620),
+ * -1 skips the exchanges (rank-local result; only for measuring the exposed exchange time) */
+int b200mf_ctx_set_overlap(b200mf_ctx *ctx, int on);
+/* 1: every cell is affine (one Jacobian per cell, as deal.II's MappingInfo compresses Cartesian/affine cells), 0: general */
+int b200mf_ctx_cell_type(const b200mf_ctx *ctx);
 int64_t b200mf_ctx_n_dofs(const b200mf_ctx *ctx);
 size_t b200mf_ctx_memory_consumption(const b200mf_ctx *ctx); /* MatrixFree::memory_consumption, mf_elasticity.h:982-990 */
 
@@ -185,6 +191,14 @@ int b200mf_nh_precondition_jacobi(b200mf_nh *op, void *dst_dvec, const void *src
 int b200mf_nh_el(b200mf_nh *op, int64_t row, double *value);
 int64_t b200mf_nh_m(const b200mf_nh *op); /* m() == n(), mf_nh_operator.h:295-309 */
 size_t b200mf_nh_memory_consumption(const b200mf_nh *op); /* mf_nh_operator.h:241-260 */
+/* Cell part of Solid::assemble_residual, fast FEEvaluation path (mf_elasticity.h:1764-1846):
+ *   rhs += int [ -tau(F) F^-T : Grad v + rho (body_force - acceleration) . v ] dV,   F = I + Grad total_displacement,
+ * both vectors read without constraints (read_dof_values_plain), constrained rows of rhs not written.  The caller
+ * zeroes rhs before (:1655), adds the interface-traction faces (:1849-1897, preCICE data) and then calls
+ * b200mf_vec_compress_add (:1899) and b200mf_vec_set_zero_constrained (:1905).  Usable right after
+ * b200mf_nh_create (needs no cache()).  *n_nonpositive_detF as in b200mf_nh_cache. */
+int b200mf_nh_assemble_residual(b200mf_nh *op, void *rhs_dvec, const void *total_displacement_dvec, const void *acceleration_dvec,
+                                const double body_force[3], int64_t *n_nonpositive_detF);
 /* test hook: copy one cached quadrature table to the host in natural order [n_cells][nq^3].
  * field ids: see B200MF_QF_* */
 int b200mf_nh_qdata_host(b200mf_nh *op, int field, double *out);
@@ -217,6 +231,7 @@ int b200mf_vec_dot(b200mf_ctx *ctx, const void *a_dvec, const void *b_dvec, doub
 int b200mf_vec_l2_norm(b200mf_ctx *ctx, const void *a_dvec, double *out);
 int b200mf_vec_sadd(b200mf_ctx *ctx, void *y_dvec, double s, double a, const void *x_dvec); /* y = s*y + a*x */
 int b200mf_vec_set_zero(b200mf_ctx *ctx, void *y_dvec);
+int b200mf_vec_set_zero_constrained(b200mf_ctx *ctx, void *y_dvec); /* AffineConstraints::set_zero, mf_elasticity.h:1905, 2059 */
 /* copy between two contexts built on the same mesh and numbering but different number types
  * (double system vector <-> float level vector: MGTransferMatrixFree::copy_to_mg / copy_from_mg,
  * level displacement mf_elasticity.h:314, 920-922) */

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200mf.so")
+LIB_PATH = os.environ.get("B200MF_LIBRARY") or os.path.join(_HERE, "libb200mf.so")  # override: tuning builds only
 
 F64, F32 = 0, 1
 CACHING = {"scalar_referential": 0, "tensor2": 1, "tensor4": 2, "tensor4_ns": 3}
@@ -71,8 +71,12 @@ SIGNATURES = {
     "b200mf_ctx_synchronize": (_i32, [_vp]),
     "b200mf_ctx_time_kernels": (_i32, [_vp, _i32]),
     "b200mf_ctx_kernel_time": (_i32, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "b200mf_ctx_set_overlap": (_i32, [_vp, _i32]),
+    "b200mf_ctx_cell_type": (_i32, [_vp]),
     "b200mf_ctx_n_dofs": (_i64, [_vp]),
     "b200mf_ctx_memory_consumption": (C.c_size_t, [_vp]),
+    "b200mf_nh_assemble_residual": (_i32, [_vp, _vp, _vp, _vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "b200mf_vec_set_zero_constrained": (_i32, [_vp, _vp]),
     "b200mf_vec_create": (_i32, [_vp, _PP]),
     "b200mf_vec_destroy": (_i32, [_vp, _vp]),
     "b200mf_vec_upload": (_i32, [_vp, _vp, _vp]),

@@ -136,6 +136,13 @@ class MatrixFree:
     def synchronize(self):
         _l.check(_l.load().b200mf_ctx_synchronize(self.h))
 
+    def set_overlap(self, on=True):
+        """Hide the ghost exchanges of vmult behind the interior cells (default on multi-rank contexts)."""
+        _l.check(_l.load().b200mf_ctx_set_overlap(self.h, int(on)))
+
+    def all_cells_affine(self):
+        return _l.load().b200mf_ctx_cell_type(self.h) == 1
+
     def time_kernels(self, on=True):
         """Bracket every cell-loop launch with CUDA events on the launching stream (bench.py roofline)."""
         _l.check(_l.load().b200mf_ctx_time_kernels(self.h, int(on)))
@@ -180,6 +187,10 @@ class DeviceVector:
         out = np.empty(self.mf.n_dofs, dtype=np.float64)
         _l.check(_l.load().b200mf_vec_download_f64(self.mf.h, _ptr(out), self.ptr))
         return out
+
+    def set_zero_constrained(self):
+        """AffineConstraints::set_zero (mf_elasticity.h:1905, 2059)."""
+        _l.check(_l.load().b200mf_vec_set_zero_constrained(self.mf.h, self.ptr))
 
     def update_ghost_values(self):
         _l.check(_l.load().b200mf_vec_update_ghost_values(self.mf.h, self.ptr))
@@ -257,6 +268,13 @@ class NeoHookOperator:
         else:
             d = np.ascontiguousarray(self.displacement, dtype=np.float64)
             _l.check(L.b200mf_nh_cache_host(self.h, _ptr(d), C.byref(bad)))
+
+    def assemble_residual(self, rhs, total_displacement, acceleration, body_force=(0.0, 0.0, 0.0)):
+        """Cell part of Solid::assemble_residual, fast path (mf_elasticity.h:1764-1846): rhs += R_cells(u, a) on
+        DeviceVectors; the caller zeroes rhs, adds interface faces, then compress_add() and set_zero_constrained()."""
+        bf = (C.c_double * 3)(*[float(x) for x in body_force])
+        bad = C.c_int64(0)
+        _l.check(_l.load().b200mf_nh_assemble_residual(self.h, _dv(rhs), _dv(total_displacement), _dv(acceleration), bf, C.byref(bad)))
 
     def vmult(self, dst, src):
         L = _l.load()

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <numeric>
@@ -130,8 +131,8 @@ void compute_shape_1d(int p, Shape1D &out) {
 
 // host copies of the 1-D matrices every kernel translation unit uploads into its own __constant__ bank (launch.cuh)
 void shape_tables(const double **hd_out, const float **hf_out) {
-  static double hd[MAXN + 1][3][MAXN * MAXN];
-  static float hf[MAXN + 1][3][MAXN * MAXN];
+  static double hd[MAXN + 1][SHAPE_ROWS][MAXN * MAXN];
+  static float hf[MAXN + 1][SHAPE_ROWS][MAXN * MAXN];
   static bool done = false;
   if (!done) {
     memset(hd, 0, sizeof hd);
@@ -143,9 +144,10 @@ void shape_tables(const double **hd_out, const float **hf_out) {
         hd[N][1][i] = s.C[i];
         hd[N][2][i] = s.D[i];  // derivative of the nodal basis at the Gauss points (= C S)
       }
+      for (int q = 0; q < N; ++q) hd[N][3][q] = s.w[q];
     }
     for (int N = 0; N <= MAXN; ++N)
-      for (int m = 0; m < 3; ++m)
+      for (int m = 0; m < SHAPE_ROWS; ++m)
         for (int i = 0; i < MAXN * MAXN; ++i) hf[N][m][i] = (float)hd[N][m][i];
     done = true;
   }
@@ -213,7 +215,8 @@ __global__ void metric_from_vertices_kernel(int N, int cpg, int L, int64_t gstri
 // natural [cell][q][nf] (double) -> group layout T [group][nf][N][L]; padded cells get `pad`-pattern (identity K)
 template <typename T>
 __global__ void table_to_group_layout_kernel(int N, int cpg, int L, int nf, int64_t gstride, int64_t n_cells, int64_t n_cells_padded,
-                                             const double *__restrict__ in, T *__restrict__ out, int identity_pad) {
+                                             const double *__restrict__ in, T *__restrict__ out, int identity_pad,
+                                             const int64_t *__restrict__ order = nullptr) {
   const int N2 = N * N, N3 = N2 * N;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_cells_padded * N3) return;
@@ -227,7 +230,7 @@ __global__ void table_to_group_layout_kernel(int N, int cpg, int L, int nf, int6
   for (int f = 0; f < nf; ++f) {
     double v;
     if (cell < n_cells)
-      v = in[((size_t)cell * N3 + q) * nf + f];
+      v = in[((size_t)(order ? order[cell] : cell) * N3 + q) * nf + f];
     else
       v = (identity_pad && (f == 0 || f == 4 || f == 8)) ? 1.0 : 0.0;
     o[f * FS] = (T)v;
@@ -237,7 +240,7 @@ __global__ void table_to_group_layout_kernel(int N, int cpg, int L, int nf, int6
 // group layout -> natural [cell][q] of one field (test hook)
 template <typename T>
 __global__ void field_from_group_layout_kernel(int N, int cpg, int L, int64_t gstride, int field, int64_t n_cells,
-                                               const T *__restrict__ in, double *__restrict__ out) {
+                                               const T *__restrict__ in, double *__restrict__ out, const int64_t *__restrict__ order = nullptr) {
   const int N2 = N * N, N3 = N2 * N;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_cells * N3) return;
@@ -246,7 +249,7 @@ __global__ void field_from_group_layout_kernel(int N, int cpg, int L, int64_t gs
   const int iq = q % N, jq = (q / N) % N, kq = q / N2;
   const int64_t group = cell / cpg;
   const int lane = (int)(cell % cpg) * N2 + jq * N + iq;  // column thread (cell, j, i) owns the q-points (i, j, kq)
-  out[idx] = (double)in[(size_t)group * gstride + ((size_t)field * N + kq) * L + lane];
+  out[(size_t)(order ? order[cell] : cell) * N3 + q] = (double)in[(size_t)group * gstride + ((size_t)field * N + kq) * L + lane];
 }
 
 template <typename TO, typename TI>
@@ -344,8 +347,11 @@ extern "C" int b200mf_ctx_create(b200mf_ctx **out, const b200mf_ctx_desc *d) {
   c->n_cells = d->n_cells;
   c->n_dofs = d->n_dofs;
   c->n_owned = d->n_owned;
+  // default: the reference's serial order; hiding the exchanges behind interior cells is opt-in
+  // (b200mf_ctx_set_overlap / B200MF_OVERLAP=1) until it beats the serial order
+  c->overlap = getenv("B200MF_OVERLAP") ? atoi(getenv("B200MF_OVERLAP")) : 0;
   const int N = c->N, N2 = N * N, N3 = N2 * N, NC = c->NC;
-  c->cpg = (N2 <= 32) ? 32 / N2 : 1;
+  c->cpg = group_cells(N, NC);
   c->L = c->cpg * N2;
   c->n_groups = (c->n_cells + c->cpg - 1) / c->cpg;
   compute_shape_1d(d->degree, c->shape);
@@ -439,6 +445,22 @@ extern "C" int b200mf_ctx_create(b200mf_ctx **out, const b200mf_ctx_desc *d) {
   for (int64_t node = 0; node < c->n_nodes; ++node)
     if (ext_of_nodecomp[node * NC] < d->n_owned) ++c->n_owned_nodes;
 
+  // ---- cell order: cells that touch a ghost node first ("boundary" cells need the ghost values of src and
+  //      produce ghost contributions of dst), so that the two exchanges hide behind the interior cells
+  std::vector<int64_t> order;  // position in the library's cell order -> caller's cell
+  if (c->n_owned_nodes < c->n_nodes) {
+    std::vector<int64_t> bnd, inner;
+    for (int64_t cell = 0; cell < c->n_cells; ++cell) {
+      bool b = false;
+      for (int a = 0; a < N3 && !b; ++a) b = (int64_t)node_of_cell[cell * N3 + a] >= c->n_owned_nodes;
+      (b ? bnd : inner).push_back(cell);
+    }
+    c->n_boundary_groups = ((int64_t)bnd.size() + c->cpg - 1) / c->cpg;
+    order = bnd;
+    order.insert(order.end(), inner.begin(), inner.end());
+  }
+  auto caller_cell = [&](int64_t cell) -> int64_t { return order.empty() ? cell : order[cell]; };
+
   std::vector<uint8_t> nflags(c->n_nodes, 0);
   std::vector<uint32_t> cons_int(d->n_constrained);
   for (int64_t i = 0; i < d->n_constrained; ++i) {
@@ -448,7 +470,17 @@ extern "C" int b200mf_ctx_create(b200mf_ctx **out, const b200mf_ctx_desc *d) {
     cons_int[i] = (uint32_t)in;
     if (in < c->cstride * NC) nflags[in % c->cstride] |= (uint8_t)(1u << (in / c->cstride));
   }
-  c->n_constrained = d->n_constrained;
+  // the index list drives dst[c] += src[c], diag[c] = 1 and constraints.set_zero: locally owned rows only, as
+  // MatrixFree::get_constrained_dofs() (ghost rows belong to their owner; the per-node flags above cover them too)
+  {
+    std::vector<uint32_t> owned_only;
+    for (uint32_t in : cons_int)
+      if ((int64_t)in < c->cstride * NC ? (int64_t)(in % c->cstride) < c->n_owned_nodes
+                                        : orphans[in - c->cstride * NC] < d->n_owned)
+        owned_only.push_back(in);
+    cons_int.swap(owned_only);
+  }
+  c->n_constrained = (int64_t)cons_int.size();
   if (!identity) c->h_ext2int = new std::vector<int64_t>(ext2int);
 
   // ---- node index table in group layout [group][k][lane] ---------------------
@@ -460,7 +492,7 @@ extern "C" int b200mf_ctx_create(b200mf_ctx **out, const b200mf_ctx_desc *d) {
       const int cw = (int)(cell % cpg);
       for (int k = 0; k < N; ++k)
         for (int ji = 0; ji < N2; ++ji) {
-          const uint32_t node = node_of_cell[cell * N3 + k * N2 + ji];
+          const uint32_t node = node_of_cell[caller_cell(cell) * N3 + k * N2 + ji];
           nidx[((size_t)g * N + k) * L + cw * N2 + ji] = node | ((uint32_t)nflags[node] << 29);
         }
     }
@@ -481,15 +513,103 @@ extern "C" int b200mf_ctx_create(b200mf_ctx **out, const b200mf_ctx_desc *d) {
     c->bytes += cons_int.size() * sizeof(uint32_t);
   }
   if (d->material_id) {
-    B2_CUDA(cudaMalloc(&c->matid, std::max<int64_t>(1, c->n_cells)));
-    B2_CUDA(cudaMemcpy(c->matid, d->material_id, c->n_cells, cudaMemcpyHostToDevice));
+    std::vector<uint8_t> mid(std::max<int64_t>(1, c->n_cells));
+    for (int64_t cell = 0; cell < c->n_cells; ++cell) mid[cell] = d->material_id[caller_cell(cell)];
+    B2_CUDA(cudaMalloc(&c->matid, mid.size()));
+    B2_CUDA(cudaMemcpy(c->matid, mid.data(), mid.size(), cudaMemcpyHostToDevice));
     c->bytes += c->n_cells;
+  }
+  if (!order.empty()) {
+    B2_CUDA(cudaMalloc(&c->cell_order, order.size() * sizeof(int64_t)));
+    B2_CUDA(cudaMemcpy(c->cell_order, order.data(), order.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+    c->bytes += order.size() * sizeof(int64_t);
   }
   B2_CUDA(cudaMalloc(&c->stage, std::max<int64_t>(c->n_dofs, c->n_int) * sizeof(double)));
   c->bytes += std::max<int64_t>(c->n_dofs, c->n_int) * sizeof(double);
 
-  // ---- reference metric -------------------------------------------------------
+  // ---- per-cell metric when every cell is affine (deal.II compresses Cartesian/affine cells to one Jacobian
+  //      per cell): M = det J (K^T K), det J
   {
+    const int64_t padded = c->n_groups * c->cpg;
+    std::vector<double> mc((size_t)padded * MC_COUNT, 0.0);
+    bool affine = true;
+    auto fill = [&](int64_t cell, const double *Ki /* K[e][f] = d xi_f / d x_e */, double det) {
+      const int I6[6] = {0, 1, 2, 0, 0, 1}, J6[6] = {0, 1, 2, 1, 2, 2};
+      for (int s6 = 0; s6 < 6; ++s6) {
+        double a = 0;
+        for (int e = 0; e < 3; ++e) a += Ki[e * 3 + I6[s6]] * Ki[e * 3 + J6[s6]];
+        mc[cell * MC_COUNT + MC_M + s6] = det * a;
+      }
+      mc[cell * MC_COUNT + MC_DET] = det;
+    };
+    if (d->vertices) {
+      for (int64_t cell = 0; cell < c->n_cells && affine; ++cell) {
+        const double *v = d->vertices + caller_cell(cell) * 24;
+        double J[9], h = 0, xmax = 0;  // J[e][f] = d x_e / d xi_f from the three edges at vertex 0
+        for (int e = 0; e < 3; ++e)
+          for (int f = 0; f < 3; ++f) {
+            J[e * 3 + f] = v[(1 << f) * 3 + e] - v[e];
+            h = std::max(h, std::fabs(J[e * 3 + f]));
+          }
+        for (int i = 0; i < 24; ++i) xmax = std::max(xmax, std::fabs(v[i]));
+        // a vertex may deviate from the parallelepiped by the rounding of its own coordinates
+        const double tol = 1e-13 * h + 16 * 2.3e-16 * xmax;
+        for (int m = 0; m < 8 && affine; ++m)
+          for (int e = 0; e < 3; ++e) {
+            double x = v[e];
+            for (int f = 0; f < 3; ++f)
+              if ((m >> f) & 1) x += J[e * 3 + f];
+            if (std::fabs(x - v[m * 3 + e]) > tol) affine = false;
+          }
+        if (!affine) break;
+        const double det = J[0] * (J[4] * J[8] - J[5] * J[7]) - J[1] * (J[3] * J[8] - J[5] * J[6]) + J[2] * (J[3] * J[7] - J[4] * J[6]);
+        const double id = 1.0 / det;
+        double Ji[9];  // Ji[f][e] = d xi_f / d x_e
+        Ji[0] = (J[4] * J[8] - J[5] * J[7]) * id;
+        Ji[1] = (J[2] * J[7] - J[1] * J[8]) * id;
+        Ji[2] = (J[1] * J[5] - J[2] * J[4]) * id;
+        Ji[3] = (J[5] * J[6] - J[3] * J[8]) * id;
+        Ji[4] = (J[0] * J[8] - J[2] * J[6]) * id;
+        Ji[5] = (J[2] * J[3] - J[0] * J[5]) * id;
+        Ji[6] = (J[3] * J[7] - J[4] * J[6]) * id;
+        Ji[7] = (J[1] * J[6] - J[0] * J[7]) * id;
+        Ji[8] = (J[0] * J[4] - J[1] * J[3]) * id;
+        double Ki[9];
+        for (int e = 0; e < 3; ++e)
+          for (int f = 0; f < 3; ++f) Ki[e * 3 + f] = Ji[f * 3 + e];
+        fill(cell, Ki, det);
+      }
+    } else {
+      for (int64_t cell = 0; cell < c->n_cells && affine; ++cell) {
+        const int64_t cc = caller_cell(cell);
+        const double *K0 = d->inverse_jacobian + (size_t)cc * N3 * 9;
+        double kmax = 0;
+        for (int i = 0; i < 9; ++i) kmax = std::max(kmax, std::fabs(K0[i]));
+        const double det0 = d->jxw[(size_t)cc * N3] / (c->shape.w[0] * c->shape.w[0] * c->shape.w[0]);
+        for (int q = 1; q < N3 && affine; ++q) {
+          for (int i = 0; i < 9; ++i)
+            if (std::fabs(K0[q * 9 + i] - K0[i]) > 1e-11 * kmax) affine = false;
+          const double wq = c->shape.w[q % N] * c->shape.w[(q / N) % N] * c->shape.w[q / N2];
+          if (std::fabs(d->jxw[(size_t)cc * N3 + q] / wq - det0) > 1e-11 * std::fabs(det0)) affine = false;
+        }
+        if (affine) fill(cell, K0, det0);
+      }
+    }
+    if (affine) {
+      const size_t es = esize(c.get());
+      B2_CUDA(cudaMalloc(&c->mcell, std::max<size_t>(8, mc.size() * es)));
+      if (c->dtype == B200MF_F64) {
+        B2_CUDA(cudaMemcpy(c->mcell, mc.data(), mc.size() * 8, cudaMemcpyHostToDevice));
+      } else {
+        std::vector<float> mf32(mc.begin(), mc.end());
+        B2_CUDA(cudaMemcpy(c->mcell, mf32.data(), mf32.size() * 4, cudaMemcpyHostToDevice));
+      }
+      c->bytes += mc.size() * es;
+    }
+  }
+
+  // ---- reference metric at the quadrature points (not needed by the scalar operator on affine cells) ------
+  if (!(c->mcell && NC == 1)) {
     const size_t es = esize(c.get());
     const int64_t gs = table_stride_rt(c.get(), MF_COUNT);
     const size_t nel = (size_t)c->n_groups * gs;
@@ -501,7 +621,13 @@ extern "C" int b200mf_ctx_create(b200mf_ctx **out, const b200mf_ctx_desc *d) {
     if (d->vertices) {
       double *dv = nullptr;
       B2_CUDA(cudaMalloc(&dv, (size_t)c->n_cells * 24 * sizeof(double)));
-      B2_CUDA(cudaMemcpy(dv, d->vertices, (size_t)c->n_cells * 24 * sizeof(double), cudaMemcpyHostToDevice));
+      if (order.empty()) {
+        B2_CUDA(cudaMemcpy(dv, d->vertices, (size_t)c->n_cells * 24 * sizeof(double), cudaMemcpyHostToDevice));
+      } else {
+        std::vector<double> pv((size_t)c->n_cells * 24);
+        for (int64_t cell = 0; cell < c->n_cells; ++cell) memcpy(&pv[cell * 24], d->vertices + order[cell] * 24, 24 * sizeof(double));
+        B2_CUDA(cudaMemcpy(dv, pv.data(), pv.size() * sizeof(double), cudaMemcpyHostToDevice));
+      }
       QuadPts qp;
       for (int i = 0; i < N; ++i) {
         qp.xq[i] = c->shape.xq[i];
@@ -525,9 +651,9 @@ extern "C" int b200mf_ctx_create(b200mf_ctx **out, const b200mf_ctx_desc *d) {
       B2_CUDA(cudaMalloc(&dn, std::max<size_t>(8, nat.size() * sizeof(double))));
       B2_CUDA(cudaMemcpy(dn, nat.data(), nat.size() * sizeof(double), cudaMemcpyHostToDevice));
       if (c->dtype == B200MF_F64)
-        table_to_group_layout_kernel<double><<<nblocks(nthreads, 256), 256>>>(N, c->cpg, c->L, MF_COUNT, gs, c->n_cells, padded, dn, (double *)c->mref, 1);
+        table_to_group_layout_kernel<double><<<nblocks(nthreads, 256), 256>>>(N, c->cpg, c->L, MF_COUNT, gs, c->n_cells, padded, dn, (double *)c->mref, 1, c->cell_order);
       else
-        table_to_group_layout_kernel<float><<<nblocks(nthreads, 256), 256>>>(N, c->cpg, c->L, MF_COUNT, gs, c->n_cells, padded, dn, (float *)c->mref, 1);
+        table_to_group_layout_kernel<float><<<nblocks(nthreads, 256), 256>>>(N, c->cpg, c->L, MF_COUNT, gs, c->n_cells, padded, dn, (float *)c->mref, 1, c->cell_order);
       B2_LAUNCHED();
       B2_CUDA(cudaDeviceSynchronize());
       cudaFree(dn);
@@ -541,6 +667,10 @@ extern "C" int b200mf_ctx_destroy(b200mf_ctx *c) {
   if (!c) return 0;
   cudaFree(c->nidx);
   cudaFree(c->mref);
+  cudaFree(c->mcell);
+  cudaFree(c->cell_order);
+  if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+  for (cudaEvent_t e : c->ev) if (e) cudaEventDestroy(e);
   cudaFree(c->matid);
   cudaFree(c->int2ext);
   cudaFree(c->constrained);
@@ -602,6 +732,12 @@ int kernel_event(b200mf_ctx *c, cudaStream_t s) {
   return 0;
 }
 }  // namespace b200mf
+extern "C" int b200mf_ctx_set_overlap(b200mf_ctx *c, int on) {
+  if (!c) return set_error(B200MF_ERR_ARG, "null ctx");
+  c->overlap = on < 0 ? -1 : on ? 1 : 0;
+  return 0;
+}
+extern "C" int b200mf_ctx_cell_type(const b200mf_ctx *c) { return c ? (c->mcell ? 1 : 0) : -1; }
 extern "C" int64_t b200mf_ctx_n_dofs(const b200mf_ctx *c) { return c ? c->n_dofs : -1; }
 extern "C" size_t b200mf_ctx_memory_consumption(const b200mf_ctx *c) { return c ? c->bytes : 0; }
 
@@ -841,6 +977,42 @@ extern "C" int b200mf_nh_cache_host(b200mf_nh *op, const double *disp, int64_t *
   return b200mf_nh_cache(op, op->tmp_src, n_bad_out);
 }
 
+// update_ghost_values(src) -> cell loop -> compress(add)(dst) (mf_nh_operator.h:609-620).  The reference leaves
+// both exchanges exposed (FIXME at :598-607); here the cells that touch ghost entries come first in the
+// library's cell order (ctx_create), so that
+//   exchange stream: [ghost update of src]                    [compress(add) of dst]
+//   main stream    : [interior cells, 1st half] [boundary cells] [interior cells, 2nd half]
+// launch(g0, g1, stream) enqueues the cell loop over the groups [g0, g1).
+template <class Launch>
+static int apply_cells_with_exchange(b200mf_ctx *c, void *dst, const void *src, Launch &&launch) {
+  const int64_t nb = c->n_boundary_groups, ng = c->n_groups;
+  if (c->overlap < 0) return launch(0, ng, c->stream);  // measurement only: no exchange at all (rank-local result)
+  if (!has_neighbors(c) || !c->overlap || nb >= ng) {
+    B2_TRY(update_ghost_values(c, const_cast<void *>(src)));  // :610
+    B2_TRY(launch(0, ng, c->stream));
+    return compress_add(c, dst);                             // :620
+  }
+  if (!c->comm_stream) {
+    B2_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t &e : c->ev) B2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  const int64_t mid = nb + (ng - nb) / 2;
+  B2_CUDA(cudaEventRecord(c->ev[0], c->stream));
+  B2_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev[0], 0));
+  B2_TRY(update_ghost_values(c, const_cast<void *>(src), c->comm_stream));
+  B2_CUDA(cudaEventRecord(c->ev[1], c->comm_stream));
+  B2_TRY(launch(nb, mid, c->stream));
+  B2_CUDA(cudaStreamWaitEvent(c->stream, c->ev[1], 0));
+  B2_TRY(launch(0, nb, c->stream));
+  B2_CUDA(cudaEventRecord(c->ev[2], c->stream));
+  B2_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev[2], 0));
+  B2_TRY(compress_add(c, dst, c->comm_stream));
+  B2_CUDA(cudaEventRecord(c->ev[3], c->comm_stream));
+  B2_TRY(launch(mid, ng, c->stream));
+  B2_CUDA(cudaStreamWaitEvent(c->stream, c->ev[3], 0));
+  return 0;
+}
+
 template <typename T>
 static int constrained_identity(b200mf_ctx *c, void *dst, const void *src) {  // :623-624
   if (c->n_constrained) {
@@ -853,8 +1025,10 @@ static int constrained_identity(b200mf_ctx *c, void *dst, const void *src) {  //
 template <typename T>
 static int nh_apply_t(b200mf_nh *op, void *dst, const void *src) {
   b200mf_ctx *c = op->ctx;
-  B2_TRY(run_nh<T>(c, op->variant, (const T *)src, (T *)dst, nh_args<T>(op), 0, c->n_groups, c->stream));
-  B2_TRY(compress_add(c, dst));  // :620
+  const NHArgs<T> oa = nh_args<T>(op);
+  B2_TRY(apply_cells_with_exchange(c, dst, src, [&](int64_t g0, int64_t g1, cudaStream_t s) {
+    return run_nh<T>(c, op->variant, (const T *)src, (T *)dst, oa, g0, g1, s);
+  }));
   return constrained_identity<T>(c, dst, src);
 }
 
@@ -864,7 +1038,6 @@ static int nh_apply(b200mf_nh *op, void *dst, const void *src, bool zero_dst) {
   if (!op->cached) return set_error(B200MF_ERR_STATE, "vmult before cache()");
   b200mf_ctx *c = op->ctx;
   if (zero_dst) B2_CUDA(cudaMemsetAsync(dst, 0, c->n_int * esize(c), c->stream));  // vmult: dst = 0, :548
-  B2_TRY(update_ghost_values(c, const_cast<void *>(src)));                          // :610
   int rc = c->dtype == B200MF_F64 ? nh_apply_t<double>(op, dst, src) : nh_apply_t<float>(op, dst, src);
   B2_TRY(rc);
   B2_CUDA(cudaGetLastError());
@@ -882,6 +1055,67 @@ extern "C" int b200mf_nh_vmult_host(b200mf_nh *op, double *dst, const double *sr
   B2_TRY(b200mf_vec_upload_f64(op->ctx, op->tmp_src, src));
   B2_TRY(nh_apply(op, op->tmp_dst, op->tmp_src, true));
   return b200mf_vec_download_f64(op->ctx, dst, op->tmp_dst);
+}
+
+// ---- cell part of Solid::assemble_residual (mf_elasticity.h:1764-1846) ------------------
+template <typename T>
+static int nh_residual_t(b200mf_nh *op, void *rhs, const void *disp, const void *acc, const double *bf) {
+  b200mf_ctx *c = op->ctx;
+  NHResidualArgs<T> oa;
+  oa.stage = (const T *)c->mref;
+  oa.stage2 = nullptr;
+  oa.acc = (const T *)acc;
+  oa.cstride = c->cstride;
+  oa.matid = c->matid;
+  oa.n_cells = c->n_cells;
+  for (int m = 0; m < 2; ++m) {
+    double kappa, c_1, lambda, rho_alpha;
+    derived(op->mat[m], kappa, c_1, lambda, rho_alpha);
+    oa.mu[m] = (T)op->mat[m].mu;
+    oa.lambda[m] = (T)lambda;
+    oa.kappa[m] = (T)kappa;
+    oa.c_1[m] = (T)c_1;
+    oa.rho[m] = (T)op->mat[m].rho;
+  }
+  oa.formulation = op->mat[0].formulation;
+  for (int d = 0; d < 3; ++d) oa.body_force[d] = (T)(bf ? bf[d] : 0.0);
+  oa.n_bad = op->n_bad;
+  return run_nh_residual<T>(c, (const T *)disp, (T *)rhs, oa);
+}
+
+extern "C" int b200mf_nh_assemble_residual(b200mf_nh *op, void *rhs, const void *total_displacement, const void *acceleration,
+                                           const double *body_force, int64_t *n_bad_out) {
+  if (!op || !rhs || !total_displacement || !acceleration) return set_error(B200MF_ERR_ARG, "null argument");
+  b200mf_ctx *c = op->ctx;
+  if (!c->mref) return set_error(B200MF_ERR_STATE, "context holds no reference metric");
+  B2_CUDA(cudaMemsetAsync(op->n_bad, 0, sizeof(unsigned long long), c->stream));
+  B2_TRY(update_ghost_values(c, const_cast<void *>(total_displacement)));  // both are read with read_dof_values_plain
+  B2_TRY(update_ghost_values(c, const_cast<void *>(acceleration)));
+  B2_TRY(c->dtype == B200MF_F64 ? nh_residual_t<double>(op, rhs, total_displacement, acceleration, body_force)
+                                : nh_residual_t<float>(op, rhs, total_displacement, acceleration, body_force));
+  unsigned long long bad = 0;
+  B2_CUDA(cudaMemcpyAsync(&bad, op->n_bad, sizeof bad, cudaMemcpyDeviceToHost, c->stream));
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  if (n_bad_out) *n_bad_out = (int64_t)bad;
+  if (bad) return set_error(B200MF_ERR_NUMERIC, "assemble_residual: det F <= 0 at %llu quadrature points", bad);
+  return 0;
+}
+
+template <typename T>
+__global__ void zero_constrained_kernel(int64_t n, const uint32_t *__restrict__ idx, T *__restrict__ v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[idx[i]] = T(0);
+}
+// AffineConstraints::set_zero (mf_elasticity.h:1905, 2059)
+extern "C" int b200mf_vec_set_zero_constrained(b200mf_ctx *c, void *v) {
+  if (!c || !v) return set_error(B200MF_ERR_ARG, "null argument");
+  if (!c->n_constrained) return 0;
+  if (c->dtype == B200MF_F64)
+    zero_constrained_kernel<double><<<nblocks(c->n_constrained, 256), 256, 0, c->stream>>>(c->n_constrained, c->constrained, (double *)v);
+  else
+    zero_constrained_kernel<float><<<nblocks(c->n_constrained, 256), 256, 0, c->stream>>>(c->n_constrained, c->constrained, (float *)v);
+  B2_LAUNCHED();
+  return 0;
 }
 
 extern "C" b200mf_ctx *b200mf_nh_ctx(b200mf_nh *op) { return op ? op->ctx : nullptr; }
@@ -912,9 +1146,9 @@ extern "C" int b200mf_nh_qdata_host(b200mf_nh *op, int field, double *out) {
   double *tmp = nullptr;
   B2_CUDA(cudaMalloc(&tmp, n * sizeof(double)));
   if (c->dtype == B200MF_F64)
-    field_from_group_layout_kernel<double><<<nblocks(n, 256), 256, 0, c->stream>>>(c->N, c->cpg, c->L, table_stride_rt(c, nf), field, c->n_cells, (const double *)tab, tmp);
+    field_from_group_layout_kernel<double><<<nblocks(n, 256), 256, 0, c->stream>>>(c->N, c->cpg, c->L, table_stride_rt(c, nf), field, c->n_cells, (const double *)tab, tmp, c->cell_order);
   else
-    field_from_group_layout_kernel<float><<<nblocks(n, 256), 256, 0, c->stream>>>(c->N, c->cpg, c->L, table_stride_rt(c, nf), field, c->n_cells, (const float *)tab, tmp);
+    field_from_group_layout_kernel<float><<<nblocks(n, 256), 256, 0, c->stream>>>(c->N, c->cpg, c->L, table_stride_rt(c, nf), field, c->n_cells, (const float *)tab, tmp, c->cell_order);
   B2_LAUNCHED();
   B2_CUDA(cudaMemcpyAsync(out, tmp, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   B2_CUDA(cudaStreamSynchronize(c->stream));
@@ -1048,9 +1282,9 @@ extern "C" int b200mf_laplace_create(b200mf_laplace **out, b200mf_ctx *ctx, doub
     B2_CUDA(cudaMalloc(&op->coef, nel * esize(c)));
     const int64_t padded = c->n_groups * c->cpg;
     if (c->dtype == B200MF_F64)
-      table_to_group_layout_kernel<double><<<nblocks(padded * N3, 256), 256>>>(N, c->cpg, c->L, 1, gs, c->n_cells, padded, dn, (double *)op->coef, 0);
+      table_to_group_layout_kernel<double><<<nblocks(padded * N3, 256), 256>>>(N, c->cpg, c->L, 1, gs, c->n_cells, padded, dn, (double *)op->coef, 0, c->cell_order);
     else
-      table_to_group_layout_kernel<float><<<nblocks(padded * N3, 256), 256>>>(N, c->cpg, c->L, 1, gs, c->n_cells, padded, dn, (float *)op->coef, 0);
+      table_to_group_layout_kernel<float><<<nblocks(padded * N3, 256), 256>>>(N, c->cpg, c->L, 1, gs, c->n_cells, padded, dn, (float *)op->coef, 0, c->cell_order);
     B2_LAUNCHED();
     B2_CUDA(cudaDeviceSynchronize());
     cudaFree(dn);
@@ -1084,14 +1318,17 @@ static LaplaceArgs<T> laplace_args(const b200mf_laplace *op) {
   LaplaceArgs<T> oa;
   oa.stage = (const T *)op->ctx->mref;
   oa.stage2 = (const T *)op->coef;
+  oa.mcell = (const T *)op->ctx->mcell;
   oa.delta_t = (T)op->delta_t;
   return oa;
 }
 template <typename T>
 static int laplace_apply_t(b200mf_laplace *op, void *dst, const void *src) {
   b200mf_ctx *c = op->ctx;
-  B2_TRY(run_laplace<T>(c, false, (const T *)src, (T *)dst, laplace_args<T>(op), 0, c->n_groups, c->stream));
-  B2_TRY(compress_add(c, dst));
+  const LaplaceArgs<T> oa = laplace_args<T>(op);
+  B2_TRY(apply_cells_with_exchange(c, dst, src, [&](int64_t g0, int64_t g1, cudaStream_t s) {
+    return run_laplace<T>(c, false, (const T *)src, (T *)dst, oa, g0, g1, s);
+  }));
   return constrained_identity<T>(c, dst, src);
 }
 
@@ -1100,7 +1337,6 @@ static int laplace_apply(b200mf_laplace *op, void *dst, const void *src, bool ze
   if (dst == src) return set_error(B200MF_ERR_ARG, "vmult: dst aliases src");
   b200mf_ctx *c = op->ctx;
   if (zero_dst) B2_CUDA(cudaMemsetAsync(dst, 0, c->n_int * esize(c), c->stream));
-  B2_TRY(update_ghost_values(c, const_cast<void *>(src)));
   int rc = c->dtype == B200MF_F64 ? laplace_apply_t<double>(op, dst, src) : laplace_apply_t<float>(op, dst, src);
   B2_TRY(rc);
   B2_CUDA(cudaGetLastError());

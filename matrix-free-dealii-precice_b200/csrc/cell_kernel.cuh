@@ -48,9 +48,11 @@ constexpr uint32_t NODE_MASK = (1u << 29) - 1u;
 __host__ __device__ constexpr uint32_t node_flag(int c) { return 1u << (29 + c); }
 constexpr uint32_t NODE_ALL_CONSTRAINED = 7u << 29;
 
-// [N][0: S[q][i] = l_i(xi_q), 1: C[q][r] = collocation derivative on the Gauss points, 2: D = C S][q*N + i]
-static __constant__ double c_shape_d[MAXN + 1][3][MAXN * MAXN];
-static __constant__ float c_shape_f[MAXN + 1][3][MAXN * MAXN];
+// [N][0: S[q][i] = l_i(xi_q), 1: C[q][r] = collocation derivative on the Gauss points, 2: D = C S][q*N + i],
+// [N][3][q] = Gauss weight w_q
+constexpr int SHAPE_ROWS = 4;
+static __constant__ double c_shape_d[MAXN + 1][SHAPE_ROWS][MAXN * MAXN];
+static __constant__ float c_shape_f[MAXN + 1][SHAPE_ROWS][MAXN * MAXN];
 
 template <typename T, int N>
 struct Shape;
@@ -59,12 +61,14 @@ struct Shape<double, N> {
   static __device__ __forceinline__ double S(int q, int i) { return c_shape_d[N][0][q * N + i]; }
   static __device__ __forceinline__ double C(int q, int r) { return c_shape_d[N][1][q * N + r]; }
   static __device__ __forceinline__ double D(int q, int i) { return c_shape_d[N][2][q * N + i]; }
+  static __device__ __forceinline__ double W(int q) { return c_shape_d[N][3][q]; }
 };
 template <int N>
 struct Shape<float, N> {
   static __device__ __forceinline__ float S(int q, int i) { return c_shape_f[N][0][q * N + i]; }
   static __device__ __forceinline__ float C(int q, int r) { return c_shape_f[N][1][q * N + r]; }
   static __device__ __forceinline__ float D(int q, int i) { return c_shape_f[N][2][q * N + i]; }
+  static __device__ __forceinline__ float W(int q) { return c_shape_f[N][3][q]; }
 };
 
 // ---------------------------------------------------------------------------
@@ -81,14 +85,29 @@ struct SmemPad3;
 
 __host__ __device__ constexpr size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
 
+// Cells per group and threads per group.  A group is the unit that shares one set of shared-memory buffers and
+// barriers: its CPG*N^2 column threads and CPG*NC*N plane tasks are both packed densely from lane 0, so that
+// a phase only issues on the warps that hold work (an SM sub-partition spends two cycles on a DFMA whatever
+// the number of active lanes).  One warp per group wherever the plane tasks fill most of it (group barriers are
+// __syncwarp); the scalar operator (N plane tasks per cell only) and N = 5 pack several cells into a
+// multi-warp group instead.  Host (ctx->cpg, ctx->L) and device use these two functions.
+__host__ __device__ constexpr int group_cells(int N, int NC) {
+#ifdef B200MF_TUNE_CPG51  // tuning builds
+  if (NC == 1 && N == 5) return B200MF_TUNE_CPG51;
+#endif
+  if (NC == 1) return N == 2 ? 8 : N == 3 ? 7 : N == 4 ? 8 : N == 5 ? 6 : N == 6 ? 4 : 2;
+  return N * N <= 32 ? 32 / (N * N) : 1;
+}
+__host__ __device__ constexpr int group_threads(int N, int NC) { return (group_cells(N, NC) * N * N + 31) / 32 * 32; }
+
 template <int N, int NC, int WORDS = 2>
 struct Layout {
   static constexpr int N2 = N * N, N3 = N * N * N;
-  static constexpr bool WARP_MODE = (N2 <= 32);
-  static constexpr int CPG = WARP_MODE ? 32 / N2 : 1;                 // cells per group
-  static constexpr int L = CPG * N2;                                  // column threads (dense lanes) per group
-  static constexpr int TPG = WARP_MODE ? 32 : ((N2 + 31) / 32) * 32;  // threads per group
-  static constexpr int NT = CPG * NC * N;                             // plane tasks per group
+  static constexpr int CPG = group_cells(N, NC);   // cells per group
+  static constexpr int L = CPG * N2;               // column threads (dense lanes) per group
+  static constexpr int TPG = group_threads(N, NC); // threads per group
+  static constexpr bool WARP_MODE = (TPG == 32);
+  static constexpr int NT = CPG * NC * N;          // plane tasks per group
   using P = SmemPad3<WORDS, NC, N>;
   static constexpr int PL = P::PL;
   static constexpr int ZCOMP = N * PL + P::CCZ, ZCELL = NC * ZCOMP + P::CZ;
@@ -173,13 +192,15 @@ __device__ __forceinline__ void sweep_C(const T (&in)[N], T (&out)[N]) {
 //   static constexpr bool PLAIN;         read_dof_values_plain (ignore constraints)
 //   static constexpr bool INTEGRATE;     run the integration half and scatter
 //   static constexpr bool PRE;           one extra evaluation-only pass (pass -1) over a second cell-local field
-//                                        (Op::load_pre) whose q-point results (Op::quad_pre) stay in shared memory
+//                                        (Op::load_pre(..., nid, column)) whose q-point results (Op::quad_pre(..., v, G))
+//                                        stay in shared memory
 //   static constexpr bool STORE_DOFS;    Op::store_dofs gets the gathered cell-local values
 //   static constexpr int  NF_IN, NF_IN2; fields of the (up to two) input tables staged through shared memory
+//                                        (NF_IN may be 0: per-cell data only, e.g. the affine Laplace operator)
 //   static constexpr int  NF_SCRATCH;    fields of per-group scratch (pre-pass -> main pass)
 //   struct Args { const T *stage, *stage2; ... }   stage2 may be null at run time
 //   struct CellState;                    per-thread per-cell state (material constants)
-//   static void cell_begin(args, cell, valid, CellState&)
+//   static void cell_begin(args, cell, valid, lane, CellState&)
 //   static void quad(args, state, active, qs, qs2, scr, group, kq, lane, v[NC], G[NC][3], ov[NC], oG[NC][3])
 //       the column thread `lane` = (cell, j, i) handles the q-points (i, j, kq), kq = 0..N-1;
 //       qs / qs2 / scr: shared-memory tables, field f of q-point (kq, lane) at qs[(f*N + kq)*L + lane];
@@ -199,7 +220,7 @@ struct KernelSmem {
   static constexpr int DIAG_ELEMS = Ly::CPG * 6 * Ly::N3;  // diagonal pass: 6 coefficient fields per cell (see below)
   static constexpr int BUF_ELEMS = (DIAG && DIAG_ELEMS > Ly::GROUP_ELEMS) ? DIAG_ELEMS : Ly::GROUP_ELEMS;
   static constexpr size_t BUF_BYTES = round_up((size_t)BUF_ELEMS * sizeof(T), 16);
-  static constexpr size_t ST1_BYTES = Ly::table_stride(Op::NF_IN) * sizeof(T);
+  static constexpr size_t ST1_BYTES = Op::NF_IN ? Ly::table_stride(Op::NF_IN) * sizeof(T) : 0;
   static constexpr size_t ST2_BYTES = Op::NF_IN2 ? Ly::table_stride(Op::NF_IN2) * sizeof(T) : 0;
   static constexpr size_t SCR_BYTES = Op::NF_SCRATCH ? Ly::table_stride(Op::NF_SCRATCH) * sizeof(T) : 0;  // pre-pass -> main pass
   static constexpr size_t GROUP_BYTES = BUF_BYTES + ST1_BYTES + ST2_BYTES + SCR_BYTES + 16;                // + mbarrier
@@ -236,11 +257,13 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
   group_sync<WM>();
 
   // stage the tables of `group` into this group's shared buffers (one elected lane drives the TMA unit)
+  // (Op::NF_IN == 0 and no second table: nothing is staged and the mbarrier is never armed or waited on)
+  const bool two = Op::NF_IN2 != 0 && oa.stage2 != nullptr;
+  const bool staged = Op::NF_IN != 0 || two;
   auto stage = [&](int64_t g) {
-    if (lane == 0) {
-      const bool two = Op::NF_IN2 != 0 && oa.stage2 != nullptr;
-      mbar_expect_tx(mbar, (unsigned)(KS_::ST1_BYTES + (two ? KS_::ST2_BYTES : 0)));
-      bulk_g2s(qs, oa.stage + (size_t)g * Ly::table_stride(Op::NF_IN), (unsigned)KS_::ST1_BYTES, mbar);
+    if (lane == 0 && staged) {
+      mbar_expect_tx(mbar, (unsigned)((Op::NF_IN ? KS_::ST1_BYTES : 0) + (two ? KS_::ST2_BYTES : 0)));
+      if (Op::NF_IN) bulk_g2s(qs, oa.stage + (size_t)g * Ly::table_stride(Op::NF_IN ? Op::NF_IN : 1), (unsigned)KS_::ST1_BYTES, mbar);
       if (two) bulk_g2s(qs2, oa.stage2 + (size_t)g * Ly::table_stride(Op::NF_IN2 ? Op::NF_IN2 : 1), (unsigned)KS_::ST2_BYTES, mbar);
     }
   };
@@ -295,7 +318,7 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
     const int64_t gnext = group + gstep;
     const bool has_next = gnext < A.n_groups;
     typename Op::CellState st;
-    Op::cell_begin(oa, group * Ly::CPG + cw, active, st);
+    Op::cell_begin(oa, group * Ly::CPG + cw, active, lane, st);
 
     if constexpr (Op::STORE_DOFS) Op::store_dofs(oa, group, lane, active, u);
     constexpr int NPASS = 1;
@@ -308,7 +331,7 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
           // ---- diagonal pass ---------------------------------------------------------------------
           if (pass == FIRST) {
             if (has_next) load_nid(gnext, nid_next);
-            mbar_wait(mbar, parity);
+            if (staged) mbar_wait(mbar, parity);
           }
           T *db = bufZ + cw * (6 * Ly::N3);  // [field][k3][j][i] of this thread's cell
           const int tj = ji / N, ti = ji % N;
@@ -420,7 +443,7 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
         T o[N];
         if (pre) {
           T up[N];
-          Op::load_pre(oa, group, lane, active, c, up);
+          Op::load_pre(oa, group, lane, active, c, nid, up);
           sweep_S<T, N, false>(up, o);
         } else {
           sweep_S<T, N, false>(u[c], o);
@@ -478,7 +501,7 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
           }
         }
       }
-      if (pass == FIRST) mbar_wait(mbar, parity);  // this group's tables have landed in shared memory
+      if (pass == FIRST && staged) mbar_wait(mbar, parity);  // this group's tables have landed in shared memory
       group_sync<WM>();
       // ---- F3 (column): d/dz in registers, quadrature loop, z part of the integration ---------
       T racc[NC][N];  // values + z-derivative terms of the test side, at the q-points of the column
@@ -504,7 +527,7 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
             G[c][2] = gz[c][kq];
           }
           if (pre) {
-            Op::quad_pre(oa, st, active, qs, scr, group, kq, lane, G);
+            Op::quad_pre(oa, st, active, qs, scr, group, kq, lane, v, G);
             continue;
           }
           Op::quad(oa, st, active, qs, qs2, scr, group, kq, lane, v, G, ov, oG);

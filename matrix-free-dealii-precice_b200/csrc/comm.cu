@@ -195,11 +195,11 @@ void free_partitioner(b200mf_ctx *c) {
 
 // forward == true : owner -> ghost (update_ghost_values); false: ghost -> owner accumulate (compress(add))
 template <typename T>
-static int exchange(b200mf_ctx *c, T *vec, bool forward) {
+static int exchange(b200mf_ctx *c, T *vec, bool forward, cudaStream_t s) {
   b200mf_partitioner *p = c->part;
   if (!p || p->nn == 0) return 0;
   const ncclDataType_t dt = sizeof(T) == 8 ? ncclFloat64 : ncclFloat32;
-  cudaStream_t s = c->stream;
+  if (!s) s = c->stream;
   T *bs = (T *)p->buf_send, *br = (T *)p->buf_recv;
   if (forward) {
     if (p->total_send) {
@@ -240,11 +240,12 @@ static int exchange(b200mf_ctx *c, T *vec, bool forward) {
   return 0;
 }
 
-int update_ghost_values(b200mf_ctx *c, void *vec) {
-  return c->dtype == B200MF_F64 ? exchange<double>(c, (double *)vec, true) : exchange<float>(c, (float *)vec, true);
+bool has_neighbors(const b200mf_ctx *c) { return c->part && c->part->nn > 0; }
+int update_ghost_values(b200mf_ctx *c, void *vec, cudaStream_t s) {
+  return c->dtype == B200MF_F64 ? exchange<double>(c, (double *)vec, true, s) : exchange<float>(c, (float *)vec, true, s);
 }
-int compress_add(b200mf_ctx *c, void *vec) {
-  return c->dtype == B200MF_F64 ? exchange<double>(c, (double *)vec, false) : exchange<float>(c, (float *)vec, false);
+int compress_add(b200mf_ctx *c, void *vec, cudaStream_t s) {
+  return c->dtype == B200MF_F64 ? exchange<double>(c, (double *)vec, false, s) : exchange<float>(c, (float *)vec, false, s);
 }
 int zero_ghosts(b200mf_ctx *c, void *vec) {
   b200mf_partitioner *p = c->part;

@@ -49,9 +49,10 @@ int kernel_event(b200mf_ctx *c, cudaStream_t s);  // b200mf.cu
 
 // comm.cu
 void free_partitioner(b200mf_ctx *c);
-int update_ghost_values(b200mf_ctx *c, void *vec);
-int compress_add(b200mf_ctx *c, void *vec);
+int update_ghost_values(b200mf_ctx *c, void *vec, cudaStream_t stream = nullptr);  // nullptr: the context's stream
+int compress_add(b200mf_ctx *c, void *vec, cudaStream_t stream = nullptr);
 int zero_ghosts(b200mf_ctx *c, void *vec);
+bool has_neighbors(const b200mf_ctx *c);
 int allreduce_sum_f64(b200mf_ctx *c, double *dptr, int n);
 
 }  // namespace b200mf
@@ -67,7 +68,13 @@ struct b200mf_ctx {
   int sm_count;
   // device data
   uint32_t *nidx;        // [group][N][L]
-  void *mref;            // T [group][MF_COUNT][N][L] reference-configuration metric
+  void *mref;            // T [group][MF_COUNT][N][L] reference-configuration metric (null: scalar context on affine cells)
+  int64_t *cell_order;   // library cell -> caller's cell (boundary cells first) or nullptr when identity
+  int64_t n_boundary_groups;  // groups [0, n_boundary_groups) touch ghost nodes
+  cudaStream_t comm_stream;   // exchanges that overlap the interior cells run here
+  cudaEvent_t ev[4];
+  int overlap;                // 1: hide the exchanges behind interior cells (default when partitioned)
+  void *mcell;           // T [cell][MC_COUNT] per-cell metric when every cell is affine, else null
   uint8_t *matid;        // [n_cells] or nullptr
   int64_t *int2ext;      // [n_int] or nullptr when identity
   uint32_t *constrained; // internal indices of constrained DoFs

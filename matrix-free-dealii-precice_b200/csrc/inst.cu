@@ -1,5 +1,5 @@
 // One kernel family per translation unit: compiled as  -DINST_KIND=<k> -DINST_T=<double|float>
-//   1 NeoHook vmult   2 NeoHook diagonal   3 NeoHook cache   4 Laplace (vmult + diagonal)
+//   1 NeoHook vmult   2 NeoHook diagonal   3 NeoHook cache   4 Laplace (vmult + diagonal)   5 NeoHook residual
 #include "launch.cuh"
 
 namespace b200mf {
@@ -41,12 +41,22 @@ template <>
 int run_laplace<TT>(const b200mf_ctx *ctx, bool diag, const TT *src, TT *dst, const LaplaceArgs<TT> &oa, int64_t g0, int64_t g1,
                     cudaStream_t stream) {
   int rc = 0;
+  const bool affine = ctx->mcell != nullptr;  // every cell affine: per-cell metric, nothing streamed per q-point
   B2_DISPATCH_N(ctx->N, TT, {
     if (diag)
-      rc = launch_cell_loop<T, N, LaplaceOp<T, N>, true>(ctx, (const T *)nullptr, dst, oa);
+      rc = affine ? launch_cell_loop<T, N, LaplaceAffineOp<T, N>, true>(ctx, (const T *)nullptr, dst, oa)
+                  : launch_cell_loop<T, N, LaplaceOp<T, N>, true>(ctx, (const T *)nullptr, dst, oa);
     else
-      rc = launch_cell_loop<T, N, LaplaceOp<T, N>>(ctx, src, dst, oa, g0, g1, stream);
+      rc = affine ? launch_cell_loop<T, N, LaplaceAffineOp<T, N>>(ctx, src, dst, oa, g0, g1, stream)
+                  : launch_cell_loop<T, N, LaplaceOp<T, N>>(ctx, src, dst, oa, g0, g1, stream);
   });
+  return rc;
+}
+#elif INST_KIND == 5
+template <>
+int run_nh_residual<TT>(const b200mf_ctx *ctx, const TT *displacement, TT *rhs, const NHResidualArgs<TT> &oa) {
+  int rc = 0;
+  B2_DISPATCH_N(ctx->N, TT, { rc = launch_cell_loop<T, N, NHResidualOp<T, N>>(ctx, displacement, rhs, oa); });
   return rc;
 }
 #else

@@ -16,6 +16,8 @@ int run_nh_diag(const b200mf_ctx *ctx, int variant, T *diag, const NHArgs<T> &oa
 template <typename T>
 int run_nh_cache(const b200mf_ctx *ctx, int variant, const T *displacement, const NHCacheArgs<T> &oa);
 template <typename T>
+int run_nh_residual(const b200mf_ctx *ctx, const T *displacement, T *rhs, const NHResidualArgs<T> &oa);
+template <typename T>
 int run_laplace(const b200mf_ctx *ctx, bool diag, const T *src, T *dst, const LaplaceArgs<T> &oa, int64_t g0, int64_t g1,
                 cudaStream_t stream);
 

@@ -1,6 +1,7 @@
 // Launch of the templated cell loop (included by the kernel translation units only).
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 
 #include "kernels.h"
 
@@ -69,11 +70,21 @@ static int launch_cell_loop(const b200mf_ctx *ctx, const T *src, T *dst, const t
   if (g1 < 0) g1 = ctx->n_groups;
   if (!stream) stream = ctx->stream;
   if constexpr (!Ly::WARP_MODE) {
-    return launch_variant<T, N, Op, DIAG, 1, 1>(ctx, src, dst, oa, g0, g1, stream);
+    // scalar Q4 (6 cells per 160-thread group): cap the registers at two resident groups per SM - only one warp of a
+    // group works during the plane phase, a second group keeps the FP64 pipe fed (B200: 0.94 -> 0.69 ms at 1.7e7 DoFs)
+    constexpr int MINB = (Op::NC == 1 && N == 5 && !DIAG) ? 2 : 1;
+    return launch_variant<T, N, Op, DIAG, 1, MINB>(ctx, src, dst, oa, g0, g1, stream);
   } else {
-    // warps per block from the B200 sweep (profiles/r01_sweep_*.jsonl): shared memory (cell buffers + staged
-    // table) bounds the resident warps, small blocks pack an SM best; N = 5 prefers 4-warp blocks
-    constexpr int GPB = (N == 5) ? 4 : (N == 2 ? 4 : 1);
+    // warps per block, from the B200 sweep tools/gpu_gpb_sweep.sh (profiles/r01_v3_gpb_sweep.jsonl): shared memory
+    // (cell buffers + staged table) bounds the resident warps and small blocks pack an SM best; N = 2 has 8 cells
+    // per warp and so little shared memory that the 32-blocks-per-SM limit binds first -> 4-warp blocks
+    constexpr int GPB = (N == 2 ? 4 : N == 3 ? 2 : (N == 4 && sizeof(T) == 4) ? 2 : 1);
+#ifdef B200MF_GPB_SWEEP  // tuning builds only: B200MF_GPB=1|2|4 picks the block size at run time
+    static const int gpb_env = getenv("B200MF_GPB") ? atoi(getenv("B200MF_GPB")) : 0;
+    if (gpb_env == 1) return launch_variant<T, N, Op, DIAG, 1, 1>(ctx, src, dst, oa, g0, g1, stream);
+    if (gpb_env == 2) return launch_variant<T, N, Op, DIAG, 2, 1>(ctx, src, dst, oa, g0, g1, stream);
+    if (gpb_env == 4) return launch_variant<T, N, Op, DIAG, 4, 1>(ctx, src, dst, oa, g0, g1, stream);
+#endif
     return launch_variant<T, N, Op, DIAG, GPB, 1>(ctx, src, dst, oa, g0, g1, stream);
   }
 }

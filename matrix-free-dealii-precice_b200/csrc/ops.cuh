@@ -92,20 +92,21 @@ struct NHOp {
   using Args = NHArgs<T>;
   using CellState = NHCell<T>;
   static constexpr int FS = N * Ly::L;
-  static __device__ __forceinline__ void cell_begin(const Args &oa, int64_t cell, bool valid, CellState &st) {
+  static __device__ __forceinline__ void cell_begin(const Args &oa, int64_t cell, bool valid, int, CellState &st) {
     nh_cell_begin(oa, cell, valid, st);
   }
   static __device__ __forceinline__ void store_dofs(const Args &, int64_t, int, bool, const T (&)[NC][N]) {}
 
   // scalar_referential: second evaluate() on the cached cell-local displacement (:861-867)
-  static __device__ __forceinline__ void load_pre(const Args &oa, int64_t group, int lane, bool active, int c, T (&up)[N]) {
+  static __device__ __forceinline__ void load_pre(const Args &oa, int64_t group, int lane, bool active, int c, const uint32_t (&)[N],
+                                                  T (&up)[N]) {
     const T *p = oa.pos + ((size_t)group * 3 + c) * FS + lane;
 #pragma unroll
     for (int k = 0; k < N; ++k) up[k] = active ? __ldg(p + (size_t)k * Ly::L) : T(0);
   }
   // F = I + Grad u through the reference inverse Jacobian (:872-899), kept in shared memory for the main pass
   static __device__ __forceinline__ void quad_pre(const Args &, const CellState &, bool active, const T *qs, T *scr,
-                                                  int64_t, int iq, int lane, const T (&G)[NC][3]) {
+                                                  int64_t, int iq, int lane, const T (&)[NC], const T (&G)[NC][3]) {
     if (!active) return;
     const T *q = qs + iq * Ly::L + lane;
     T K[9];
@@ -310,7 +311,7 @@ struct NHCacheOp {
     T mu, lambda;
     bool real;
   };
-  static __device__ __forceinline__ void cell_begin(const Args &oa, int64_t cell, bool valid, CellState &st) {
+  static __device__ __forceinline__ void cell_begin(const Args &oa, int64_t cell, bool valid, int, CellState &st) {
     int m = 0;
     st.real = valid && cell < oa.n_cells;
     if (oa.matid != nullptr && st.real) m = oa.matid[cell] != 0;  // :402-404
@@ -325,9 +326,9 @@ struct NHCacheOp {
 #pragma unroll
       for (int k = 0; k < N; ++k) oa.pos[((size_t)group * 3 + c) * FS + (size_t)k * Ly::L + lane] = u[c][k];
   }
-  static __device__ __forceinline__ void load_pre(const Args &, int64_t, int, bool, int, T (&)[N]) {}
+  static __device__ __forceinline__ void load_pre(const Args &, int64_t, int, bool, int, const uint32_t (&)[N], T (&)[N]) {}
   static __device__ __forceinline__ void quad_pre(const Args &, const CellState &, bool, const T *, T *, int64_t, int, int,
-                                                  const T (&)[NC][3]) {}
+                                                  const T (&)[NC], const T (&)[NC][3]) {}
   static __device__ __forceinline__ void quad(const Args &oa, const CellState &st, bool active, const T *qs, const T *, const T *,
                                               int64_t group, int iq, int lane, const T (&)[NC], const T (&G)[NC][3],
                                               T (&)[NC], T (&)[NC][3]) {
@@ -424,10 +425,14 @@ struct NHCacheOp {
 // a13: LaplaceOperator::do_operation_on_cell (heat_transfer.h:234-250): (M + dt*c*K) u
 template <typename T>
 struct LaplaceArgs {
-  const T *stage;   // reference metric [group][MF_COUNT][N][L]
+  const T *stage;   // reference metric [group][MF_COUNT][N][L]  (general cells)
   const T *stage2;  // coefficient [group][1][N][L] or nullptr (Coefficient::value == 1, heat_transfer.h:64-71)
+  const T *mcell;   // affine cells: [cell][MC_COUNT] (padded to whole groups)
   T delta_t;
 };
+// per-cell metric of an affine cell (deal.II stores one Jacobian per Cartesian/affine cell):
+// M = det J * K^T K (symmetric, 00 11 22 01 02 12: the Laplacian pulled back to the reference cell), det J
+enum { MC_M = 0, MC_DET = 6, MC_COUNT = 8 };
 template <typename T, int N>
 struct LaplaceOp {
   static constexpr int NC = 1, NF_IN = MF_COUNT, NF_IN2 = 1, NF_SCRATCH = 0;
@@ -435,11 +440,11 @@ struct LaplaceOp {
   using Ly = Layout<N, NC, sizeof(T) / 4>;
   using Args = LaplaceArgs<T>;
   struct CellState {};
-  static __device__ __forceinline__ void cell_begin(const Args &, int64_t, bool, CellState &) {}
+  static __device__ __forceinline__ void cell_begin(const Args &, int64_t, bool, int, CellState &) {}
   static __device__ __forceinline__ void store_dofs(const Args &, int64_t, int, bool, const T (&)[NC][N]) {}
-  static __device__ __forceinline__ void load_pre(const Args &, int64_t, int, bool, int, T (&)[N]) {}
+  static __device__ __forceinline__ void load_pre(const Args &, int64_t, int, bool, int, const uint32_t (&)[N], T (&)[N]) {}
   static __device__ __forceinline__ void quad_pre(const Args &, const CellState &, bool, const T *, T *, int64_t, int, int,
-                                                  const T (&)[NC][3]) {}
+                                                  const T (&)[NC], const T (&)[NC][3]) {}
   static __device__ __forceinline__ void quad(const Args &oa, const CellState &, bool active, const T *qs, const T *qs2, const T *,
                                               int64_t, int iq, int lane, const T (&v)[NC], const T (&G)[NC][3],
                                               T (&ov)[NC], T (&oG)[NC][3]) {
@@ -462,6 +467,149 @@ struct LaplaceOp {
 #pragma unroll
     for (int f = 0; f < 3; ++f) oG[0][f] = wk * (K[0 * 3 + f] * g[0] + K[1 * 3 + f] * g[1] + K[2 * 3 + f] * g[2]);
     ov[0] = w * v[0];  // submit_value(get_value) :244
+  }
+};
+
+// The same operator on affine cells: no q-point table at all (the metric is 7 numbers per cell), so the
+// kernel streams only the vectors and the index table and is bound by the FP64/FP32 pipe instead of HBM.
+template <typename T, int N>
+struct LaplaceAffineOp {
+  static constexpr int NC = 1, NF_IN = 0, NF_IN2 = 1, NF_SCRATCH = 0;
+  static constexpr bool PLAIN = false, INTEGRATE = true, PRE = false, STORE_DOFS = false;
+  using Ly = Layout<N, NC, sizeof(T) / 4>;
+  using Args = LaplaceArgs<T>;
+  struct CellState {
+    T M[6], mw;  // delta_t * w_i w_j * M,  det J * w_i w_j
+  };
+  static __device__ __forceinline__ void cell_begin(const Args &oa, int64_t cell, bool valid, int lane, CellState &st) {
+    const int ji = lane % Ly::N2;
+    const T wij = valid ? Shape<T, N>::W(ji % N) * Shape<T, N>::W(ji / N) : T(0);
+    const T *m = oa.mcell + (size_t)cell * MC_COUNT;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) st.M[i] = valid ? __ldg(m + MC_M + i) * wij * oa.delta_t : T(0);
+    st.mw = valid ? __ldg(m + MC_DET) * wij : T(0);
+  }
+  static __device__ __forceinline__ void store_dofs(const Args &, int64_t, int, bool, const T (&)[NC][N]) {}
+  static __device__ __forceinline__ void load_pre(const Args &, int64_t, int, bool, int, const uint32_t (&)[N], T (&)[N]) {}
+  static __device__ __forceinline__ void quad_pre(const Args &, const CellState &, bool, const T *, T *, int64_t, int, int,
+                                                  const T (&)[NC], const T (&)[NC][3]) {}
+  static __device__ __forceinline__ void quad(const Args &oa, const CellState &st, bool active, const T *, const T *qs2, const T *,
+                                              int64_t, int iq, int lane, const T (&v)[NC], const T (&G)[NC][3],
+                                              T (&ov)[NC], T (&oG)[NC][3]) {
+    const T wk = Shape<T, N>::W(iq);
+    T k = wk;
+    if (oa.stage2 != nullptr && active) k *= qs2[iq * Ly::L + lane];  // coefficient(cell, q), heat_transfer.h:245-247
+    oG[0][0] = k * (st.M[0] * G[0][0] + st.M[3] * G[0][1] + st.M[4] * G[0][2]);
+    oG[0][1] = k * (st.M[3] * G[0][0] + st.M[1] * G[0][1] + st.M[5] * G[0][2]);
+    oG[0][2] = k * (st.M[4] * G[0][0] + st.M[5] * G[0][1] + st.M[2] * G[0][2]);
+    ov[0] = st.mw * wk * v[0];  // submit_value(get_value) :244
+  }
+};
+
+// ---------------------------------------------------------------------------
+// the cell part of Solid::assemble_residual, fast path (mf_elasticity.h:1764-1846):
+//   rhs += int [ -tau(F) F^-T : Grad v  +  rho (b - a) . v ] dV  on the reference configuration,
+// total_displacement and acceleration read with read_dof_values_plain, constrained rows not written.
+// The acceleration is the extra evaluation-only pass (gathered through the same node indices); its q-point
+// values wait in shared memory for the main pass over the displacement.
+template <typename T>
+struct NHResidualArgs {
+  const T *stage;   // reference metric [group][MF_COUNT][N][L]
+  const T *stage2;  // unused
+  const T *acc;     // acceleration vector (component blocks)
+  int64_t cstride;
+  const uint8_t *matid;
+  int64_t n_cells;
+  T mu[2], lambda[2], kappa[2], c_1[2], rho[2];
+  int formulation;
+  T body_force[3];
+  unsigned long long *n_bad;  // quadrature points with det F <= 0 (debug assertion :1812-1817)
+};
+template <typename T, int N>
+struct NHResidualOp {
+  static constexpr int NC = 3, NF_IN = MF_COUNT, NF_IN2 = 0, NF_SCRATCH = 3;
+  static constexpr bool PLAIN = true, INTEGRATE = true, PRE = true, STORE_DOFS = false;
+  using Ly = Layout<N, NC, sizeof(T) / 4>;
+  using Args = NHResidualArgs<T>;
+  static constexpr int FS = N * Ly::L;
+  struct CellState {
+    T mu, lambda, kappa, c_1, rho;
+    bool real;
+  };
+  static __device__ __forceinline__ void cell_begin(const Args &oa, int64_t cell, bool valid, int, CellState &st) {
+    int m = 0;
+    st.real = valid && cell < oa.n_cells;
+    if (oa.matid != nullptr && st.real) m = oa.matid[cell] != 0;  // :1781-1784
+    st.mu = m ? oa.mu[1] : oa.mu[0];
+    st.lambda = m ? oa.lambda[1] : oa.lambda[0];
+    st.kappa = m ? oa.kappa[1] : oa.kappa[0];
+    st.c_1 = m ? oa.c_1[1] : oa.c_1[0];
+    st.rho = m ? oa.rho[1] : oa.rho[0];
+  }
+  static __device__ __forceinline__ void store_dofs(const Args &, int64_t, int, bool, const T (&)[NC][N]) {}
+  // phi_acc.read_dof_values_plain(acceleration) :1790-1792
+  static __device__ __forceinline__ void load_pre(const Args &oa, int64_t, int, bool active, int c, const uint32_t (&nid)[N], T (&up)[N]) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) up[k] = active ? __ldg(oa.acc + (size_t)c * oa.cstride + (nid[k] & NODE_MASK)) : T(0);
+  }
+  static __device__ __forceinline__ void quad_pre(const Args &, const CellState &, bool active, const T *, T *scr, int64_t, int iq,
+                                                  int lane, const T (&v)[NC], const T (&)[NC][3]) {
+    if (!active) return;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) scr[(c * N + iq) * Ly::L + lane] = v[c];  // phi_acc.get_value(q)
+  }
+  static __device__ __forceinline__ void quad(const Args &oa, const CellState &st, bool active, const T *qs, const T *, const T *scr,
+                                              int64_t, int iq, int lane, const T (&)[NC], const T (&G)[NC][3], T (&ov)[NC],
+                                              T (&oG)[NC][3]) {
+    if (!active) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) ov[c] = oG[c][0] = oG[c][1] = oG[c][2] = T(0);
+      return;
+    }
+    const T *q = qs + iq * Ly::L + lane;
+    T K[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) K[i] = q[(MF_K + i) * FS];
+    const T w = q[MF_W * FS];
+    T F[3][3], Fa[3][3];  // F = I + Grad u :1802-1805
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int e = 0; e < 3; ++e)
+        F[c][e] = K[e * 3 + 0] * G[c][0] + K[e * 3 + 1] * G[c][1] + K[e * 3 + 2] * G[c][2] + (c == e ? T(1) : T(0));
+    const T detF = adj3(F, Fa);
+    if (st.real && !(detF > T(0))) atomicAdd(oa.n_bad, 1ull);
+    const T idet = T(1) / detF;
+    T tau[3][3];  // get_tau, material.h:116-161
+    if (oa.formulation == 0) {
+      const T cs = pow(detF, T(-1.0 / 3.0));           // F_iso = J^(-1/3) F
+      const T tb = cs * cs * (T(2) * st.c_1);          // tau_bar = 2 c_1 b_bar
+      const T tmp = (st.kappa * T(0.5)) * (detF - idet) * detF;  // dPsi_vol/dJ * J
+      T tr = T(0);
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) tau[i][j] = (F[i][0] * F[j][0] + F[i][1] * F[j][1] + F[i][2] * F[j][2]) * tb;
+      tr = tau[0][0] + tau[1][1] + tau[2][2];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) tau[d][d] += tmp - tr / T(3);
+    } else {
+      const T tmp = st.mu - T(2) * st.lambda * log(detF);
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          tau[i][j] = st.mu * (F[i][0] * F[j][0] + F[i][1] * F[j][1] + F[i][2] * F[j][2]) - (i == j ? tmp : T(0));
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      T sub[3];  // -(tau F^-T)[c][e] = -sum_k tau[c][k] Finv[e][k] :1830
+#pragma unroll
+      for (int e = 0; e < 3; ++e) sub[e] = -(tau[c][0] * Fa[e][0] + tau[c][1] * Fa[e][1] + tau[c][2] * Fa[e][2]) * idet;
+#pragma unroll
+      for (int f = 0; f < 3; ++f) oG[c][f] = w * (K[0 * 3 + f] * sub[0] + K[1 * 3 + f] * sub[1] + K[2 * 3 + f] * sub[2]);
+      ov[c] = w * st.rho * (oa.body_force[c] - scr[(c * N + iq) * Ly::L + lane]);  // :1831-1834
+    }
   }
 };
 

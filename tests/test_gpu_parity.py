@@ -228,8 +228,10 @@ def test_nh_vmult_fp32_level_operator(p):
 
 @pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6])
 @pytest.mark.parametrize("with_coef", [False, True])
-def test_laplace_vmult_and_diagonal(p, with_coef):
-    m = make_mesh(p, NCELLS[p], ncomp=1, clamp=((0, 0), (1, 1)))
+@pytest.mark.parametrize("mapped", [True, False], ids=["general", "affine"])
+def test_laplace_vmult_and_diagonal(p, with_coef, mapped):
+    # mapped=False: every cell is affine -> the library's per-cell-metric kernel (LaplaceAffineOp)
+    m = make_mesh(p, NCELLS[p], mapped=mapped, ncomp=1, clamp=((0, 0), (1, 1)))
     cells = c_cells(m, 1)
     nq3 = (p + 1) ** 3
     coef = np.random.default_rng(1).uniform(0.5, 2.0, (m.n_cells, nq3)) if with_coef else None
@@ -239,6 +241,7 @@ def test_laplace_vmult_and_diagonal(p, with_coef):
     ref = np.zeros_like(src)
     orc.vmult(ref, src)
     mf = MatrixFree.from_mesh(m, 1)
+    assert mf.all_cells_affine() == (not mapped)
     op = LaplaceOperator(mf, dt, coef)
     out = np.zeros_like(src)
     op.vmult(out, src)
@@ -248,9 +251,10 @@ def test_laplace_vmult_and_diagonal(p, with_coef):
         assert rel(op.get_matrix_diagonal(), orc.compute_diagonal()) < TOL64
 
 
-def test_laplace_fp32():
+@pytest.mark.parametrize("mapped", [True, False], ids=["general", "affine"])
+def test_laplace_fp32(mapped):
     p = 4
-    m = make_mesh(p, NCELLS[p], ncomp=1, clamp=((0, 0),))
+    m = make_mesh(p, NCELLS[p], mapped=mapped, ncomp=1, clamp=((0, 0),))
     orc = CO.LaplaceOperator(c_cells(m, 1), 0.1)
     src = np.random.default_rng(0).uniform(-1, 1, m.n_nodes)
     ref = np.zeros_like(src)
@@ -312,3 +316,32 @@ def test_symmetry_large_random():
     assert abs(b @ Aa - a @ Ab) < 1e-11 * abs(b @ Aa)
     con = m.constrained_dofs(3)
     assert np.array_equal(Aa[con], a[con])
+
+
+# ---------------------------------------------------------------------------
+# cell part of assemble_residual (mf_elasticity.h:1764-1846) against the dense numpy oracle
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("formulation", [1, 0])
+def test_nh_residual_cells(p, formulation):
+    from b200mf import DeviceVector
+    from common import np_cells
+    from oracle import np_oracle as NO
+
+    m = make_mesh(p, NCELLS[p])
+    u = displacement(m)
+    rng = np.random.default_rng(100 + p)
+    acc = rng.uniform(-1, 1, 3 * m.n_nodes) * 50.0
+    bf = (0.0, -0.5, 0.25)
+    mat = NO.Material(formulation=formulation, **MAT)
+    ref = NO.nh_residual(np_cells(m), mat, u, acc, bf)
+    mf = MatrixFree.from_mesh(m, 3)
+    op = NeoHookOperator()
+    op.set_material(mf, dict(formulation=formulation, **MAT))
+    rhs = DeviceVector(mf)
+    op.assemble_residual(rhs, DeviceVector(mf, u), DeviceVector(mf, acc), bf)
+    out = rhs.download()
+    assert rel(out, ref) < TOL64
+    # constrained rows are not written (distribute_local_to_global), and set_zero keeps them zero
+    assert np.all(out[m.constrained_dofs(3)] == 0.0)
+    rhs.set_zero_constrained()
+    assert rel(rhs.download(), ref) < TOL64

@@ -25,15 +25,21 @@ def ideal(addrs, wordsize):
     return sum(1 for h in halves if any(x is not None for x in h))
 
 
+def group_cells(N, NC):
+    """mirror of group_cells() in csrc/cell_kernel.cuh"""
+    if NC == 1:
+        return {2: 8, 3: 7, 4: 8, 5: 6, 6: 4}.get(N, 2)
+    return 32 // (N * N) if N * N <= 16 else (2 if N == 5 else 1)
+
+
 def evaluate(N, NC, PL, CZ, CQ, ws, CCZ=0, CCQ=0, FQ=0, which="zq"):
     N2 = N * N
-    warp = N2 <= 32
-    CPG = 32 // N2 if warp else 1
+    CPG = group_cells(N, NC)
     L = CPG * N2
     NT = CPG * NC * N
     exc = 0
     tot = 0
-    nwarps = 1 if warp else (N2 + 31) // 32
+    nwarps = (L + 31) // 32
 
     def zaddr(cw, c, kq, e):
         return cw * (NC * (N * PL + CCZ) + CZ) + c * (N * PL + CCZ) + kq * PL + e
@@ -66,13 +72,18 @@ def evaluate(N, NC, PL, CZ, CQ, ws, CCZ=0, CCQ=0, FQ=0, which="zq"):
 
 
 if __name__ == "__main__":
+    # usage: smem_layout_search2.py [max extra plane stride] [N ...]
     R = range(0, 16, 1)
+    extra = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+    only = [int(a) for a in sys.argv[2:]]
     for ws in (8, 4):
         for NC in (3, 1):
             for N in range(2, 8):
+                if only and N not in only:
+                    continue
                 N2 = N * N
                 best = None
-                for PL in range(N2, N2 + 3):
+                for PL in range(N2, N2 + extra):
                     bz = min(((evaluate(N, NC, PL, CZ, 0, ws, CCZ, 0, 0, "z")[0], CZ + CCZ, CZ, CCZ) for CZ in R for CCZ in (R if NC > 1 else [0])))
                     bq = min(((evaluate(N, NC, PL, 0, CQ, ws, 0, CCQ, FQ, "q")[0], CQ + CCQ + FQ, CQ, CCQ, FQ) for CQ in R for CCQ in (R if NC > 1 else [0]) for FQ in R))
                     key = (bz[0] + bq[0], PL)
