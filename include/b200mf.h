@@ -179,6 +179,11 @@ int b200mf_nh_vmult(b200mf_nh *op, void *dst_dvec, const void *src_dvec);
 int b200mf_nh_vmult_add(b200mf_nh *op, void *dst_dvec, const void *src_dvec);
 int b200mf_nh_Tvmult(b200mf_nh *op, void *dst_dvec, const void *src_dvec);
 int b200mf_nh_Tvmult_add(b200mf_nh *op, void *dst_dvec, const void *src_dvec);
+/* "Fused solver vector work": vmult that also accumulates *dot_device += src . (A src) (this rank's cells and identity
+ * rows; sum over ranks = the global value) inside the operator pass - the p . Ap of SolverCG without a second sweep
+ * over the vectors.  dot_device is a device double the caller zeroes. */
+int b200mf_nh_vmult_dot(b200mf_nh *op, void *dst_dvec, const void *src_dvec, double *dot_device);
+int b200mf_nh_vmult_dot_host(b200mf_nh *op, void *dst_dvec, const void *src_dvec, double *result_host); /* summed over ranks */
 /* parity / drop-in mode: caller-owned host vectors, H2D + vmult + D2H */
 int b200mf_nh_vmult_host(b200mf_nh *op, double *dst_host, const double *src_host);
 /* compute_diagonal(), mf_nh_operator.h:1023-1060: fills diagonal and inverse (constrained -> 1) */
@@ -214,6 +219,8 @@ int b200mf_laplace_set_delta_t(b200mf_laplace *op, double delta_t); /* set_delta
 int b200mf_laplace_vmult(b200mf_laplace *op, void *dst_dvec, const void *src_dvec);     /* Base::vmult -> apply_add :194-201 */
 int b200mf_laplace_vmult_add(b200mf_laplace *op, void *dst_dvec, const void *src_dvec);
 int b200mf_laplace_Tvmult(b200mf_laplace *op, void *dst_dvec, const void *src_dvec);
+int b200mf_laplace_vmult_dot(b200mf_laplace *op, void *dst_dvec, const void *src_dvec, double *dot_device);
+int b200mf_laplace_vmult_dot_host(b200mf_laplace *op, void *dst_dvec, const void *src_dvec, double *result_host);
 int b200mf_laplace_vmult_host(b200mf_laplace *op, double *dst_host, const double *src_host);
 int b200mf_laplace_compute_diagonal(b200mf_laplace *op); /* :205-230 */
 int b200mf_laplace_diagonal(b200mf_laplace *op, const void **diag_dvec, const void **inv_diag_dvec);

@@ -77,6 +77,10 @@ SIGNATURES = {
     "b200mf_ctx_memory_consumption": (C.c_size_t, [_vp]),
     "b200mf_nh_assemble_residual": (_i32, [_vp, _vp, _vp, _vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "b200mf_vec_set_zero_constrained": (_i32, [_vp, _vp]),
+    "b200mf_nh_vmult_dot": (_i32, [_vp, _vp, _vp, _vp]),
+    "b200mf_nh_vmult_dot_host": (_i32, [_vp, _vp, _vp, C.POINTER(C.c_double)]),
+    "b200mf_laplace_vmult_dot_host": (_i32, [_vp, _vp, _vp, C.POINTER(C.c_double)]),
+    "b200mf_laplace_vmult_dot": (_i32, [_vp, _vp, _vp, _vp]),
     "b200mf_vec_create": (_i32, [_vp, _PP]),
     "b200mf_vec_destroy": (_i32, [_vp, _vp]),
     "b200mf_vec_upload": (_i32, [_vp, _vp, _vp]),

@@ -285,6 +285,12 @@ class NeoHookOperator:
         else:
             _l.check(L.b200mf_nh_vmult(self.h, _dv(dst), _dv(src)))
 
+    def vmult_dot(self, dst, src):
+        """dst = A src and return src . (A src), accumulated inside the operator pass (fused CG dot product)."""
+        out = C.c_double(0)
+        _l.check(_l.load().b200mf_nh_vmult_dot_host(self.h, _dv(dst), _dv(src), C.byref(out)))
+        return out.value
+
     def vmult_add(self, dst, src):
         _l.check(_l.load().b200mf_nh_vmult_add(self.h, _dv(dst), _dv(src)))
 
@@ -366,6 +372,12 @@ class LaplaceOperator:
             _l.check(L.b200mf_laplace_vmult(self.h, _dv(dst), _dv(src)))
 
     Tvmult = vmult
+
+    def vmult_dot(self, dst, src):
+        """dst = A src and return src . (A src), accumulated inside the operator pass (fused CG dot product)."""
+        out = C.c_double(0)
+        _l.check(_l.load().b200mf_laplace_vmult_dot_host(self.h, _dv(dst), _dv(src), C.byref(out)))
+        return out.value
 
     def vmult_add(self, dst, src):
         _l.check(_l.load().b200mf_laplace_vmult_add(self.h, _dv(dst), _dv(src)))

@@ -271,9 +271,20 @@ __global__ void permute_out_kernel(int64_t n, const int64_t *__restrict__ int2ex
 
 // dst[c] += src[c] on constrained rows (mf_nh_operator.h:623-624; MatrixFreeOperators::Base::vmult)
 template <typename T>
-__global__ void constrained_identity_kernel(int64_t n, const uint32_t *__restrict__ idx, T *__restrict__ dst, const T *__restrict__ src) {
+__global__ void constrained_identity_kernel(int64_t n, const uint32_t *__restrict__ idx, T *__restrict__ dst, const T *__restrict__ src,
+                                            double *dot) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[idx[i]] += src[idx[i]];
+  double s = 0.0;
+  if (i < n) {
+    const T v = src[idx[i]];
+    dst[idx[i]] += v;
+    s = (double)v * (double)v;
+  }
+  if (dot != nullptr) {  // the identity rows' share of src . (A src)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s != 0.0) atomicAdd(dot, s);
+  }
 }
 
 // diag[constrained] = 1 (mf_nh_operator.h:1043-1044, heat_transfer.h:220)
@@ -668,6 +679,7 @@ extern "C" int b200mf_ctx_destroy(b200mf_ctx *c) {
   cudaFree(c->nidx);
   cudaFree(c->mref);
   cudaFree(c->mcell);
+  cudaFree(c->scalars);
   cudaFree(c->cell_order);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   for (cudaEvent_t e : c->ev) if (e) cudaEventDestroy(e);
@@ -1014,31 +1026,31 @@ static int apply_cells_with_exchange(b200mf_ctx *c, void *dst, const void *src, 
 }
 
 template <typename T>
-static int constrained_identity(b200mf_ctx *c, void *dst, const void *src) {  // :623-624
+static int constrained_identity(b200mf_ctx *c, void *dst, const void *src, double *dot = nullptr) {  // :623-624
   if (c->n_constrained) {
-    constrained_identity_kernel<T><<<nblocks(c->n_constrained, 256), 256, 0, c->stream>>>(c->n_constrained, c->constrained, (T *)dst, (const T *)src);
+    constrained_identity_kernel<T><<<nblocks(c->n_constrained, 256), 256, 0, c->stream>>>(c->n_constrained, c->constrained, (T *)dst, (const T *)src, dot);
     B2_LAUNCHED();
   }
   return 0;
 }
 
 template <typename T>
-static int nh_apply_t(b200mf_nh *op, void *dst, const void *src) {
+static int nh_apply_t(b200mf_nh *op, void *dst, const void *src, double *dot) {
   b200mf_ctx *c = op->ctx;
   const NHArgs<T> oa = nh_args<T>(op);
   B2_TRY(apply_cells_with_exchange(c, dst, src, [&](int64_t g0, int64_t g1, cudaStream_t s) {
-    return run_nh<T>(c, op->variant, (const T *)src, (T *)dst, oa, g0, g1, s);
+    return run_nh<T>(c, op->variant, (const T *)src, (T *)dst, oa, g0, g1, s, dot);
   }));
-  return constrained_identity<T>(c, dst, src);
+  return constrained_identity<T>(c, dst, src, dot);
 }
 
-static int nh_apply(b200mf_nh *op, void *dst, const void *src, bool zero_dst) {
+static int nh_apply(b200mf_nh *op, void *dst, const void *src, bool zero_dst, double *dot = nullptr) {
   if (!op || !dst || !src) return set_error(B200MF_ERR_ARG, "null argument");
   if (dst == src) return set_error(B200MF_ERR_ARG, "vmult: dst aliases src");
   if (!op->cached) return set_error(B200MF_ERR_STATE, "vmult before cache()");
   b200mf_ctx *c = op->ctx;
   if (zero_dst) B2_CUDA(cudaMemsetAsync(dst, 0, c->n_int * esize(c), c->stream));  // vmult: dst = 0, :548
-  int rc = c->dtype == B200MF_F64 ? nh_apply_t<double>(op, dst, src) : nh_apply_t<float>(op, dst, src);
+  int rc = c->dtype == B200MF_F64 ? nh_apply_t<double>(op, dst, src, dot) : nh_apply_t<float>(op, dst, src, dot);
   B2_TRY(rc);
   B2_CUDA(cudaGetLastError());
   return 0;
@@ -1048,6 +1060,31 @@ extern "C" int b200mf_nh_vmult(b200mf_nh *op, void *dst, const void *src) { retu
 extern "C" int b200mf_nh_vmult_add(b200mf_nh *op, void *dst, const void *src) { return nh_apply(op, dst, src, false); }
 extern "C" int b200mf_nh_Tvmult(b200mf_nh *op, void *dst, const void *src) { return nh_apply(op, dst, src, true); }       // :556-561
 extern "C" int b200mf_nh_Tvmult_add(b200mf_nh *op, void *dst, const void *src) { return nh_apply(op, dst, src, false); }  // :566-571
+
+// vmult with the CG dot product fused into the operator pass: *dot_device += (this rank's share of) src . (A src)
+extern "C" int b200mf_nh_vmult_dot(b200mf_nh *op, void *dst, const void *src, double *dot_device) {
+  if (!dot_device) return set_error(B200MF_ERR_ARG, "null argument");
+  return nh_apply(op, dst, src, true, dot_device);
+}
+
+static int fused_dot_result(b200mf_ctx *c, double *result_host) {
+  B2_TRY(allreduce_sum_f64(c, c->scalars, 1));
+  B2_CUDA(cudaMemcpyAsync(result_host, c->scalars, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+static int fused_dot_slot(b200mf_ctx *c) {
+  if (!c->scalars) B2_CUDA(cudaMalloc(&c->scalars, 8 * sizeof(double)));
+  B2_CUDA(cudaMemsetAsync(c->scalars, 0, sizeof(double), c->stream));
+  return 0;
+}
+// same, result summed over ranks and returned on the host
+extern "C" int b200mf_nh_vmult_dot_host(b200mf_nh *op, void *dst, const void *src, double *result_host) {
+  if (!op || !result_host) return set_error(B200MF_ERR_ARG, "null argument");
+  B2_TRY(fused_dot_slot(op->ctx));
+  B2_TRY(nh_apply(op, dst, src, true, op->ctx->scalars));
+  return fused_dot_result(op->ctx, result_host);
+}
 
 extern "C" int b200mf_nh_vmult_host(b200mf_nh *op, double *dst, const double *src) {
   if (!op || !dst || !src) return set_error(B200MF_ERR_ARG, "null argument");
@@ -1323,21 +1360,21 @@ static LaplaceArgs<T> laplace_args(const b200mf_laplace *op) {
   return oa;
 }
 template <typename T>
-static int laplace_apply_t(b200mf_laplace *op, void *dst, const void *src) {
+static int laplace_apply_t(b200mf_laplace *op, void *dst, const void *src, double *dot) {
   b200mf_ctx *c = op->ctx;
   const LaplaceArgs<T> oa = laplace_args<T>(op);
   B2_TRY(apply_cells_with_exchange(c, dst, src, [&](int64_t g0, int64_t g1, cudaStream_t s) {
-    return run_laplace<T>(c, false, (const T *)src, (T *)dst, oa, g0, g1, s);
+    return run_laplace<T>(c, false, (const T *)src, (T *)dst, oa, g0, g1, s, dot);
   }));
-  return constrained_identity<T>(c, dst, src);
+  return constrained_identity<T>(c, dst, src, dot);
 }
 
-static int laplace_apply(b200mf_laplace *op, void *dst, const void *src, bool zero_dst) {
+static int laplace_apply(b200mf_laplace *op, void *dst, const void *src, bool zero_dst, double *dot = nullptr) {
   if (!op || !dst || !src) return set_error(B200MF_ERR_ARG, "null argument");
   if (dst == src) return set_error(B200MF_ERR_ARG, "vmult: dst aliases src");
   b200mf_ctx *c = op->ctx;
   if (zero_dst) B2_CUDA(cudaMemsetAsync(dst, 0, c->n_int * esize(c), c->stream));
-  int rc = c->dtype == B200MF_F64 ? laplace_apply_t<double>(op, dst, src) : laplace_apply_t<float>(op, dst, src);
+  int rc = c->dtype == B200MF_F64 ? laplace_apply_t<double>(op, dst, src, dot) : laplace_apply_t<float>(op, dst, src, dot);
   B2_TRY(rc);
   B2_CUDA(cudaGetLastError());
   return 0;
@@ -1346,6 +1383,18 @@ static int laplace_apply(b200mf_laplace *op, void *dst, const void *src, bool ze
 extern "C" int b200mf_laplace_vmult(b200mf_laplace *op, void *dst, const void *src) { return laplace_apply(op, dst, src, true); }
 extern "C" int b200mf_laplace_vmult_add(b200mf_laplace *op, void *dst, const void *src) { return laplace_apply(op, dst, src, false); }
 extern "C" int b200mf_laplace_Tvmult(b200mf_laplace *op, void *dst, const void *src) { return laplace_apply(op, dst, src, true); }
+
+extern "C" int b200mf_laplace_vmult_dot(b200mf_laplace *op, void *dst, const void *src, double *dot_device) {
+  if (!dot_device) return set_error(B200MF_ERR_ARG, "null argument");
+  return laplace_apply(op, dst, src, true, dot_device);
+}
+
+extern "C" int b200mf_laplace_vmult_dot_host(b200mf_laplace *op, void *dst, const void *src, double *result_host) {
+  if (!op || !result_host) return set_error(B200MF_ERR_ARG, "null argument");
+  B2_TRY(fused_dot_slot(op->ctx));
+  B2_TRY(laplace_apply(op, dst, src, true, op->ctx->scalars));
+  return fused_dot_result(op->ctx, result_host);
+}
 
 extern "C" int b200mf_laplace_vmult_host(b200mf_laplace *op, double *dst, const double *src) {
   if (!op || !dst || !src) return set_error(B200MF_ERR_ARG, "null argument");

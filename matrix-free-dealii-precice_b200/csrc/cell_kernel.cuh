@@ -161,6 +161,8 @@ struct CellArgs {
   const T *src;
   T *dst;
   int64_t cstride;  // vector layout: DoF (node, c) lives at c*cstride + node ("component blocks")
+  double *dot;      // non-null: += sum over the cells of u_cell . (A_cell u_cell), i.e. this rank's share of src . (A src)
+                    // on the unconstrained rows: the CG dot product p . Ap fused into the operator pass
 };
 
 // 1-D sweeps on a register column -------------------------------------------
@@ -226,7 +228,7 @@ struct KernelSmem {
   static constexpr size_t GROUP_BYTES = BUF_BYTES + ST1_BYTES + ST2_BYTES + SCR_BYTES + 16;                // + mbarrier
 };
 
-template <typename T, int N, class Op, int GPB, bool DIAG = false, int MINB = 1>
+template <typename T, int N, class Op, int GPB, bool DIAG = false, int MINB = 1, bool DOT = false>
 __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
     cell_loop_kernel(const CellArgs<T> A, const typename Op::Args oa) {
   constexpr int NC = Op::NC;
@@ -314,6 +316,7 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
     if (!DIAG) gather(nid, u);
   }
 
+  double dot_acc = 0.0;  // DOT: the fused p . Ap of SolverCG (a separate instantiation: the plain vmult pays nothing)
   for (; group < A.n_groups; group += gstep) {
     const int64_t gnext = group + gstep;
     const bool has_next = gnext < A.n_groups;
@@ -531,6 +534,14 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
             continue;
           }
           Op::quad(oa, st, active, qs, qs2, scr, group, kq, lane, v, G, ov, oG);
+          if constexpr (DOT) {
+            // src . (A src) = sum over cells and q-points of (value, gradient) . (submitted value, gradient): every operand
+            // is live here, so the fused dot product costs no registers beyond its accumulator
+            T e = T(0);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) e += v[c] * ov[c] + G[c][0] * oG[c][0] + G[c][1] * oG[c][1] + G[c][2] * oG[c][2];
+            dot_acc += (double)e;
+          }
           if (Op::INTEGRATE) {
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
@@ -636,6 +647,11 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
     if (!Op::INTEGRATE && has_next) gather(nid_next, u);  // evaluation-only ops (cache): plain prefetch
 #pragma unroll
     for (int k = 0; k < N; ++k) nid[k] = nid_next[k];
+  }
+  if constexpr (DOT) {  // one atomic per warp and launch
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot_acc += __shfl_down_sync(0xffffffffu, dot_acc, o);
+    if ((threadIdx.x & 31) == 0 && dot_acc != 0.0) atomicAdd(A.dot, dot_acc);
   }
 }
 

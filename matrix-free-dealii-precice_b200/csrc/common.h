@@ -74,6 +74,7 @@ struct b200mf_ctx {
   cudaStream_t comm_stream;   // exchanges that overlap the interior cells run here
   cudaEvent_t ev[4];
   int overlap;                // 1: hide the exchanges behind interior cells (default when partitioned)
+  double *scalars;            // a few device doubles for fused reductions (lazily allocated)
   void *mcell;           // T [cell][MC_COUNT] per-cell metric when every cell is affine, else null
   uint8_t *matid;        // [n_cells] or nullptr
   int64_t *int2ext;      // [n_int] or nullptr when identity

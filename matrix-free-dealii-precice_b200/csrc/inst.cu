@@ -17,9 +17,9 @@ using TT = INST_T;
 #if INST_KIND == 1
 template <>
 int run_nh<TT>(const b200mf_ctx *ctx, int variant, const TT *src, TT *dst, const NHArgs<TT> &oa, int64_t g0, int64_t g1,
-               cudaStream_t stream) {
+               cudaStream_t stream, double *dot) {
   int rc = 0;
-  B2_DISPATCH_N(ctx->N, TT, { B2_DISPATCH_NHV(variant, { rc = launch_cell_loop<T, N, NHOp<T, N, V>>(ctx, src, dst, oa, g0, g1, stream); }); });
+  B2_DISPATCH_N(ctx->N, TT, { B2_DISPATCH_NHV(variant, { rc = launch_cell_loop<T, N, NHOp<T, N, V>>(ctx, src, dst, oa, g0, g1, stream, dot); }); });
   return rc;
 }
 #elif INST_KIND == 2
@@ -39,7 +39,7 @@ int run_nh_cache<TT>(const b200mf_ctx *ctx, int variant, const TT *displacement,
 #elif INST_KIND == 4
 template <>
 int run_laplace<TT>(const b200mf_ctx *ctx, bool diag, const TT *src, TT *dst, const LaplaceArgs<TT> &oa, int64_t g0, int64_t g1,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, double *dot) {
   int rc = 0;
   const bool affine = ctx->mcell != nullptr;  // every cell affine: per-cell metric, nothing streamed per q-point
   B2_DISPATCH_N(ctx->N, TT, {
@@ -47,8 +47,8 @@ int run_laplace<TT>(const b200mf_ctx *ctx, bool diag, const TT *src, TT *dst, co
       rc = affine ? launch_cell_loop<T, N, LaplaceAffineOp<T, N>, true>(ctx, (const T *)nullptr, dst, oa)
                   : launch_cell_loop<T, N, LaplaceOp<T, N>, true>(ctx, (const T *)nullptr, dst, oa);
     else
-      rc = affine ? launch_cell_loop<T, N, LaplaceAffineOp<T, N>>(ctx, src, dst, oa, g0, g1, stream)
-                  : launch_cell_loop<T, N, LaplaceOp<T, N>>(ctx, src, dst, oa, g0, g1, stream);
+      rc = affine ? launch_cell_loop<T, N, LaplaceAffineOp<T, N>>(ctx, src, dst, oa, g0, g1, stream, dot)
+                  : launch_cell_loop<T, N, LaplaceOp<T, N>>(ctx, src, dst, oa, g0, g1, stream, dot);
   });
   return rc;
 }

@@ -10,7 +10,8 @@ void shape_tables(const double **hd, const float **hf);  // [MAXN+1][3][MAXN*MAX
 
 // cell-group range [g0, g1) on `stream`
 template <typename T>
-int run_nh(const b200mf_ctx *ctx, int variant, const T *src, T *dst, const NHArgs<T> &oa, int64_t g0, int64_t g1, cudaStream_t stream);
+int run_nh(const b200mf_ctx *ctx, int variant, const T *src, T *dst, const NHArgs<T> &oa, int64_t g0, int64_t g1, cudaStream_t stream,
+           double *dot = nullptr);  // dot: see CellArgs::dot
 template <typename T>
 int run_nh_diag(const b200mf_ctx *ctx, int variant, T *diag, const NHArgs<T> &oa);
 template <typename T>
@@ -19,6 +20,6 @@ template <typename T>
 int run_nh_residual(const b200mf_ctx *ctx, const T *displacement, T *rhs, const NHResidualArgs<T> &oa);
 template <typename T>
 int run_laplace(const b200mf_ctx *ctx, bool diag, const T *src, T *dst, const LaplaceArgs<T> &oa, int64_t g0, int64_t g1,
-                cudaStream_t stream);
+                cudaStream_t stream, double *dot = nullptr);
 
 }  // namespace b200mf

@@ -23,11 +23,14 @@ static int ensure_shape_constants() {
 // ---------------------------------------------------------------------------
 // launch of the templated cell loop
 
-template <typename T, int N, class Op, bool DIAG, int GPB, int MINB>
+template <typename T, int N, class Op, bool DIAG, int GPB, int MINB, bool DOT = false>
 static int launch_variant(const b200mf_ctx *ctx, const T *src, T *dst, const typename Op::Args &oa, int64_t g0, int64_t g1,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, double *dot) {
   using Ly = Layout<N, Op::NC, sizeof(T) / 4>;
-  auto kern = cell_loop_kernel<T, N, Op, GPB, DIAG, MINB>;
+  if constexpr (!DOT && !DIAG && !Op::PLAIN) {
+    if (dot != nullptr) return launch_variant<T, N, Op, DIAG, GPB, MINB, true>(ctx, src, dst, oa, g0, g1, stream, dot);
+  }
+  auto kern = cell_loop_kernel<T, N, Op, GPB, DIAG, MINB, DOT>;
   const size_t smem = (size_t)GPB * KernelSmem<T, N, Op, DIAG>::GROUP_BYTES;
   static int occ = 0;  // per instantiation
   B2_TRY(ensure_shape_constants());
@@ -53,6 +56,7 @@ static int launch_variant(const b200mf_ctx *ctx, const T *src, T *dst, const typ
   A.src = src;
   A.dst = dst;
   A.cstride = ctx->cstride;
+  A.dot = dot;
   const int64_t want = (g1 - g0 + GPB - 1) / GPB;
   const int64_t cap = (int64_t)ctx->sm_count * occ;
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min(want, cap));
@@ -65,7 +69,7 @@ static int launch_variant(const b200mf_ctx *ctx, const T *src, T *dst, const typ
 
 template <typename T, int N, class Op, bool DIAG = false>
 static int launch_cell_loop(const b200mf_ctx *ctx, const T *src, T *dst, const typename Op::Args &oa, int64_t g0 = 0, int64_t g1 = -1,
-                            cudaStream_t stream = nullptr) {
+                            cudaStream_t stream = nullptr, double *dot = nullptr) {
   using Ly = Layout<N, Op::NC, sizeof(T) / 4>;
   if (g1 < 0) g1 = ctx->n_groups;
   if (!stream) stream = ctx->stream;
@@ -73,7 +77,7 @@ static int launch_cell_loop(const b200mf_ctx *ctx, const T *src, T *dst, const t
     // scalar Q4 (6 cells per 160-thread group): cap the registers at two resident groups per SM - only one warp of a
     // group works during the plane phase, a second group keeps the FP64 pipe fed (B200: 0.94 -> 0.69 ms at 1.7e7 DoFs)
     constexpr int MINB = (Op::NC == 1 && N == 5 && !DIAG) ? 2 : 1;
-    return launch_variant<T, N, Op, DIAG, 1, MINB>(ctx, src, dst, oa, g0, g1, stream);
+    return launch_variant<T, N, Op, DIAG, 1, MINB>(ctx, src, dst, oa, g0, g1, stream, dot);
   } else {
     // warps per block, from the B200 sweep tools/gpu_gpb_sweep.sh (profiles/r01_v3_gpb_sweep.jsonl): shared memory
     // (cell buffers + staged table) bounds the resident warps and small blocks pack an SM best; N = 2 has 8 cells
@@ -81,11 +85,11 @@ static int launch_cell_loop(const b200mf_ctx *ctx, const T *src, T *dst, const t
     constexpr int GPB = (N == 2 ? 4 : N == 3 ? 2 : (N == 4 && sizeof(T) == 4) ? 2 : 1);
 #ifdef B200MF_GPB_SWEEP  // tuning builds only: B200MF_GPB=1|2|4 picks the block size at run time
     static const int gpb_env = getenv("B200MF_GPB") ? atoi(getenv("B200MF_GPB")) : 0;
-    if (gpb_env == 1) return launch_variant<T, N, Op, DIAG, 1, 1>(ctx, src, dst, oa, g0, g1, stream);
-    if (gpb_env == 2) return launch_variant<T, N, Op, DIAG, 2, 1>(ctx, src, dst, oa, g0, g1, stream);
-    if (gpb_env == 4) return launch_variant<T, N, Op, DIAG, 4, 1>(ctx, src, dst, oa, g0, g1, stream);
+    if (gpb_env == 1) return launch_variant<T, N, Op, DIAG, 1, 1>(ctx, src, dst, oa, g0, g1, stream, dot);
+    if (gpb_env == 2) return launch_variant<T, N, Op, DIAG, 2, 1>(ctx, src, dst, oa, g0, g1, stream, dot);
+    if (gpb_env == 4) return launch_variant<T, N, Op, DIAG, 4, 1>(ctx, src, dst, oa, g0, g1, stream, dot);
 #endif
-    return launch_variant<T, N, Op, DIAG, GPB, 1>(ctx, src, dst, oa, g0, g1, stream);
+    return launch_variant<T, N, Op, DIAG, GPB, 1>(ctx, src, dst, oa, g0, g1, stream, dot);
   }
 }
 

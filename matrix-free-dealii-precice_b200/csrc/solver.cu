@@ -143,6 +143,7 @@ __global__ void zero_indexed_kernel2(int64_t n, const uint32_t *__restrict__ idx
 struct LinOp {
   b200mf_ctx *ctx = nullptr;
   std::function<int(void *, const void *)> vmult;
+  std::function<int(void *, const void *, double *)> vmult_dot;  // dst = A src and *slot += src . (A src) in one operator pass
   std::function<int(const void **)> inv_diag;
 };
 
@@ -293,9 +294,13 @@ static int cg_solve_t(LinOp &A, const CGPrecond &P, T *x, const T *b, double tol
       axpby_kernel<T><<<g, 256, 0, st>>>(n, T(1), direction, T(0), p);
     }
     B2_LAUNCHED();
-    B2_TRY(A.vmult(v, p));
     B2_CUDA(cudaMemsetAsync(sc.d, 0, 8 * sizeof(double), st));
-    B2_TRY(dot_t<T>(c, p, v, sc.d));
+    if (A.vmult_dot) {
+      B2_TRY(A.vmult_dot(v, p, sc.d));  // p . Ap accumulated inside the cell loop
+    } else {
+      B2_TRY(A.vmult(v, p));
+      B2_TRY(dot_t<T>(c, p, v, sc.d));
+    }
     B2_TRY(fetch(c, sc, 1));
     const double pAp = sc.h[0];
     alpha = rPr / pAp;
@@ -339,6 +344,7 @@ static LinOp linop_nh(b200mf_nh *op, b200mf_ctx *ctx) {
   LinOp A;
   A.ctx = ctx;
   A.vmult = [op](void *d, const void *s) { return b200mf_nh_vmult(op, d, s); };
+  A.vmult_dot = [op](void *d, const void *s, double *slot) { return b200mf_nh_vmult_dot(op, d, s, slot); };
   A.inv_diag = [op](const void **inv) { return b200mf_nh_diagonal(op, nullptr, inv); };
   return A;
 }
@@ -346,6 +352,7 @@ static LinOp linop_laplace(b200mf_laplace *op, b200mf_ctx *ctx) {
   LinOp A;
   A.ctx = ctx;
   A.vmult = [op](void *d, const void *s) { return b200mf_laplace_vmult(op, d, s); };
+  A.vmult_dot = [op](void *d, const void *s, double *slot) { return b200mf_laplace_vmult_dot(op, d, s, slot); };
   A.inv_diag = [op](const void **inv) { return b200mf_laplace_diagonal(op, nullptr, inv); };
   return A;
 }

@@ -345,3 +345,32 @@ def test_nh_residual_cells(p, formulation):
     assert np.all(out[m.constrained_dofs(3)] == 0.0)
     rhs.set_zero_constrained()
     assert rel(rhs.download(), ref) < TOL64
+
+
+# "Fused solver vector work": p . Ap accumulated inside the operator pass (b200mf_*_vmult_dot)
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_vmult_dot_fused(p, dtype):
+    from b200mf import DeviceVector
+
+    m = make_mesh(p, NCELLS[p])
+    u = displacement(m)
+    src = np.random.default_rng(p).uniform(-1, 1, 3 * m.n_nodes)  # non-zero on constrained rows: identity rows count too
+    mf, op = gpu_nh(m, u, dtype=dtype)
+    s, d = DeviceVector(mf, src), DeviceVector(mf)
+    op.vmult(d, s)
+    ref_vec = d.download()
+    ref = float(np.dot(s.download(), ref_vec))
+    val = op.vmult_dot(d, s)
+    assert np.array_equal(d.download(), ref_vec) or rel(d.download(), ref_vec) < (1e-14 if dtype == "f64" else 1e-6)
+    assert abs(val - ref) <= (1e-12 if dtype == "f64" else 2e-5) * abs(ref)
+    # scalar operator, affine and general cells
+    for mapped in (True, False):
+        ms = make_mesh(p, NCELLS[p], mapped=mapped, ncomp=1, clamp=((0, 0),))
+        mfs = MatrixFree.from_mesh(ms, 1, dtype=dtype)
+        lop = LaplaceOperator(mfs, 0.1)
+        x = np.random.default_rng(3).uniform(-1, 1, ms.n_nodes)
+        xs, ys = DeviceVector(mfs, x), DeviceVector(mfs)
+        v = lop.vmult_dot(ys, xs)
+        r = float(np.dot(xs.download(), ys.download()))
+        assert abs(v - r) <= (1e-12 if dtype == "f64" else 2e-5) * abs(r)
