@@ -105,8 +105,8 @@ int b200mf_ctx_synchronize(b200mf_ctx *ctx);
  * b200mf_ctx_kernel_time synchronises and returns their summed duration and the number of launches since `on` */
 int b200mf_ctx_time_kernels(b200mf_ctx *ctx, int on);
 int b200mf_ctx_kernel_time(b200mf_ctx *ctx, double *total_ms, int64_t *n_launches);
-/* multi-rank contexts: 1 (default) hides update_ghost_values / compress(add) of vmult behind the interior cells on a
- * second stream, 0 runs exchange -> cells -> exchange on one stream as the reference does (mf_nh_operator.h:598-620),
+/* multi-rank contexts: 1 (default; env B200MF_OVERLAP) hides update_ghost_values / compress(add) of vmult behind the interior
+ * cells on a second stream, 0 runs exchange -> cells -> exchange on one stream as the reference does (mf_nh_operator.h:598-620),
  * -1 skips the exchanges (rank-local result; only for measuring the exposed exchange time) */
 int b200mf_ctx_set_overlap(b200mf_ctx *ctx, int on);
 /* 1: every cell is affine (one Jacobian per cell, as deal.II's MappingInfo compresses Cartesian/affine cells), 0: general */

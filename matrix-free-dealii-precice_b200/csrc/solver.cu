@@ -7,6 +7,7 @@
 // the Chebyshev smoother and the whole V-cycle run without any host synchronisation.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <memory>
@@ -324,6 +325,132 @@ static int cg_solve_t(LinOp &A, const CGPrecond &P, T *x, const T *b, double tol
   return 0;
 }
 
+// ---------------------------------------------------------------------------
+// Sync-free CG for the eigenvalue estimate of PreconditionChebyshev (fixed iteration count, diagonal preconditioner):
+// alpha and beta never leave the device; every iteration enqueues its kernels without a host round trip (the
+// synchronising loop above costs 3 stream synchronisations per iteration, which dominated the coarse levels).
+// Device scalars S[]: 0 r.z (new)  1 r.z (old)  2 p.Ap  3 r.r  4 alpha  5 beta;  history H[3][max_it + 1] = alpha, beta, r.r
+template <typename T>
+__global__ void axpby_dev_kernel(int64_t n, const T *__restrict__ x, const double *__restrict__ b, T *__restrict__ y) {
+  const T beta = (T)*b;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = x[i] + (beta == T(0) ? T(0) : beta * y[i]);
+}
+template <typename T>
+__global__ void cg_update_dev_kernel(int64_t n, Own own, const double *__restrict__ a, const T *__restrict__ p, const T *__restrict__ v,
+                                     T *__restrict__ x, T *__restrict__ r, double *out) {
+  const T alpha = (T)*a;
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] += alpha * p[i];
+    const T rn = r[i] - alpha * v[i];
+    r[i] = rn;
+    if (own(i)) s += (double)rn * (double)rn;
+  }
+  s = block_sum(s);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
+// after r.z: beta = r.z / (r.z)_old, keep the previous r.r in the history, clear the accumulators of this iteration
+__global__ void cg_scalars_beta_kernel(double *S, double *H, int it, int stride) {
+  if (it > 1) H[2 * stride + (it - 1)] = S[3];
+  const double beta = it > 1 ? S[0] / S[1] : 0.0;
+  S[5] = beta;
+  H[stride + it] = beta;
+  S[1] = S[0];
+  S[0] = 0.0;
+  S[2] = 0.0;
+  S[3] = 0.0;
+}
+// after p.Ap: alpha = r.z / p.Ap
+__global__ void cg_scalars_alpha_kernel(double *S, double *H, int it) {
+  const double alpha = S[1] / S[2];
+  S[4] = alpha;
+  H[it] = alpha;
+}
+__global__ void cg_scalars_final_kernel(double *S, double *H, int it, int stride) { H[2 * stride + it] = S[3]; }
+
+template <typename T>
+static int cg_fixed_iterations_t(LinOp &A, double omega, const void *inv, T *x, const T *b, double tol, int max_it, void *const work[3],
+                                 Scratch &sc, CGResult &res) {
+  b200mf_ctx *c = A.ctx;
+  const int64_t n = c->n_int;
+  T *r = (T *)work[0], *p = (T *)work[1], *v = (T *)work[2];
+  cudaStream_t st = c->stream;
+  const Own own = own_of(c);
+  const unsigned g = vgrid(n, c);
+  B2_TRY(sc.init());
+  const int stride = max_it + 1;
+  double *H = nullptr;
+  B2_CUDA(cudaMalloc(&H, 3 * (size_t)stride * sizeof(double)));
+  B2_CUDA(cudaMemsetAsync(H, 0, 3 * (size_t)stride * sizeof(double), st));
+  B2_CUDA(cudaMemcpyAsync(r, b, n * sizeof(T), cudaMemcpyDeviceToDevice, st));  // x = 0
+  B2_CUDA(cudaMemsetAsync(sc.d, 0, 8 * sizeof(double), st));
+  B2_TRY(dot_t<T>(c, r, r, sc.d));
+  B2_TRY(fetch(c, sc, 1));
+  res.initial_residual = std::sqrt(std::fabs(sc.h[0]));
+  res.diag.clear();
+  res.offdiag.clear();
+  if (res.initial_residual <= tol || max_it <= 0) {
+    cudaFree(H);
+    res.iterations = 0;
+    res.residual = res.initial_residual;
+    res.converged = true;
+    return 0;
+  }
+  B2_CUDA(cudaMemsetAsync(sc.d, 0, 8 * sizeof(double), st));
+  double *S = sc.d;
+  for (int it = 1; it <= max_it; ++it) {
+    diag_precond_dot_kernel<T><<<g, 256, 0, st>>>(n, own, (T)omega, (const T *)inv, r, v, S + 0);
+    B2_LAUNCHED();
+    B2_TRY(allreduce_sum_f64(c, S + 0, 1));
+    if (it > 1) B2_TRY(allreduce_sum_f64(c, S + 3, 1));
+    cg_scalars_beta_kernel<<<1, 1, 0, st>>>(S, H, it, stride);
+    B2_LAUNCHED();
+    axpby_dev_kernel<T><<<g, 256, 0, st>>>(n, v, S + 5, p);  // p = z + beta p
+    B2_LAUNCHED();
+    if (A.vmult_dot) {
+      B2_TRY(A.vmult_dot(v, p, S + 2));
+    } else {
+      B2_TRY(A.vmult(v, p));
+      B2_TRY(dot_t<T>(c, p, v, S + 2));
+    }
+    B2_TRY(allreduce_sum_f64(c, S + 2, 1));
+    cg_scalars_alpha_kernel<<<1, 1, 0, st>>>(S, H, it);
+    B2_LAUNCHED();
+    cg_update_dev_kernel<T><<<g, 256, 0, st>>>(n, own, S + 4, p, v, x, r, S + 3);
+    B2_LAUNCHED();
+  }
+  B2_TRY(allreduce_sum_f64(c, S + 3, 1));
+  cg_scalars_final_kernel<<<1, 1, 0, st>>>(S, H, max_it, stride);
+  B2_LAUNCHED();
+  std::vector<double> h(3 * (size_t)stride);
+  B2_CUDA(cudaMemcpyAsync(h.data(), H, h.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+  B2_CUDA(cudaStreamSynchronize(st));
+  cudaFree(H);
+  // replay the stopping rule of the synchronising loop on the recorded history
+  int n_it = max_it;
+  for (int it = 1; it <= max_it; ++it) {
+    const double rn = std::sqrt(std::fabs(h[2 * stride + it]));
+    if (rn <= tol || !(rn == rn)) {
+      n_it = it;
+      break;
+    }
+  }
+  for (int it = 1; it <= n_it; ++it) {
+    const double alpha = h[it], beta = h[stride + it];
+    if (it > 1) {
+      res.diag.push_back(1.0 / alpha + beta / h[it - 1]);
+      res.offdiag.push_back(std::sqrt(beta) / h[it - 1]);
+    } else {
+      res.diag.push_back(1.0 / alpha);
+    }
+  }
+  res.iterations = n_it;
+  res.residual = std::sqrt(std::fabs(h[2 * stride + n_it]));
+  res.converged = true;
+  return 0;
+}
+
 }  // namespace b200mf
 
 using namespace b200mf;
@@ -414,7 +541,10 @@ static int cheb_estimate_t(b200mf_chebyshev *ch) {
     P.omega = 1.0;
     P.inv = inv;
     CGResult r;
-    B2_TRY(cg_solve_t<T>(ch->A, P, x, rhs, 1e-10, ch->data.eig_cg_n_iterations, true, true, ch->w, ch->sc, r));
+    if (getenv("B200MF_SYNC_EIG_CG"))  // the synchronising loop (3 host round trips per iteration), kept for A/B runs
+      B2_TRY(cg_solve_t<T>(ch->A, P, x, rhs, 1e-10, ch->data.eig_cg_n_iterations, true, true, ch->w, ch->sc, r));
+    else
+      B2_TRY(cg_fixed_iterations_t<T>(ch->A, P.omega, P.inv, x, rhs, 1e-10, ch->data.eig_cg_n_iterations, ch->w, ch->sc, r));
     ch->cg_iterations = r.iterations;
     if (r.diag.empty()) {
       mn = mx = 1.0;
