@@ -38,7 +38,8 @@ QPOINT_VALUES = {"tensor2": 18, "scalar_referential": 14, "tensor4": 53, "tensor
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the cell-loop kernel from the committed
 # `ncu --set full` captures (profiles/r01_v3_ncu_summary.md), keyed by (degree, variant, dtype) at the default mesh
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {(2, "tensor2", "f64"): 9.95e9, (3, "tensor2", "f64"): 7.46e9, (4, "tensor2", "f64"): 6.81e9,
+               (3, "tensor2", "f32"): 3.63e9}
 
 
 def algorithmic_bytes_per_cell(p, esize=8, variant="tensor2"):
@@ -74,7 +75,7 @@ def build_problem(p, ncell_dir, dtype="f64", comm=None, caching="tensor2", formu
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region (NVML from a thread, ~4 ms period - a faster poll contends with the launch path for driver locks;
+    """SM clock and throttle reasons sampled DURING the timed region (NVML from a thread, ~10 ms period - a 1 ms poll measurably slows the launch path of multi-rank steps (driver locks);
     the timed region of the default run is only tens of ms, too short for `nvidia-smi -lms`)."""
 
     REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
@@ -114,7 +115,7 @@ class ClockSampler:
                 self.rows.append(self._sample())
             except Exception:
                 break
-            time.sleep(0.004)
+            time.sleep(0.010)
 
     def __enter__(self):
         if self.h is not None:
@@ -134,7 +135,7 @@ class ClockSampler:
             bits |= r[1]
         reasons = sorted(k for k, m in self.REASONS.items() if bits & m)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
-                "samples": len(sm), "how": "NVML clock + clocks-event-reasons polled every ~4 ms inside the timed region"}
+                "samples": len(sm), "how": "NVML clock + clocks-event-reasons polled every ~10 ms inside the timed region"}
 
 
 def cpu_oracle_rate(p, ncell_dir, min_seconds=10.0, max_reps=100000):
@@ -336,11 +337,11 @@ def main():
             return float(t.item())
 
         t_serial, t_overlap, t_none = timed(0), timed(1), timed(-1)
-        mf.set_overlap(1)  # library default on multi-rank contexts
+        mf.set_overlap(0)  # library default
         exchange = {"ms_step_default": ms, "ms_overlapped_exchange": t_overlap, "ms_serial_exchange": t_serial,
                     "ms_no_exchange": t_none, "exposed_ms_overlapped": t_overlap - t_none, "exposed_ms_serial": t_serial - t_none,
-                    "note": "default (timed step) = boundary cells first, exchanges on a second stream behind the interior cells; "
-                            "serial = the reference's order update_ghost_values -> cells -> compress(add); "
+                    "note": "default (timed step) = serial = the reference's order update_ghost_values -> cells -> compress(add); "
+                            "overlapped = boundary cells first, exchanges on a second stream behind the interior cells (opt-in); "
                             "no_exchange = rank-local cells only (measurement mode); 10 steps each after 3 warm-ups"}
 
     # ---- e2e: host buffers through the C-ABI host entry point ----------------------------------

@@ -105,8 +105,8 @@ int b200mf_ctx_synchronize(b200mf_ctx *ctx);
  * b200mf_ctx_kernel_time synchronises and returns their summed duration and the number of launches since `on` */
 int b200mf_ctx_time_kernels(b200mf_ctx *ctx, int on);
 int b200mf_ctx_kernel_time(b200mf_ctx *ctx, double *total_ms, int64_t *n_launches);
-/* multi-rank contexts: 1 (default; env B200MF_OVERLAP) hides update_ghost_values / compress(add) of vmult behind the interior
- * cells on a second stream, 0 runs exchange -> cells -> exchange on one stream as the reference does (mf_nh_operator.h:598-620),
+/* multi-rank contexts: 1 hides update_ghost_values / compress(add) of vmult behind the interior cells on a second stream,
+ * 0 (default; env B200MF_OVERLAP) runs exchange -> cells -> exchange on one stream as the reference does (mf_nh_operator.h:598-620),
  * -1 skips the exchanges (rank-local result; only for measuring the exposed exchange time) */
 int b200mf_ctx_set_overlap(b200mf_ctx *ctx, int on);
 /* 1: every cell is affine (one Jacobian per cell, as deal.II's MappingInfo compresses Cartesian/affine cells), 0: general */
@@ -223,6 +223,13 @@ int b200mf_laplace_vmult_dot(b200mf_laplace *op, void *dst_dvec, const void *src
 int b200mf_laplace_vmult_dot_host(b200mf_laplace *op, void *dst_dvec, const void *src_dvec, double *result_host);
 int b200mf_laplace_vmult_host(b200mf_laplace *op, double *dst_host, const double *src_host);
 int b200mf_laplace_compute_diagonal(b200mf_laplace *op); /* :205-230 */
+/* Cell loop of LaplaceProblem::assemble_rhs (heat_transfer.h:599-615): rhs += int (solution_old + delta_t f(x_q)) phi on
+ * this operator's MatrixFree (the reference uses the unconstrained inhomogeneous_operator's).  source_q: f at the
+ * quadrature points [n_cells][nq^3] (evaluate_function on phi.quadrature_point(q)) or NULL for the constant source_const.
+ * The caller adds the lifting -A_inhom * solution_bc (:586-592, a vmult) before, the interface-flux faces (:617-652) and
+ * b200mf_vec_compress_add (:654) after. */
+int b200mf_laplace_assemble_rhs(b200mf_laplace *op, void *rhs_dvec, const void *solution_old_dvec, const double *source_q,
+                                double source_const);
 int b200mf_laplace_diagonal(b200mf_laplace *op, const void **diag_dvec, const void **inv_diag_dvec);
 int b200mf_laplace_diagonal_host(b200mf_laplace *op, double *diag_host, double *inv_diag_host);
 

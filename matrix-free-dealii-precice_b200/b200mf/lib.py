@@ -81,6 +81,7 @@ SIGNATURES = {
     "b200mf_nh_vmult_dot_host": (_i32, [_vp, _vp, _vp, C.POINTER(C.c_double)]),
     "b200mf_laplace_vmult_dot_host": (_i32, [_vp, _vp, _vp, C.POINTER(C.c_double)]),
     "b200mf_laplace_vmult_dot": (_i32, [_vp, _vp, _vp, _vp]),
+    "b200mf_laplace_assemble_rhs": (_i32, [_vp, _vp, _vp, _vp, _dbl]),
     "b200mf_vec_create": (_i32, [_vp, _PP]),
     "b200mf_vec_destroy": (_i32, [_vp, _vp]),
     "b200mf_vec_upload": (_i32, [_vp, _vp, _vp]),

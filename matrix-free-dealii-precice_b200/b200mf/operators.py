@@ -379,6 +379,11 @@ class LaplaceOperator:
         _l.check(_l.load().b200mf_laplace_vmult_dot_host(self.h, _dv(dst), _dv(src), C.byref(out)))
         return out.value
 
+    def assemble_rhs(self, rhs, solution_old, source_q=None, source_const=0.0):
+        """Cell loop of LaplaceProblem::assemble_rhs (heat_transfer.h:599-615): rhs += int (u_old + dt f) phi."""
+        sq = None if source_q is None else np.ascontiguousarray(source_q, dtype=np.float64)
+        _l.check(_l.load().b200mf_laplace_assemble_rhs(self.h, _dv(rhs), _dv(solution_old), _ptr(sq), float(source_const)))
+
     def vmult_add(self, dst, src):
         _l.check(_l.load().b200mf_laplace_vmult_add(self.h, _dv(dst), _dv(src)))
 

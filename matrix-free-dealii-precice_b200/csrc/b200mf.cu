@@ -358,10 +358,10 @@ extern "C" int b200mf_ctx_create(b200mf_ctx **out, const b200mf_ctx_desc *d) {
   c->n_cells = d->n_cells;
   c->n_dofs = d->n_dofs;
   c->n_owned = d->n_owned;
-  // multi-rank contexts hide the two exchanges of vmult behind the interior cells by default (B200, Q3 bricks: 2x2x1 ranks
-  // 2.05 -> 1.54 ms per vmult, 2x1x1 ranks within noise of the serial order); B200MF_OVERLAP=0 / b200mf_ctx_set_overlap(ctx, 0)
-  // select the reference's serial order update_ghost_values -> cells -> compress(add)
-  c->overlap = getenv("B200MF_OVERLAP") ? atoi(getenv("B200MF_OVERLAP")) : 1;
+  // default: the reference's serial order update_ghost_values -> cells -> compress(add).  Hiding the exchanges behind the
+  // interior cells (b200mf_ctx_set_overlap(ctx, 1) / B200MF_OVERLAP=1) is implemented and parity-tested but measures
+  // ~60 us slower per vmult at 2 and 8 ranks on B200 today (three persistent launches instead of one)
+  c->overlap = getenv("B200MF_OVERLAP") ? atoi(getenv("B200MF_OVERLAP")) : 0;
   const int N = c->N, N2 = N * N, N3 = N2 * N, NC = c->NC;
   c->cpg = group_cells(N, NC);
   c->L = c->cpg * N2;
@@ -1405,6 +1405,46 @@ extern "C" int b200mf_laplace_vmult_host(b200mf_laplace *op, double *dst, const 
   B2_TRY(b200mf_vec_upload_f64(c, op->tmp_src, src));
   B2_TRY(laplace_apply(op, op->tmp_dst, op->tmp_src, true));
   return b200mf_vec_download_f64(c, dst, op->tmp_dst);
+}
+
+// ---- cell loop of LaplaceProblem::assemble_rhs (heat_transfer.h:599-615) ---------------------
+extern "C" int b200mf_laplace_assemble_rhs(b200mf_laplace *op, void *rhs, const void *solution_old, const double *source_q,
+                                           double source_const) {
+  if (!op || !rhs || !solution_old) return set_error(B200MF_ERR_ARG, "null argument");
+  b200mf_ctx *c = op->ctx;
+  const int N = c->N, N3 = N * N * N;
+  void *src_tab = nullptr;
+  if (source_q) {  // f at the quadrature points, natural [cell][q] -> group layout
+    const int64_t gs = table_stride_rt(c, 1);
+    const size_t nel = (size_t)c->n_groups * gs;
+    B2_CUDA(cudaMalloc(&src_tab, nel * esize(c)));
+    B2_CUDA(cudaMemsetAsync(src_tab, 0, nel * esize(c), c->stream));
+    double *dn = nullptr;
+    B2_CUDA(cudaMalloc(&dn, std::max<size_t>(8, (size_t)c->n_cells * N3 * sizeof(double))));
+    B2_CUDA(cudaMemcpyAsync(dn, source_q, (size_t)c->n_cells * N3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    const int64_t padded = c->n_groups * c->cpg;
+    if (c->dtype == B200MF_F64)
+      table_to_group_layout_kernel<double><<<nblocks(padded * N3, 256), 256, 0, c->stream>>>(N, c->cpg, c->L, 1, gs, c->n_cells, padded, dn, (double *)src_tab, 0, c->cell_order);
+    else
+      table_to_group_layout_kernel<float><<<nblocks(padded * N3, 256), 256, 0, c->stream>>>(N, c->cpg, c->L, 1, gs, c->n_cells, padded, dn, (float *)src_tab, 0, c->cell_order);
+    B2_LAUNCHED();
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(dn);
+  }
+  B2_TRY(update_ghost_values(c, const_cast<void *>(solution_old)));  // :599
+  int rc;
+  if (c->dtype == B200MF_F64) {
+    LaplaceRhsArgs<double> oa{(const double *)c->mref, (const double *)src_tab, (const double *)c->mcell, op->delta_t, source_const};
+    rc = run_laplace_rhs<double>(c, (const double *)solution_old, (double *)rhs, oa);
+  } else {
+    LaplaceRhsArgs<float> oa{(const float *)c->mref, (const float *)src_tab, (const float *)c->mcell, (float)op->delta_t, (float)source_const};
+    rc = run_laplace_rhs<float>(c, (const float *)solution_old, (float *)rhs, oa);
+  }
+  if (src_tab) {
+    cudaStreamSynchronize(c->stream);
+    cudaFree(src_tab);
+  }
+  return rc;
 }
 
 extern "C" int b200mf_laplace_compute_diagonal(b200mf_laplace *op) {

@@ -52,6 +52,16 @@ int run_laplace<TT>(const b200mf_ctx *ctx, bool diag, const TT *src, TT *dst, co
   });
   return rc;
 }
+template <>
+int run_laplace_rhs<TT>(const b200mf_ctx *ctx, const TT *solution_old, TT *rhs, const LaplaceRhsArgs<TT> &oa) {
+  int rc = 0;
+  const bool affine = ctx->mcell != nullptr;
+  B2_DISPATCH_N(ctx->N, TT, {
+    rc = affine ? launch_cell_loop<T, N, LaplaceRhsOp<T, N, true>>(ctx, solution_old, rhs, oa)
+                : launch_cell_loop<T, N, LaplaceRhsOp<T, N, false>>(ctx, solution_old, rhs, oa);
+  });
+  return rc;
+}
 #elif INST_KIND == 5
 template <>
 int run_nh_residual<TT>(const b200mf_ctx *ctx, const TT *displacement, TT *rhs, const NHResidualArgs<TT> &oa) {

@@ -22,4 +22,7 @@ template <typename T>
 int run_laplace(const b200mf_ctx *ctx, bool diag, const T *src, T *dst, const LaplaceArgs<T> &oa, int64_t g0, int64_t g1,
                 cudaStream_t stream, double *dot = nullptr);
 
+template <typename T>
+int run_laplace_rhs(const b200mf_ctx *ctx, const T *solution_old, T *rhs, const LaplaceRhsArgs<T> &oa);
+
 }  // namespace b200mf

@@ -613,4 +613,48 @@ struct NHResidualOp {
   }
 };
 
+// ---------------------------------------------------------------------------
+// cell loop of LaplaceProblem::assemble_rhs (heat_transfer.h:599-615):
+//   rhs += int (u_old + dt f(x_q)) phi   (gather_evaluate(values), submit_value, integrate_scatter(values))
+// AFFINE: per-cell metric (JxW = det J w_i w_j w_k), else the staged reference metric.
+template <typename T>
+struct LaplaceRhsArgs {
+  const T *stage;   // reference metric [group][MF_COUNT][N][L] (general cells)
+  const T *stage2;  // f at the quadrature points [group][1][N][L] or nullptr (then source_const)
+  const T *mcell;   // affine cells
+  T delta_t, source_const;
+};
+template <typename T, int N, bool AFFINE>
+struct LaplaceRhsOp {
+  static constexpr int NC = 1, NF_IN = AFFINE ? 0 : MF_COUNT, NF_IN2 = 1, NF_SCRATCH = 0;
+  static constexpr bool PLAIN = false, INTEGRATE = true, PRE = false, STORE_DOFS = false;
+  using Ly = Layout<N, NC, sizeof(T) / 4>;
+  using Args = LaplaceRhsArgs<T>;
+  struct CellState {
+    T mw;  // affine: det J * w_i w_j
+  };
+  static __device__ __forceinline__ void cell_begin(const Args &oa, int64_t cell, bool valid, int lane, CellState &st) {
+    st.mw = T(0);
+    if (AFFINE && valid) {
+      const int ji = lane % Ly::N2;
+      st.mw = __ldg(oa.mcell + (size_t)cell * MC_COUNT + MC_DET) * Shape<T, N>::W(ji % N) * Shape<T, N>::W(ji / N);
+    }
+  }
+  static __device__ __forceinline__ void store_dofs(const Args &, int64_t, int, bool, const T (&)[NC][N]) {}
+  static __device__ __forceinline__ void load_pre(const Args &, int64_t, int, bool, int, const uint32_t (&)[N], T (&)[N]) {}
+  static __device__ __forceinline__ void quad_pre(const Args &, const CellState &, bool, const T *, T *, int64_t, int, int,
+                                                  const T (&)[NC], const T (&)[NC][3]) {}
+  static __device__ __forceinline__ void quad(const Args &oa, const CellState &st, bool active, const T *qs, const T *qs2, const T *,
+                                              int64_t, int iq, int lane, const T (&v)[NC], const T (&)[NC][3], T (&ov)[NC],
+                                              T (&oG)[NC][3]) {
+    oG[0][0] = oG[0][1] = oG[0][2] = T(0);
+    ov[0] = T(0);
+    if (!active) return;
+    constexpr int FS = N * Ly::L;
+    const T w = AFFINE ? st.mw * Shape<T, N>::W(iq) : qs[MF_W * FS + iq * Ly::L + lane];
+    const T f = oa.stage2 != nullptr ? qs2[iq * Ly::L + lane] : oa.source_const;
+    ov[0] = w * (v[0] + oa.delta_t * f);  // :607-611
+  }
+};
+
 }  // namespace b200mf

@@ -399,11 +399,18 @@ static int cg_fixed_iterations_t(LinOp &A, double omega, const void *inv, T *x, 
   }
   B2_CUDA(cudaMemsetAsync(sc.d, 0, 8 * sizeof(double), st));
   double *S = sc.d;
-  for (int it = 1; it <= max_it; ++it) {
+  // the residual history is inspected every CHUNK iterations (one host read), so a solve that reaches the tolerance
+  // early (level 0 asks for up to m() iterations, heat_transfer.h:780-782) stops within CHUNK iterations of it
+  constexpr int CHUNK = 32;
+  std::vector<double> h(3 * (size_t)stride, 0.0);
+  bool rr_reduced = false;  // r.r of the previous iteration already summed over the ranks
+  int done_it = 0, last_it = 0;
+  for (int it = 1; it <= max_it && !done_it; ++it) {
     diag_precond_dot_kernel<T><<<g, 256, 0, st>>>(n, own, (T)omega, (const T *)inv, r, v, S + 0);
     B2_LAUNCHED();
     B2_TRY(allreduce_sum_f64(c, S + 0, 1));
-    if (it > 1) B2_TRY(allreduce_sum_f64(c, S + 3, 1));
+    if (it > 1 && !rr_reduced) B2_TRY(allreduce_sum_f64(c, S + 3, 1));
+    rr_reduced = false;
     cg_scalars_beta_kernel<<<1, 1, 0, st>>>(S, H, it, stride);
     B2_LAUNCHED();
     axpby_dev_kernel<T><<<g, 256, 0, st>>>(n, v, S + 5, p);  // p = z + beta p
@@ -419,23 +426,31 @@ static int cg_fixed_iterations_t(LinOp &A, double omega, const void *inv, T *x, 
     B2_LAUNCHED();
     cg_update_dev_kernel<T><<<g, 256, 0, st>>>(n, own, S + 4, p, v, x, r, S + 3);
     B2_LAUNCHED();
-  }
-  B2_TRY(allreduce_sum_f64(c, S + 3, 1));
-  cg_scalars_final_kernel<<<1, 1, 0, st>>>(S, H, max_it, stride);
-  B2_LAUNCHED();
-  std::vector<double> h(3 * (size_t)stride);
-  B2_CUDA(cudaMemcpyAsync(h.data(), H, h.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
-  B2_CUDA(cudaStreamSynchronize(st));
-  cudaFree(H);
-  // replay the stopping rule of the synchronising loop on the recorded history
-  int n_it = max_it;
-  for (int it = 1; it <= max_it; ++it) {
-    const double rn = std::sqrt(std::fabs(h[2 * stride + it]));
-    if (rn <= tol || !(rn == rn)) {
-      n_it = it;
-      break;
+    last_it = it;
+    if (it % CHUNK == 0 || it == max_it) {
+      B2_TRY(allreduce_sum_f64(c, S + 3, 1));
+      rr_reduced = true;
+      cg_scalars_final_kernel<<<1, 1, 0, st>>>(S, H, it, stride);
+      B2_LAUNCHED();
+      const int first = it - ((it - 1) % CHUNK);  // first iteration of this chunk
+      B2_CUDA(cudaMemcpyAsync(h.data() + 2 * stride + first, H + 2 * stride + first, (size_t)(it - first + 1) * sizeof(double),
+                              cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaStreamSynchronize(st));
+      for (int k = first; k <= it; ++k) {
+        const double rn = std::sqrt(std::fabs(h[2 * stride + k]));
+        if (rn <= tol || !(rn == rn)) {
+          done_it = k;
+          break;
+        }
+      }
     }
   }
+  B2_CUDA(cudaMemcpyAsync(h.data(), H, 2 * (size_t)stride * sizeof(double), cudaMemcpyDeviceToHost, st));  // alpha, beta
+  B2_CUDA(cudaStreamSynchronize(st));
+  cudaFree(H);
+  const int n_run = done_it ? done_it : last_it;
+  // the stopping rule of the synchronising loop, replayed on the recorded history
+  const int n_it = n_run;
   for (int it = 1; it <= n_it; ++it) {
     const double alpha = h[it], beta = h[stride + it];
     if (it > 1) {

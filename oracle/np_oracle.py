@@ -484,3 +484,18 @@ class LaplaceOperator:
         self.diagonal = diag
         self.inverse_diagonal = 1.0 / diag
         return diag
+
+
+def heat_rhs_cells(cd: CellData, delta_t, solution_old, source_q=None, source_const=0.0):
+    """Cell loop of LaplaceProblem::assemble_rhs (include/heat_transfer/heat_transfer.h:599-615):
+    rhs += int (u_old + dt * f(x_q)) phi, on the MatrixFree of the (unconstrained) inhomogeneous operator;
+    source_q [n_cells, n_q] = f at the quadrature points (evaluate_function on phi.quadrature_point(q))."""
+    loc = cd.read(solution_old)
+    val, g = cd.evaluate(loc, cd.invjac)
+    f = np.full((cd.n_cells, cd.n_q), float(source_const)) if source_q is None else np.asarray(source_q)
+    sub_v = val + delta_t * f[..., None]  # val: [cell, q, component]
+    loc_out = cd.integrate(sub_v, np.zeros_like(g), cd.invjac, cd.JxW)
+    rhs = np.zeros(cd.n_dofs)
+    cd.scatter_add(rhs, loc_out)
+    return rhs
+

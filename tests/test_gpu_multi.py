@@ -62,7 +62,7 @@ def _worker(rank, world, port, grid, nc, p, q):
         errs = []
         # 1: exchanges hidden behind the interior cells (boundary cells first, second stream); 0: the reference's
         # serial order update_ghost_values -> cells -> compress(add)
-        for overlap in (1, 0, 1):  # 1 is the library default
+        for overlap in (1, 0, 1):  # 0 is the library default
             mf.set_overlap(overlap)
             s.upload(v)  # stale ghosts again
             op.vmult(d, s)

@@ -374,3 +374,26 @@ def test_vmult_dot_fused(p, dtype):
         v = lop.vmult_dot(ys, xs)
         r = float(np.dot(xs.download(), ys.download()))
         assert abs(v - r) <= (1e-12 if dtype == "f64" else 2e-5) * abs(r)
+
+
+# cell loop of LaplaceProblem::assemble_rhs (heat_transfer.h:599-615)
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("mapped", [True, False], ids=["general", "affine"])
+def test_heat_rhs_cells(p, mapped):
+    from b200mf import DeviceVector
+    from common import np_cells
+    from oracle import np_oracle as NO
+
+    m = make_mesh(p, NCELLS[p], mapped=mapped, ncomp=1, clamp=None)  # the inhomogeneous operator carries no constraints
+    cd = np_cells(m, 1)
+    rng = np.random.default_rng(7 + p)
+    u_old = rng.uniform(-1, 1, m.n_nodes)
+    f_q = rng.uniform(-2, 2, (m.n_cells, (p + 1) ** 3))
+    dt = 0.1
+    mf = MatrixFree.from_mesh(m, 1)
+    op = LaplaceOperator(mf, dt)
+    for src_q, const in ((f_q, 0.0), (None, -1.5)):
+        ref = NO.heat_rhs_cells(cd, dt, u_old, src_q, const)
+        rhs = DeviceVector(mf)
+        op.assemble_rhs(rhs, DeviceVector(mf, u_old), src_q, const)
+        assert rel(rhs.download(), ref) < TOL64
