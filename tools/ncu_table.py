@@ -25,7 +25,10 @@ WANT = [
 cols = []
 for arg in sys.argv[1:]:
     label, path = arg.split("=", 1)
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if path.endswith(".csv"):  # already exported with `ncu -i x.ncu-rep --page raw --csv`
+        out = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units, vals = rows[0], rows[1], rows[2]
     d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
