@@ -269,6 +269,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    if world > 1:  # connection set-up: NCCL opens its peer channels lazily during the first exchanges
+        for _ in range(10):
+            op.vmult(dst, src)
+        barrier()
     for _ in range(max(args.warmup, 3)):
         op.vmult(dst, src)
     barrier()
@@ -276,6 +280,9 @@ def main():
     mf.time_kernels(True)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     with ClockSampler(local_rank) as clocks:
+        # an untimed ~2 ms spin kernel in front of the first event lets the host run ahead, so that the timed region
+        # measures K steps of device work and not the host latency of enqueueing the first one after the barrier
+        torch.cuda._sleep(4_000_000)
         ev[0].record(stream)
         for i in range(args.steps):
             op.vmult(dst, src)
@@ -286,6 +293,7 @@ def main():
     mf.time_kernels(False)
     kernel_ms = kernel_ms_total / args.steps  # all cell-loop launches of one step (1 on one rank; interior/boundary/interior when partitioned)
     total_ms = ev[0].elapsed_time(ev[-1])
+    step_ms = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps))  # this rank's per-step times (diagnostic)
     if dist is not None:
         t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -401,6 +409,7 @@ def main():
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
             "data": "synthetic", "config": workload_config(p, nc, world, args.caching, args.formulation), "roofline": roofline, "cpu_baseline": cpu,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(),
+            "step_ms_rank0": {"min": step_ms[0], "median": step_ms[len(step_ms) // 2], "max": step_ms[-1]},
         }
         if exchange:
             line["ghost_exchange"] = exchange
