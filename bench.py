@@ -169,6 +169,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 for every worker; the CPU arm is one process that should use all host cores
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 or os.environ.get("TORCHELASTIC_RUN_ID"):
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     p = args.degree
     nc = args.cpu_cells
     times = []

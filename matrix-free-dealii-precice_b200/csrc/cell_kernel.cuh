@@ -75,7 +75,7 @@ struct Shape<float, N> {
 // Shared-memory layout.  Two plane buffers per group with nested strides (plane stride PL, element j*N + i):
 //   bufZ plane (cw, c, kq)    at cw*ZCELL + c*ZCOMP + kq*PL,             ZCOMP = N*PL + CCZ, ZCELL = NC*ZCOMP + CZ
 //   bufQ plane (cw, c, f, kq) at cw*QCELL + c*QCOMP + f*QFIELD + kq*PL,  QFIELD = N*PL + FQ, QCOMP = 3*QFIELD + CCQ, QCELL = NC*QCOMP + CQ
-// Pads from tools/smem_layout_search2.py (64-bit accesses are served per half-warp over 16 8-byte banks).
+// Pads from tools/smem_layout_search.py (64-bit accesses are served per half-warp over 16 8-byte banks).
 template <int WORDS, int NC, int N>
 struct SmemPad3;
 #define B2_PAD3(W, NC_, N_, PL_, CZ_, CCZ_, CQ_, CCQ_, FQ_) \
