@@ -151,3 +151,23 @@ def test_laplace_against_assembled_matrix():
     cop.vmult(d2, src)
     assert rel(d2, d) < 1e-13
     assert rel(cop.compute_diagonal(), np.diag(A)) < 1e-13
+
+
+def test_heat_rhs_cells_is_mass_action_plus_source():
+    """oracle pin for SURVEY §8(f) row 4 (heat_transfer.h:599-615): int (u_old + dt f) phi == M u_old + dt f M 1 for constant f,
+    with M taken from the (independently pinned) LaplaceOperator at dt = 0."""
+    from common import make_mesh, np_cells
+
+    m = make_mesh(2, (3, 2, 2), ncomp=1, clamp=None)
+    cd = np_cells(m, 1)
+    u = np.random.default_rng(0).uniform(-1, 1, m.n_nodes)
+    r = NO.heat_rhs_cells(cd, 0.1, u, None, 2.0)
+    mass = NO.LaplaceOperator(cd, 0.0)
+    mu, m1 = np.zeros_like(u), np.zeros_like(u)
+    mass.vmult(mu, u)
+    mass.vmult(m1, np.ones_like(u))
+    assert np.linalg.norm(r - (mu + 0.1 * 2.0 * m1)) <= 1e-13 * np.linalg.norm(r)
+    # a q-point table equal to the constant gives the same vector
+    r2 = NO.heat_rhs_cells(cd, 0.1, u, np.full((cd.n_cells, cd.n_q), 2.0), 0.0)
+    assert np.array_equal(r, r2)
+
