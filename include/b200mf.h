@@ -219,6 +219,13 @@ int b200mf_laplace_set_delta_t(b200mf_laplace *op, double delta_t); /* set_delta
 int b200mf_laplace_vmult(b200mf_laplace *op, void *dst_dvec, const void *src_dvec);     /* Base::vmult -> apply_add :194-201 */
 int b200mf_laplace_vmult_add(b200mf_laplace *op, void *dst_dvec, const void *src_dvec);
 int b200mf_laplace_Tvmult(b200mf_laplace *op, void *dst_dvec, const void *src_dvec);
+int b200mf_laplace_Tvmult_add(b200mf_laplace *op, void *dst_dvec, const void *src_dvec);
+/* MatrixFreeOperators::Base::vmult_interface_down/_up (used by mg::Matrix on adaptively refined levels): dst = 0 + the
+ * refinement-edge rows; the reference refines globally only (heat_transfer.h:421-425), so both reduce to dst = 0 */
+int b200mf_laplace_vmult_interface_down(b200mf_laplace *op, void *dst_dvec, const void *src_dvec);
+int b200mf_laplace_vmult_interface_up(b200mf_laplace *op, void *dst_dvec, const void *src_dvec);
+int64_t b200mf_laplace_m(const b200mf_laplace *op);                        /* Base::m() == n(), heat_transfer.h:81 (inherited) */
+int b200mf_laplace_el(b200mf_laplace *op, int64_t row, double *value);     /* Base::el(row, row): diagonal entry, needs compute_diagonal */
 int b200mf_laplace_vmult_dot(b200mf_laplace *op, void *dst_dvec, const void *src_dvec, double *dot_device);
 int b200mf_laplace_vmult_dot_host(b200mf_laplace *op, void *dst_dvec, const void *src_dvec, double *result_host);
 int b200mf_laplace_vmult_host(b200mf_laplace *op, double *dst_host, const double *src_host);

@@ -120,6 +120,11 @@ SIGNATURES = {
     "b200mf_laplace_vmult": (_i32, [_vp, _vp, _vp]),
     "b200mf_laplace_vmult_add": (_i32, [_vp, _vp, _vp]),
     "b200mf_laplace_Tvmult": (_i32, [_vp, _vp, _vp]),
+    "b200mf_laplace_Tvmult_add": (_i32, [_vp, _vp, _vp]),
+    "b200mf_laplace_vmult_interface_down": (_i32, [_vp, _vp, _vp]),
+    "b200mf_laplace_vmult_interface_up": (_i32, [_vp, _vp, _vp]),
+    "b200mf_laplace_m": (_i64, [_vp]),
+    "b200mf_laplace_el": (_i32, [_vp, _i64, C.POINTER(_dbl)]),
     "b200mf_laplace_vmult_host": (_i32, [_vp, _vp, _vp]),
     "b200mf_laplace_compute_diagonal": (_i32, [_vp]),
     "b200mf_laplace_diagonal": (_i32, [_vp, _PP, _PP]),

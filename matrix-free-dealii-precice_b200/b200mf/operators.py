@@ -387,6 +387,36 @@ class LaplaceOperator:
     def vmult_add(self, dst, src):
         _l.check(_l.load().b200mf_laplace_vmult_add(self.h, _dv(dst), _dv(src)))
 
+    def Tvmult_add(self, dst, src):
+        _l.check(_l.load().b200mf_laplace_Tvmult_add(self.h, _dv(dst), _dv(src)))
+
+    def vmult_interface_down(self, dst, src):
+        """MatrixFreeOperators::Base: dst = 0 + refinement-edge rows (none on globally refined meshes)."""
+        _l.check(_l.load().b200mf_laplace_vmult_interface_down(self.h, _dv(dst), _dv(src)))
+
+    def vmult_interface_up(self, dst, src):
+        _l.check(_l.load().b200mf_laplace_vmult_interface_up(self.h, _dv(dst), _dv(src)))
+
+    def m(self):
+        return int(_l.load().b200mf_laplace_m(self.h))
+
+    n = m
+
+    def el(self, row, col=None):
+        """Base::el(row, col): only the diagonal is available (deal.II asserts row == col)."""
+        if col is not None and col != row:
+            raise ValueError("el(): only diagonal entries are available (MatrixFreeOperators::Base::el)")
+        out = C.c_double(0)
+        _l.check(_l.load().b200mf_laplace_el(self.h, int(row), C.byref(out)))
+        return out.value
+
+    def initialize_dof_vector(self):
+        """Base::initialize_dof_vector: a zeroed device vector on this operator's MatrixFree."""
+        return DeviceVector(self.mf)
+
+    def get_matrix_free(self):
+        return self.mf
+
     def compute_diagonal(self):
         _l.check(_l.load().b200mf_laplace_compute_diagonal(self.h))
 

@@ -164,7 +164,7 @@ struct QuadPts {
 // Q1 metric of StaticMappingQ1 at the Gauss points, written straight into the group layout.
 // invjac[e][f] = d xi_f / d x_e (mf_nh_operator.h:872-887), JxW = det J * w.
 template <typename T>
-__global__ void metric_from_vertices_kernel(int N, int cpg, int L, int64_t gstride, int64_t n_cells, int64_t n_cells_padded,
+__global__ void metric_from_vertices_kernel(int N, int cpg, int L, TableGeom tg, int64_t n_cells, int64_t n_cells_padded,
                                             const double *__restrict__ vtx, QuadPts qp, T *__restrict__ mref) {
   const int N2 = N * N, N3 = N2 * N;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -206,15 +206,16 @@ __global__ void metric_from_vertices_kernel(int N, int cpg, int L, int64_t gstri
       for (int f = 0; f < 3; ++f) Ki[e * 3 + f] = Ji[f * 3 + e];
     jxw = det * qp.wq[iq] * qp.wq[jq] * qp.wq[kq];
   }
-  const size_t FS = (size_t)N * L;
-  T *o = mref + (size_t)group * gstride + (size_t)kq * L + lane;
+  const size_t FS = (size_t)tg.fstride;
+  T *o = mref + (size_t)group * tg.gstride + (size_t)kq * tg.kqstride + lane;
   for (int i = 0; i < 9; ++i) o[(MF_K + i) * FS] = (T)Ki[i];
   o[MF_W * FS] = (T)jxw;
 }
 
-// natural [cell][q][nf] (double) -> group layout T [group][nf][N][L]; padded cells get `pad`-pattern (identity K)
+// natural [cell][q][nf] (double) -> group layout T (plain [group][nf][N][L] or sliced [group][N][nf][L], see table_geom);
+// padded cells get `pad`-pattern (identity K)
 template <typename T>
-__global__ void table_to_group_layout_kernel(int N, int cpg, int L, int nf, int64_t gstride, int64_t n_cells, int64_t n_cells_padded,
+__global__ void table_to_group_layout_kernel(int N, int cpg, int L, int nf, TableGeom tg, int64_t n_cells, int64_t n_cells_padded,
                                              const double *__restrict__ in, T *__restrict__ out, int identity_pad,
                                              const int64_t *__restrict__ order = nullptr) {
   const int N2 = N * N, N3 = N2 * N;
@@ -225,8 +226,8 @@ __global__ void table_to_group_layout_kernel(int N, int cpg, int L, int nf, int6
   const int iq = q % N, jq = (q / N) % N, kq = q / N2;
   const int64_t group = cell / cpg;
   const int lane = (int)(cell % cpg) * N2 + jq * N + iq;  // column thread (cell, j, i) owns the q-points (i, j, kq)
-  const size_t FS = (size_t)N * L;
-  T *o = out + (size_t)group * gstride + (size_t)kq * L + lane;
+  const size_t FS = (size_t)tg.fstride;
+  T *o = out + (size_t)group * tg.gstride + (size_t)kq * tg.kqstride + lane;
   for (int f = 0; f < nf; ++f) {
     double v;
     if (cell < n_cells)
@@ -239,7 +240,7 @@ __global__ void table_to_group_layout_kernel(int N, int cpg, int L, int nf, int6
 
 // group layout -> natural [cell][q] of one field (test hook)
 template <typename T>
-__global__ void field_from_group_layout_kernel(int N, int cpg, int L, int64_t gstride, int field, int64_t n_cells,
+__global__ void field_from_group_layout_kernel(int N, int cpg, int L, TableGeom tg, int field, int64_t n_cells,
                                                const T *__restrict__ in, double *__restrict__ out, const int64_t *__restrict__ order = nullptr) {
   const int N2 = N * N, N3 = N2 * N;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -249,7 +250,7 @@ __global__ void field_from_group_layout_kernel(int N, int cpg, int L, int64_t gs
   const int iq = q % N, jq = (q / N) % N, kq = q / N2;
   const int64_t group = cell / cpg;
   const int lane = (int)(cell % cpg) * N2 + jq * N + iq;  // column thread (cell, j, i) owns the q-points (i, j, kq)
-  out[(size_t)(order ? order[cell] : cell) * N3 + q] = (double)in[(size_t)group * gstride + ((size_t)field * N + kq) * L + lane];
+  out[(size_t)(order ? order[cell] : cell) * N3 + q] = (double)in[(size_t)group * tg.gstride + (size_t)kq * tg.kqstride + (size_t)field * tg.fstride + lane];
 }
 
 template <typename TO, typename TI>
@@ -318,10 +319,12 @@ __global__ void jacobi_kernel(int64_t n, T *__restrict__ dst, const T *__restric
 static inline unsigned nblocks(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 static inline size_t esize(const b200mf_ctx *c) { return c->dtype == B200MF_F64 ? 8 : 4; }
-// elements between groups of a [group][NF][N][L] table (== Layout::table_stride)
-static inline int64_t table_stride_rt(const b200mf_ctx *c, int NF) {
-  return (int64_t)round_up((size_t)NF * c->N * c->L, 16 / esize(c));
+// geometry of a staged table (== Layout::table_stride / kq_stride / FS) or, plain = true, of a table that is only ever
+// read or written straight from/to global memory (== Layout::plain_stride / L / FSP)
+static inline TableGeom table_geom_rt(const b200mf_ctx *c, int NF, bool plain = false) {
+  return table_geom(!plain && table_sliced(c->N, c->NC), c->N, c->L, NF, (int)esize(c));
 }
+static inline int64_t table_stride_rt(const b200mf_ctx *c, int NF, bool plain = false) { return table_geom_rt(c, NF, plain).gstride; }
 
 }  // namespace b200mf
 
@@ -646,9 +649,9 @@ extern "C" int b200mf_ctx_create(b200mf_ctx **out, const b200mf_ctx_desc *d) {
         qp.wq[i] = c->shape.w[i];
       }
       if (c->dtype == B200MF_F64)
-        metric_from_vertices_kernel<double><<<nblocks(nthreads, 256), 256>>>(N, c->cpg, c->L, gs, c->n_cells, padded, dv, qp, (double *)c->mref);
+        metric_from_vertices_kernel<double><<<nblocks(nthreads, 256), 256>>>(N, c->cpg, c->L, table_geom_rt(c.get(), MF_COUNT), c->n_cells, padded, dv, qp, (double *)c->mref);
       else
-        metric_from_vertices_kernel<float><<<nblocks(nthreads, 256), 256>>>(N, c->cpg, c->L, gs, c->n_cells, padded, dv, qp, (float *)c->mref);
+        metric_from_vertices_kernel<float><<<nblocks(nthreads, 256), 256>>>(N, c->cpg, c->L, table_geom_rt(c.get(), MF_COUNT), c->n_cells, padded, dv, qp, (float *)c->mref);
       B2_LAUNCHED();
       B2_CUDA(cudaDeviceSynchronize());
       cudaFree(dv);
@@ -663,9 +666,9 @@ extern "C" int b200mf_ctx_create(b200mf_ctx **out, const b200mf_ctx_desc *d) {
       B2_CUDA(cudaMalloc(&dn, std::max<size_t>(8, nat.size() * sizeof(double))));
       B2_CUDA(cudaMemcpy(dn, nat.data(), nat.size() * sizeof(double), cudaMemcpyHostToDevice));
       if (c->dtype == B200MF_F64)
-        table_to_group_layout_kernel<double><<<nblocks(nthreads, 256), 256>>>(N, c->cpg, c->L, MF_COUNT, gs, c->n_cells, padded, dn, (double *)c->mref, 1, c->cell_order);
+        table_to_group_layout_kernel<double><<<nblocks(nthreads, 256), 256>>>(N, c->cpg, c->L, MF_COUNT, table_geom_rt(c.get(), MF_COUNT), c->n_cells, padded, dn, (double *)c->mref, 1, c->cell_order);
       else
-        table_to_group_layout_kernel<float><<<nblocks(nthreads, 256), 256>>>(N, c->cpg, c->L, MF_COUNT, gs, c->n_cells, padded, dn, (float *)c->mref, 1, c->cell_order);
+        table_to_group_layout_kernel<float><<<nblocks(nthreads, 256), 256>>>(N, c->cpg, c->L, MF_COUNT, table_geom_rt(c.get(), MF_COUNT), c->n_cells, padded, dn, (float *)c->mref, 1, c->cell_order);
       B2_LAUNCHED();
       B2_CUDA(cudaDeviceSynchronize());
       cudaFree(dn);
@@ -859,6 +862,15 @@ extern "C" int b200mf_nh_create(b200mf_nh **out, b200mf_ctx *ctx, const b200mf_m
   return 0;
 }
 
+// a device-side failure counter, summed over the ranks of the partitioner before the host reads it: every rank returns
+// the same status (a rank that bailed out alone would leave its peers hanging in the next exchange)
+static int read_failure_count(b200mf_ctx *c, unsigned long long *dev, unsigned long long *host) {
+  B2_TRY(allreduce_sum_u64(c, dev, 1));
+  B2_CUDA(cudaMemcpyAsync(host, dev, sizeof *host, cudaMemcpyDeviceToHost, c->stream));
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 static void nh_free_tables(b200mf_nh *op) {
   cudaFree(op->qd);
   cudaFree(op->qd2);
@@ -894,8 +906,8 @@ extern "C" int b200mf_nh_initialize(b200mf_nh *op, int caching) {
                 : caching == B200MF_CACHE_TENSOR4_NS   ? NHV_TENSOR4_NS
                                                        : NHV_SCALAR_REF;
   nh_free_tables(op);
-  auto alloc = [&](void **p, int nf) -> int {
-    const size_t bytes = (size_t)c->n_groups * table_stride_rt(c, nf) * esize(c);
+  auto alloc = [&](void **p, int nf, bool plain = false) -> int {
+    const size_t bytes = (size_t)c->n_groups * table_stride_rt(c, nf, plain) * esize(c);
     B2_CUDA(cudaMalloc(p, std::max<size_t>(bytes, 16)));
     B2_CUDA(cudaMemsetAsync(*p, 0, bytes, c->stream));
     op->table_bytes += bytes;
@@ -903,10 +915,10 @@ extern "C" int b200mf_nh_initialize(b200mf_nh *op, int caching) {
   };
   const int v = op->variant;
   if (nhv_deformed(v)) B2_TRY(alloc(&op->qd, nhv_staged_fields(v)));
-  if (nhv_big_fields(v)) B2_TRY(alloc(&op->big, nhv_big_fields(v)));
+  if (nhv_big_fields(v)) B2_TRY(alloc(&op->big, nhv_big_fields(v), true));
   if (v == NHV_SCALAR_REF) {
     B2_TRY(alloc(&op->qd2, 1));
-    B2_TRY(alloc(&op->pos, 3));
+    B2_TRY(alloc(&op->pos, 3, true));
   }
   op->initialized = true;
   op->cached = false;
@@ -967,10 +979,9 @@ extern "C" int b200mf_nh_cache(b200mf_nh *op, const void *disp, int64_t *n_bad_o
   int rc = c->dtype == B200MF_F64 ? nh_cache_t<double>(op, disp) : nh_cache_t<float>(op, disp);
   B2_TRY(rc);
   unsigned long long bad = 0;
-  B2_CUDA(cudaMemcpyAsync(&bad, op->n_bad, sizeof bad, cudaMemcpyDeviceToHost, c->stream));
-  B2_CUDA(cudaStreamSynchronize(c->stream));
+  B2_TRY(read_failure_count(c, op->n_bad, &bad));
   if (n_bad_out) *n_bad_out = (int64_t)bad;
-  op->cached = true;
+  op->cached = (bad == 0);  // tables built from det F <= 0 must not be applied (the reference asserts, :430-435)
   op->have_diag = false;
   if (bad) return set_error(B200MF_ERR_NUMERIC, "det_F is not positive at %llu quadrature points", bad);  // :430-435
   return 0;
@@ -1050,7 +1061,10 @@ static int nh_apply(b200mf_nh *op, void *dst, const void *src, bool zero_dst, do
   if (dst == src) return set_error(B200MF_ERR_ARG, "vmult: dst aliases src");
   if (!op->cached) return set_error(B200MF_ERR_STATE, "vmult before cache()");
   b200mf_ctx *c = op->ctx;
-  if (zero_dst) B2_CUDA(cudaMemsetAsync(dst, 0, c->n_int * esize(c), c->stream));  // vmult: dst = 0, :548
+  if (zero_dst)
+    B2_CUDA(cudaMemsetAsync(dst, 0, c->n_int * esize(c), c->stream));  // vmult: dst = 0, :548
+  else
+    B2_TRY(zero_ghosts(c, dst));  // vmult_add: stale ghost entries of dst must not be summed into their owners by compress(add)
   int rc = c->dtype == B200MF_F64 ? nh_apply_t<double>(op, dst, src, dot) : nh_apply_t<float>(op, dst, src, dot);
   B2_TRY(rc);
   B2_CUDA(cudaGetLastError());
@@ -1132,8 +1146,7 @@ extern "C" int b200mf_nh_assemble_residual(b200mf_nh *op, void *rhs, const void 
   B2_TRY(c->dtype == B200MF_F64 ? nh_residual_t<double>(op, rhs, total_displacement, acceleration, body_force)
                                 : nh_residual_t<float>(op, rhs, total_displacement, acceleration, body_force));
   unsigned long long bad = 0;
-  B2_CUDA(cudaMemcpyAsync(&bad, op->n_bad, sizeof bad, cudaMemcpyDeviceToHost, c->stream));
-  B2_CUDA(cudaStreamSynchronize(c->stream));
+  B2_TRY(read_failure_count(c, op->n_bad, &bad));
   if (n_bad_out) *n_bad_out = (int64_t)bad;
   if (bad) return set_error(B200MF_ERR_NUMERIC, "assemble_residual: det F <= 0 at %llu quadrature points", bad);
   return 0;
@@ -1175,18 +1188,20 @@ extern "C" int b200mf_nh_qdata_host(b200mf_nh *op, int field, double *out) {
   const int ns = nhv_deformed(v) ? nhv_staged_fields(v) : v == NHV_SCALAR_REF ? 1 : 0;
   const void *tab = nhv_deformed(v) ? op->qd : op->qd2;
   int nf = ns;
+  bool plain = false;
   if (field >= ns) {
     tab = op->big;
     nf = nhv_big_fields(v);
     field -= ns;
+    plain = true;  // never staged
   }
   const int64_t n = c->n_cells * c->N * c->N * c->N;
   double *tmp = nullptr;
   B2_CUDA(cudaMalloc(&tmp, n * sizeof(double)));
   if (c->dtype == B200MF_F64)
-    field_from_group_layout_kernel<double><<<nblocks(n, 256), 256, 0, c->stream>>>(c->N, c->cpg, c->L, table_stride_rt(c, nf), field, c->n_cells, (const double *)tab, tmp, c->cell_order);
+    field_from_group_layout_kernel<double><<<nblocks(n, 256), 256, 0, c->stream>>>(c->N, c->cpg, c->L, table_geom_rt(c, nf, plain), field, c->n_cells, (const double *)tab, tmp, c->cell_order);
   else
-    field_from_group_layout_kernel<float><<<nblocks(n, 256), 256, 0, c->stream>>>(c->N, c->cpg, c->L, table_stride_rt(c, nf), field, c->n_cells, (const float *)tab, tmp, c->cell_order);
+    field_from_group_layout_kernel<float><<<nblocks(n, 256), 256, 0, c->stream>>>(c->N, c->cpg, c->L, table_geom_rt(c, nf, plain), field, c->n_cells, (const float *)tab, tmp, c->cell_order);
   B2_LAUNCHED();
   B2_CUDA(cudaMemcpyAsync(out, tmp, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   B2_CUDA(cudaStreamSynchronize(c->stream));
@@ -1218,8 +1233,7 @@ static int finish_diagonal(b200mf_ctx *c, void *diag, void *inv, unsigned long l
   B2_TRY(update_ghost_values(c, diag));  // mf_nh_operator.h:1056-1057
   B2_TRY(update_ghost_values(c, inv));
   unsigned long long bad = 0;
-  B2_CUDA(cudaMemcpyAsync(&bad, n_bad, sizeof bad, cudaMemcpyDeviceToHost, c->stream));
-  B2_CUDA(cudaStreamSynchronize(c->stream));
+  B2_TRY(read_failure_count(c, n_bad, &bad));
   if (bad)
     return set_error(B200MF_ERR_NUMERIC, "No diagonal entry in a positive definite operator should be zero or negative (%llu entries)", bad);
   return 0;
@@ -1272,22 +1286,26 @@ extern "C" int b200mf_nh_precondition_jacobi(b200mf_nh *op, void *dst, const voi
   return 0;
 }
 
-extern "C" int b200mf_nh_el(b200mf_nh *op, int64_t row, double *value) {
-  if (!op || !value) return set_error(B200MF_ERR_ARG, "null argument");
-  if (!op->have_diag) return set_error(B200MF_ERR_STATE, "el(): diagonal not available (mf_nh_operator.h:1069-1071)");
-  b200mf_ctx *c = op->ctx;
+// one entry of a device vector addressed by the caller's row number (el(): a diagonal entry)
+static int read_entry(b200mf_ctx *c, const void *vec, int64_t row, double *value) {
   if (row < 0 || row >= c->n_dofs) return set_error(B200MF_ERR_ARG, "row out of range");
   const int64_t in = c->h_ext2int ? (*c->h_ext2int)[row] : row;
   if (c->dtype == B200MF_F64) {
-    B2_CUDA(cudaMemcpyAsync(value, (const double *)op->diag + in, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA(cudaMemcpyAsync(value, (const double *)vec + in, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     B2_CUDA(cudaStreamSynchronize(c->stream));
   } else {
     float f;
-    B2_CUDA(cudaMemcpyAsync(&f, (const float *)op->diag + in, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA(cudaMemcpyAsync(&f, (const float *)vec + in, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     B2_CUDA(cudaStreamSynchronize(c->stream));
     *value = f;
   }
   return 0;
+}
+
+extern "C" int b200mf_nh_el(b200mf_nh *op, int64_t row, double *value) {
+  if (!op || !value) return set_error(B200MF_ERR_ARG, "null argument");
+  if (!op->have_diag) return set_error(B200MF_ERR_STATE, "el(): diagonal not available (mf_nh_operator.h:1069-1071)");
+  return read_entry(op->ctx, op->diag, row, value);
 }
 
 // ===========================================================================
@@ -1320,9 +1338,9 @@ extern "C" int b200mf_laplace_create(b200mf_laplace **out, b200mf_ctx *ctx, doub
     B2_CUDA(cudaMalloc(&op->coef, nel * esize(c)));
     const int64_t padded = c->n_groups * c->cpg;
     if (c->dtype == B200MF_F64)
-      table_to_group_layout_kernel<double><<<nblocks(padded * N3, 256), 256>>>(N, c->cpg, c->L, 1, gs, c->n_cells, padded, dn, (double *)op->coef, 0, c->cell_order);
+      table_to_group_layout_kernel<double><<<nblocks(padded * N3, 256), 256>>>(N, c->cpg, c->L, 1, table_geom_rt(c, 1), c->n_cells, padded, dn, (double *)op->coef, 0, c->cell_order);
     else
-      table_to_group_layout_kernel<float><<<nblocks(padded * N3, 256), 256>>>(N, c->cpg, c->L, 1, gs, c->n_cells, padded, dn, (float *)op->coef, 0, c->cell_order);
+      table_to_group_layout_kernel<float><<<nblocks(padded * N3, 256), 256>>>(N, c->cpg, c->L, 1, table_geom_rt(c, 1), c->n_cells, padded, dn, (float *)op->coef, 0, c->cell_order);
     B2_LAUNCHED();
     B2_CUDA(cudaDeviceSynchronize());
     cudaFree(dn);
@@ -1374,7 +1392,10 @@ static int laplace_apply(b200mf_laplace *op, void *dst, const void *src, bool ze
   if (!op || !dst || !src) return set_error(B200MF_ERR_ARG, "null argument");
   if (dst == src) return set_error(B200MF_ERR_ARG, "vmult: dst aliases src");
   b200mf_ctx *c = op->ctx;
-  if (zero_dst) B2_CUDA(cudaMemsetAsync(dst, 0, c->n_int * esize(c), c->stream));
+  if (zero_dst)
+    B2_CUDA(cudaMemsetAsync(dst, 0, c->n_int * esize(c), c->stream));
+  else
+    B2_TRY(zero_ghosts(c, dst));  // see nh_apply
   int rc = c->dtype == B200MF_F64 ? laplace_apply_t<double>(op, dst, src, dot) : laplace_apply_t<float>(op, dst, src, dot);
   B2_TRY(rc);
   B2_CUDA(cudaGetLastError());
@@ -1384,6 +1405,24 @@ static int laplace_apply(b200mf_laplace *op, void *dst, const void *src, bool ze
 extern "C" int b200mf_laplace_vmult(b200mf_laplace *op, void *dst, const void *src) { return laplace_apply(op, dst, src, true); }
 extern "C" int b200mf_laplace_vmult_add(b200mf_laplace *op, void *dst, const void *src) { return laplace_apply(op, dst, src, false); }
 extern "C" int b200mf_laplace_Tvmult(b200mf_laplace *op, void *dst, const void *src) { return laplace_apply(op, dst, src, true); }
+extern "C" int b200mf_laplace_Tvmult_add(b200mf_laplace *op, void *dst, const void *src) { return laplace_apply(op, dst, src, false); }
+// MatrixFreeOperators::Base::vmult_interface_down / _up: dst = 0, then the refinement-edge rows.  The reference only refines
+// globally (mf_elasticity.h:638, heat_transfer.h:421-425: no hanging nodes, no refinement edges on any level), so there are no
+// edge rows and both are "dst = 0".
+static int laplace_interface(b200mf_laplace *op, void *dst) {
+  if (!op || !dst) return set_error(B200MF_ERR_ARG, "null argument");
+  B2_CUDA(cudaMemsetAsync(dst, 0, op->ctx->n_int * esize(op->ctx), op->ctx->stream));
+  return 0;
+}
+extern "C" int b200mf_laplace_vmult_interface_down(b200mf_laplace *op, void *dst, const void *) { return laplace_interface(op, dst); }
+extern "C" int b200mf_laplace_vmult_interface_up(b200mf_laplace *op, void *dst, const void *) { return laplace_interface(op, dst); }
+extern "C" int64_t b200mf_laplace_m(const b200mf_laplace *op) { return op ? op->ctx->n_dofs : -1; }
+// Base::el(row, row): the diagonal entry (asserts row == col and an initialised diagonal like deal.II)
+extern "C" int b200mf_laplace_el(b200mf_laplace *op, int64_t row, double *value) {
+  if (!op || !value) return set_error(B200MF_ERR_ARG, "null argument");
+  if (!op->have_diag) return set_error(B200MF_ERR_STATE, "el(): call compute_diagonal() first");
+  return read_entry(op->ctx, op->diag, row, value);
+}
 
 extern "C" int b200mf_laplace_vmult_dot(b200mf_laplace *op, void *dst, const void *src, double *dot_device) {
   if (!dot_device) return set_error(B200MF_ERR_ARG, "null argument");
@@ -1424,9 +1463,9 @@ extern "C" int b200mf_laplace_assemble_rhs(b200mf_laplace *op, void *rhs, const 
     B2_CUDA(cudaMemcpyAsync(dn, source_q, (size_t)c->n_cells * N3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     const int64_t padded = c->n_groups * c->cpg;
     if (c->dtype == B200MF_F64)
-      table_to_group_layout_kernel<double><<<nblocks(padded * N3, 256), 256, 0, c->stream>>>(N, c->cpg, c->L, 1, gs, c->n_cells, padded, dn, (double *)src_tab, 0, c->cell_order);
+      table_to_group_layout_kernel<double><<<nblocks(padded * N3, 256), 256, 0, c->stream>>>(N, c->cpg, c->L, 1, table_geom_rt(c, 1), c->n_cells, padded, dn, (double *)src_tab, 0, c->cell_order);
     else
-      table_to_group_layout_kernel<float><<<nblocks(padded * N3, 256), 256, 0, c->stream>>>(N, c->cpg, c->L, 1, gs, c->n_cells, padded, dn, (float *)src_tab, 0, c->cell_order);
+      table_to_group_layout_kernel<float><<<nblocks(padded * N3, 256), 256, 0, c->stream>>>(N, c->cpg, c->L, 1, table_geom_rt(c, 1), c->n_cells, padded, dn, (float *)src_tab, 0, c->cell_order);
     B2_LAUNCHED();
     B2_CUDA(cudaStreamSynchronize(c->stream));
     cudaFree(dn);

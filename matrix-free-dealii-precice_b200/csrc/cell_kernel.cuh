@@ -40,6 +40,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace b200mf {
 
 constexpr int MAXN = 7;  // p = 1..6
@@ -89,16 +91,66 @@ __host__ __device__ constexpr size_t round_up(size_t x, size_t m) { return (x + 
 // barriers: its CPG*N^2 column threads and CPG*NC*N plane tasks are both packed densely from lane 0, so that
 // a phase only issues on the warps that hold work (an SM sub-partition spends two cycles on a DFMA whatever
 // the number of active lanes).  One warp per group wherever the plane tasks fill most of it (group barriers are
-// __syncwarp); the scalar operator (N plane tasks per cell only) and N = 5 pack several cells into a
-// multi-warp group instead.  Host (ctx->cpg, ctx->L) and device use these two functions.
+// __syncwarp); the scalar operator (N plane tasks per cell only) and the vector operator at N >= 5 pack several
+// cells into a multi-warp group instead (N = 5: 2 cells = 50 columns / 30 plane tasks in 64 threads, N = 6:
+// 3 cells = 108 / 54 in 128, N = 7: 2 cells = 98 / 42 in 128).  Host (ctx->cpg, ctx->L) and device use these functions.
+#ifndef B200MF_CPG5
+#define B200MF_CPG5 2
+#endif
+#ifndef B200MF_CPG6
+#define B200MF_CPG6 3
+#endif
+#ifndef B200MF_CPG7
+#define B200MF_CPG7 2
+#endif
 __host__ __device__ constexpr int group_cells(int N, int NC) {
 #ifdef B200MF_TUNE_CPG51  // tuning builds
   if (NC == 1 && N == 5) return B200MF_TUNE_CPG51;
 #endif
   if (NC == 1) return N == 2 ? 8 : N == 3 ? 7 : N == 4 ? 8 : N == 5 ? 6 : N == 6 ? 4 : 2;
-  return N * N <= 32 ? 32 / (N * N) : 1;
+  if (N == 5) return B200MF_CPG5;
+  if (N == 6) return B200MF_CPG6;
+  if (N == 7) return B200MF_CPG7;
+  return 32 / (N * N);
 }
 __host__ __device__ constexpr int group_threads(int N, int NC) { return (group_cells(N, NC) * N * N + 31) / 32 * 32; }
+
+// Staged q-point tables come in two layouts (lane = (cell in group, j, i), L lanes per group):
+//   plain  [group][field][kq][lane]   one TMA bulk copy per group stages the whole table of the group;
+//   sliced [group][kq][field][lane]   one bulk copy per z-plane of quadrature points into a small ring of
+//          slots: the column threads consume plane kq while the planes kq+1.. (of this or the next group) are in
+//          flight.  Shared memory per cell drops from NF*N^3 to RING*NF*N^2 elements - at N >= 5 the whole-group
+//          table was what held the kernel at 7 warps per SM (profiles/r01_v3_ncu_summary.md).
+// A slice is padded to a multiple of 16 bytes (cp.async.bulk granularity).
+#ifndef B200MF_SLICED_MINN
+#define B200MF_SLICED_MINN 5
+#endif
+#ifndef B200MF_RING
+#define B200MF_RING 2
+#endif
+#ifndef B200MF_VAL_REGS
+#define B200MF_VAL_REGS 0
+#endif
+__host__ __device__ constexpr bool table_sliced(int N, int NC) { return NC == 3 && N >= B200MF_SLICED_MINN; }
+// the z-swept nodal planes (column -> plane hand-off) live in field 0 of the q-point buffer: a plane task reads
+// its own plane completely before it writes it, so no second buffer is needed
+#ifndef B200MF_ALIAS_MINN
+#define B200MF_ALIAS_MINN 4
+#endif
+__host__ __device__ constexpr bool alias_z(int N, int NC) { return NC == 3 && N >= B200MF_ALIAS_MINN; }
+
+struct TableGeom {  // element (group, field, kq, lane) of a table lives at group*gstride + kq*kqstride + field*fstride + lane
+  int64_t gstride;
+  int kqstride, fstride;
+};
+__host__ __device__ constexpr TableGeom table_geom(bool sliced, int N, int L, int NF, int elem_bytes) {
+  const int al = 16 / elem_bytes;
+  if (sliced) {
+    const int sl = (int)round_up((size_t)NF * L, al);
+    return TableGeom{(int64_t)N * sl, sl, L};
+  }
+  return TableGeom{(int64_t)round_up((size_t)NF * N * L, al), L, N * L};
+}
 
 template <int N, int NC, int WORDS = 2>
 struct Layout {
@@ -108,17 +160,31 @@ struct Layout {
   static constexpr int TPG = group_threads(N, NC); // threads per group
   static constexpr bool WARP_MODE = (TPG == 32);
   static constexpr int NT = CPG * NC * N;          // plane tasks per group
+  static constexpr bool SLICED = table_sliced(N, NC);
+  static constexpr bool ALIAS_Z = alias_z(N, NC);
+  static constexpr int RING = B200MF_RING;
   using P = SmemPad3<WORDS, NC, N>;
   static constexpr int PL = P::PL;
   static constexpr int ZCOMP = N * PL + P::CCZ, ZCELL = NC * ZCOMP + P::CZ;
   static constexpr int QFIELD = N * PL + P::FQ, QCOMP = 3 * QFIELD + P::CCQ, QCELL = NC * QCOMP + P::CQ;
-  static constexpr int ZSIZE = CPG * ZCELL;
+  static constexpr int ZSIZE = ALIAS_Z ? 0 : CPG * ZCELL;
   static constexpr int QSIZE = CPG * QCELL;
   static constexpr int GROUP_ELEMS = ZSIZE + QSIZE;
-  __host__ __device__ static constexpr int zplane(int cw, int c, int kq) { return cw * ZCELL + c * ZCOMP + kq * PL; }
   __host__ __device__ static constexpr int qplane(int cw, int c, int f, int kq) { return cw * QCELL + c * QCOMP + f * QFIELD + kq * PL; }
-  // elements between consecutive groups of a [group][NF][N][L] table (16-byte multiple for cp.async.bulk)
-  __host__ __device__ static constexpr size_t table_stride(int NF) { return round_up((size_t)NF * N * L, 16 / (4 * WORDS)); }
+  // relative to bufZ (== bufQ when aliased)
+  __host__ __device__ static constexpr int zplane(int cw, int c, int kq) {
+    return ALIAS_Z ? qplane(cw, c, 0, kq) : cw * ZCELL + c * ZCOMP + kq * PL;
+  }
+  // staged tables (see table_geom): q-point (kq, lane), field f at  kq*kq_stride(NF) + f*FS + lane  behind the group's base
+  static constexpr int FS = SLICED ? L : N * L;
+  __host__ __device__ static constexpr size_t slice_stride(int NF) { return round_up((size_t)NF * L, 16 / (4 * WORDS)); }
+  __host__ __device__ static constexpr size_t kq_stride(int NF) { return SLICED ? slice_stride(NF) : (size_t)L; }
+  __host__ __device__ static constexpr size_t table_stride(int NF) {
+    return SLICED ? N * slice_stride(NF) : round_up((size_t)NF * N * L, 16 / (4 * WORDS));
+  }
+  // tables that are never staged (read or written straight from/to global memory) and the shared-memory scratch: always plain
+  static constexpr int FSP = N * L;
+  __host__ __device__ static constexpr size_t plain_stride(int NF) { return round_up((size_t)NF * N * L, 16 / (4 * WORDS)); }
 };
 
 template <bool WARP>
@@ -215,9 +281,10 @@ __device__ __forceinline__ void sweep_C(const T (&in)[N], T (&out)[N]) {
 //   struct Args { const T *stage, *stage2; ... }   stage2 may be null at run time
 //   struct CellState;                    per-thread per-cell state (material constants)
 //   static void cell_begin(args, cell, valid, lane, CellState&)
-//   static void quad(args, state, active, qs, qs2, scr, group, kq, lane, v[NC], G[NC][3], ov[NC], oG[NC][3])
+//   static void quad(args, state, active, q, q2, scr, group, kq, lane, v[NC], G[NC][3], ov[NC], oG[NC][3])
 //       the column thread `lane` = (cell, j, i) handles the q-points (i, j, kq), kq = 0..N-1;
-//       qs / qs2 / scr: shared-memory tables, field f of q-point (kq, lane) at qs[(f*N + kq)*L + lane];
+//       q / q2: this q-point's entry of the two staged tables in shared memory, field f at q[f * Layout::FS];
+//       scr: the group's scratch, plain layout: field f of q-point (kq, lane) at scr[(f*N + kq)*L + lane];
 //       G[c][d] = d u_c / d xi_d (reference gradient), oG likewise for the test-function side
 //
 // DIAG = true computes what MatrixFreeTools::compute_diagonal computes - entry i of the cell
@@ -234,10 +301,15 @@ struct KernelSmem {
   static constexpr int DIAG_ELEMS = Ly::CPG * 6 * Ly::N3;  // diagonal pass: 6 coefficient fields per cell (see below)
   static constexpr int BUF_ELEMS = (DIAG && DIAG_ELEMS > Ly::GROUP_ELEMS) ? DIAG_ELEMS : Ly::GROUP_ELEMS;
   static constexpr size_t BUF_BYTES = round_up((size_t)BUF_ELEMS * sizeof(T), 16);
-  static constexpr size_t ST1_BYTES = Op::NF_IN ? Ly::table_stride(Op::NF_IN) * sizeof(T) : 0;
-  static constexpr size_t ST2_BYTES = Op::NF_IN2 ? Ly::table_stride(Op::NF_IN2) * sizeof(T) : 0;
-  static constexpr size_t SCR_BYTES = Op::NF_SCRATCH ? Ly::table_stride(Op::NF_SCRATCH) * sizeof(T) : 0;  // pre-pass -> main pass
-  static constexpr size_t GROUP_BYTES = BUF_BYTES + ST1_BYTES + ST2_BYTES + SCR_BYTES + 16;                // + mbarrier
+  // plain: the whole table of the group; sliced: RING slots of one z-plane of both tables
+  static constexpr size_t SL1_ELEMS = Op::NF_IN ? Ly::slice_stride(Op::NF_IN) : 0;
+  static constexpr size_t SL2_ELEMS = Op::NF_IN2 ? Ly::slice_stride(Op::NF_IN2) : 0;
+  static constexpr size_t SLOT_ELEMS = SL1_ELEMS + SL2_ELEMS;
+  static constexpr size_t ST1_BYTES = Ly::SLICED ? Ly::RING * SLOT_ELEMS * sizeof(T) : (Op::NF_IN ? Ly::table_stride(Op::NF_IN) * sizeof(T) : 0);
+  static constexpr size_t ST2_BYTES = Ly::SLICED ? 0 : (Op::NF_IN2 ? Ly::table_stride(Op::NF_IN2) * sizeof(T) : 0);
+  static constexpr size_t SCR_BYTES = Op::NF_SCRATCH ? Ly::plain_stride(Op::NF_SCRATCH) * sizeof(T) : 0;  // pre-pass -> main pass
+  static constexpr size_t MBAR_BYTES = Ly::SLICED ? round_up(8 * Ly::RING, 16) : 16;
+  static constexpr size_t GROUP_BYTES = BUF_BYTES + ST1_BYTES + ST2_BYTES + SCR_BYTES + MBAR_BYTES;
 };
 
 template <typename T, int N, class Op, int GPB, bool DIAG = false, int MINB = 1, bool DOT = false>
@@ -249,6 +321,8 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
   using KS_ = KernelSmem<T, N, Op, DIAG>;
   constexpr int N2 = Ly::N2, L = Ly::L, PL = Ly::PL, NT = Ly::NT;
   constexpr bool WM = Ly::WARP_MODE;
+  constexpr bool SLICED = Ly::SLICED;
+  constexpr int RING = Ly::RING;
   static_assert(WM || GPB == 1, "block mode runs one group per block");
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -261,26 +335,89 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
 
   unsigned char *gbase = smem_raw + (size_t)gib * KS_::GROUP_BYTES;
   T *bufZ = reinterpret_cast<T *>(gbase);
-  T *bufQ = bufZ + Ly::ZSIZE;
-  T *qs = reinterpret_cast<T *>(gbase + KS_::BUF_BYTES);
+  T *bufQ = bufZ + Ly::ZSIZE;  // == bufZ when the z-swept planes live in field 0 of the q-point buffer
+  T *qs = reinterpret_cast<T *>(gbase + KS_::BUF_BYTES);  // plain: table 1 of the group; sliced: the ring
   T *qs2 = reinterpret_cast<T *>(gbase + KS_::BUF_BYTES + KS_::ST1_BYTES);
   T *scr = reinterpret_cast<T *>(gbase + KS_::BUF_BYTES + KS_::ST1_BYTES + KS_::ST2_BYTES);
   uint64_t *mbar = reinterpret_cast<uint64_t *>(gbase + KS_::BUF_BYTES + KS_::ST1_BYTES + KS_::ST2_BYTES + KS_::SCR_BYTES);
 
-  if (lane == 0) mbar_init(mbar, 1);
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < (SLICED ? RING : 1); ++r) mbar_init(mbar + r, 1);
+  }
   group_sync<WM>();
 
-  // stage the tables of `group` into this group's shared buffers (one elected lane drives the TMA unit)
-  // (Op::NF_IN == 0 and no second table: nothing is staged and the mbarrier is never armed or waited on)
+  const int64_t gstep = (int64_t)gridDim.x * GPB;
+  int64_t group = A.group_begin + (int64_t)blockIdx.x * GPB + gib;
+
+  // (Op::NF_IN == 0 and no second table: nothing is staged and the mbarriers are never armed or waited on)
   const bool two = Op::NF_IN2 != 0 && oa.stage2 != nullptr;
   const bool staged = Op::NF_IN != 0 || two;
+  // ---- plain layout: one elected lane stages the tables of `group` with one bulk copy per table ------------
   auto stage = [&](int64_t g) {
-    if (lane == 0 && staged) {
+    if (!SLICED && lane == 0 && staged) {
       mbar_expect_tx(mbar, (unsigned)((Op::NF_IN ? KS_::ST1_BYTES : 0) + (two ? KS_::ST2_BYTES : 0)));
       if (Op::NF_IN) bulk_g2s(qs, oa.stage + (size_t)g * Ly::table_stride(Op::NF_IN ? Op::NF_IN : 1), (unsigned)KS_::ST1_BYTES, mbar);
       if (two) bulk_g2s(qs2, oa.stage2 + (size_t)g * Ly::table_stride(Op::NF_IN2 ? Op::NF_IN2 : 1), (unsigned)KS_::ST2_BYTES, mbar);
     }
   };
+  // ---- sliced layout: a ring of z-plane slots.  The slices of a group are consumed in SWEEPS sweeps over
+  // kq = 0..N-1 (pre-pass, main pass; the diagonal pass sweeps once per component); the producer cursor runs RING
+  // slices ahead of the consumer across sweeps and groups.
+  constexpr int SWEEPS = (Op::PRE ? 1 : 0) + (DIAG ? NC : 1);
+  int islot = 0, ikq = 0, isw = 0;  // producer cursor (uniform over the group)
+  int64_t ig = group;
+  int cslot = 0;                    // consumer
+  unsigned cpar = 0;
+  auto ring_issue = [&]() {
+    if (SLICED && staged && ig < A.n_groups) {
+      if (lane == 0) {
+        uint64_t *mb = mbar + islot;
+        T *slot = qs + (size_t)islot * KS_::SLOT_ELEMS;
+        mbar_expect_tx(mb, (unsigned)(((Op::NF_IN ? KS_::SL1_ELEMS : 0) + (two ? KS_::SL2_ELEMS : 0)) * sizeof(T)));
+        if (Op::NF_IN)
+          bulk_g2s(slot, oa.stage + (size_t)ig * Ly::table_stride(Op::NF_IN ? Op::NF_IN : 1) + (size_t)ikq * KS_::SL1_ELEMS,
+                   (unsigned)(KS_::SL1_ELEMS * sizeof(T)), mb);
+        if (two)
+          bulk_g2s(slot + KS_::SL1_ELEMS, oa.stage2 + (size_t)ig * Ly::table_stride(Op::NF_IN2 ? Op::NF_IN2 : 1) + (size_t)ikq * KS_::SL2_ELEMS,
+                   (unsigned)(KS_::SL2_ELEMS * sizeof(T)), mb);
+      }
+      islot = (islot + 1 == RING) ? 0 : islot + 1;
+      if (++ikq == N) {
+        ikq = 0;
+        if (++isw == SWEEPS) {
+          isw = 0;
+          ig += gstep;
+        }
+      }
+    }
+  };
+  // this q-plane's entries of the staged tables (field 0, this lane); q_release after the last read of the plane
+  const T *q1p = nullptr, *q2p = nullptr;
+  auto q_acquire = [&](int kq) {
+    if constexpr (SLICED) {
+      if (staged) mbar_wait(mbar + cslot, cpar);
+      q1p = qs + (size_t)cslot * KS_::SLOT_ELEMS + lane;
+      q2p = q1p + KS_::SL1_ELEMS;
+    } else {
+      q1p = qs + kq * L + lane;
+      q2p = qs2 + kq * L + lane;
+    }
+  };
+  auto q_release = [&]() {
+    if constexpr (SLICED) {
+      if (staged) {
+        group_sync<WM>();  // every column thread is done with the slot
+        fence_proxy_async();
+        ring_issue();
+        if (++cslot == RING) {
+          cslot = 0;
+          cpar ^= 1u;
+        }
+      }
+    }
+  };
+
   auto load_nid = [&](int64_t g, uint32_t(&id)[N]) {
 #pragma unroll
     for (int k = 0; k < N; ++k) id[k] = active ? __ldg(A.nidx + ((size_t)g * N + k) * L + lane) : NODE_ALL_CONSTRAINED;
@@ -300,7 +437,8 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
   // column-thread offsets into the plane buffers
   const int zoff = Ly::zplane(cw, 0, 0) + ji;
   const int qoff = Ly::qplane(cw, 0, 0, 0) + ji;
-  auto zidx = [&](int c, int kq) { return zoff + c * Ly::ZCOMP + kq * PL; };
+  constexpr int ZC = Ly::ALIAS_Z ? Ly::QCOMP : Ly::ZCOMP;
+  auto zidx = [&](int c, int kq) { return zoff + c * ZC + kq * PL; };
   auto qidx = [&](int c, int f, int kq) { return qoff + c * Ly::QCOMP + f * Ly::QFIELD + kq * PL; };
 
   // diagonal pass: this thread's columns of S and D (row index q) for its j (y sweep) and i (x sweep)
@@ -315,15 +453,18 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
     }
   }
 
-  const int64_t gstep = (int64_t)gridDim.x * GPB;
-  int64_t group = A.group_begin + (int64_t)blockIdx.x * GPB + gib;
   unsigned parity = 0;
   uint32_t nid[N], nid_next[N];
   T u[NC][N];
 #pragma unroll
   for (int k = 0; k < N; ++k) nid[k] = nid_next[k] = NODE_ALL_CONSTRAINED;
   if (group < A.n_groups) {
-    stage(group);
+    if constexpr (SLICED) {
+#pragma unroll
+      for (int r = 0; r < RING; ++r) ring_issue();
+    } else {
+      stage(group);
+    }
     load_nid(group, nid);
     if (!DIAG) gather(nid, u);
   }
@@ -346,7 +487,7 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
           // ---- diagonal pass ---------------------------------------------------------------------
           if (pass == FIRST) {
             if (has_next) load_nid(gnext, nid_next);
-            if (staged) mbar_wait(mbar, parity);
+            if (!SLICED && staged) mbar_wait(mbar, parity);
           }
           T *db = bufZ + cw * (6 * Ly::N3);  // [field][k3][j][i] of this thread's cell
           const int tj = ji / N, ti = ji % N;
@@ -360,6 +501,7 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
 #pragma unroll 1
             for (int kq = 0; kq < N; ++kq) {
               T Q[4][4];  // Q[a][b]: output a (value, d/dxi_1..3 of the test side) for unit input b
+              q_acquire(kq);
 #pragma unroll
               for (int b = 0; b < 4; ++b) {
                 T v[NC], G[NC][3], ov[NC], oG[NC][3];
@@ -369,7 +511,7 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
 #pragma unroll
                   for (int d = 0; d < 3; ++d) G[cc][d] = (cc == c && b == d + 1) ? T(1) : T(0);
                 }
-                Op::quad(oa, st, active, qs, qs2, scr, group, kq, lane, v, G, ov, oG);
+                Op::quad(oa, st, active, q1p, q2p, scr, group, kq, lane, v, G, ov, oG);
 #pragma unroll
                 for (int a = 0; a < 4; ++a) {
                   T o = T(0);
@@ -378,6 +520,7 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
                   Q[a][b] = o;
                 }
               }
+              q_release();
 #pragma unroll
               for (int k = 0; k < N; ++k) {
                 const T sv = Sh::S(kq, k), dv = Sh::D(kq, k);
@@ -444,10 +587,12 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
             }
             group_sync<WM>();
           }
-          parity ^= 1u;
-          if (has_next) {
-            fence_proxy_async();
-            stage(gnext);
+          if constexpr (!SLICED) {
+            parity ^= 1u;
+            if (has_next) {
+              fence_proxy_async();
+              stage(gnext);
+            }
           }
           continue;
         }
@@ -516,56 +661,80 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
           }
         }
       }
-      if (pass == FIRST && staged) mbar_wait(mbar, parity);  // this group's tables have landed in shared memory
+      if (!SLICED && pass == FIRST && staged) mbar_wait(mbar, parity);  // this group's tables have landed in shared memory
       group_sync<WM>();
       // ---- F3 (column): d/dz in registers, quadrature loop, z part of the integration ---------
       T racc[NC][N];  // values + z-derivative terms of the test side, at the q-points of the column
       {
-        T val[NC][N], gz[NC][N];
+        // the values of the column (for d/dz): registers, or - rolled loop - re-read from shared memory in every plane
+        // (N^2 instead of N loads per component, 2 N NC fewer live registers)
+        constexpr bool VAL_REGS = !SLICED || B200MF_VAL_REGS;
+        T val[NC][N];
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
 #pragma unroll
           for (int kq = 0; kq < N; ++kq) {
-            val[c][kq] = bufQ[qidx(c, 0, kq)];
+            if (VAL_REGS) val[c][kq] = bufQ[qidx(c, 0, kq)];
             racc[c][kq] = T(0);
           }
-          sweep_C<T, N>(val[c], gz[c]);
         }
-#pragma unroll
-        for (int kq = 0; kq < N; ++kq) {
+        // one z-plane of quadrature points; STATIC: kq is a compile-time constant (unrolled loop), else the loop is
+        // rolled (sliced tables: one small body, no load hoisting across planes -> far fewer registers) and whatever is
+        // indexed by kq comes from shared / constant memory
+        auto plane = [&](const int kq, auto STATIC) {
           T G[NC][3], v[NC], ov[NC], oG[NC][3];
+          T crow[N];
+#pragma unroll
+          for (int m = 0; m < N; ++m) crow[m] = Sh::C(kq, m);
 #pragma unroll
           for (int c = 0; c < NC; ++c) {
-            v[c] = val[c][kq];
+            if constexpr (decltype(STATIC)::value)
+              v[c] = val[c][kq];
+            else
+              v[c] = bufQ[qidx(c, 0, kq)];
             G[c][0] = bufQ[qidx(c, 1, kq)];
             G[c][1] = bufQ[qidx(c, 2, kq)];
-            G[c][2] = gz[c][kq];
+            T acc = T(0);
+#pragma unroll
+            for (int m = 0; m < N; ++m) acc += crow[m] * (VAL_REGS ? val[c][m] : bufQ[qidx(c, 0, m)]);
+            G[c][2] = acc;
           }
+          q_acquire(kq);
           if (pre) {
-            Op::quad_pre(oa, st, active, qs, scr, group, kq, lane, v, G);
-            continue;
-          }
-          Op::quad(oa, st, active, qs, qs2, scr, group, kq, lane, v, G, ov, oG);
-          if constexpr (DOT) {
-            // src . (A src) = sum over cells and q-points of (value, gradient) . (submitted value, gradient): every operand
-            // is live here, so the fused dot product costs no registers beyond its accumulator
-            T e = T(0);
+            Op::quad_pre(oa, st, active, q1p, scr, group, kq, lane, v, G);
+          } else {
+            Op::quad(oa, st, active, q1p, q2p, scr, group, kq, lane, v, G, ov, oG);
+            if constexpr (DOT) {
+              // src . (A src) = sum over cells and q-points of (value, gradient) . (submitted value, gradient): every
+              // operand is live here, so the fused dot product costs no registers beyond its accumulator
+              T e = T(0);
 #pragma unroll
-            for (int c = 0; c < NC; ++c) e += v[c] * ov[c] + G[c][0] * oG[c][0] + G[c][1] * oG[c][1] + G[c][2] * oG[c][2];
-            dot_acc += (double)e;
-          }
-          if (Op::INTEGRATE) {
+              for (int c = 0; c < NC; ++c) e += v[c] * ov[c] + G[c][0] * oG[c][0] + G[c][1] * oG[c][1] + G[c][2] * oG[c][2];
+              dot_acc += (double)e;
+            }
+            if (Op::INTEGRATE) {
 #pragma unroll
-            for (int c = 0; c < NC; ++c) {
+              for (int c = 0; c < NC; ++c) {
 #pragma unroll
-              for (int m = 0; m < N; ++m) racc[c][m] += Sh::C(kq, m) * oG[c][2];
-              racc[c][kq] += ov[c];
-              if (active) {
-                bufQ[qidx(c, 1, kq)] = oG[c][0];
-                bufQ[qidx(c, 2, kq)] = oG[c][1];
+                for (int m = 0; m < N; ++m) {
+                  racc[c][m] += crow[m] * oG[c][2];
+                  if (m == kq) racc[c][m] += ov[c];
+                }
+                if (active) {
+                  bufQ[qidx(c, 1, kq)] = oG[c][0];
+                  bufQ[qidx(c, 2, kq)] = oG[c][1];
+                }
               }
             }
           }
+          q_release();
+        };
+        if constexpr (SLICED) {
+#pragma unroll 1
+          for (int kq = 0; kq < N; ++kq) plane(kq, std::false_type{});
+        } else {
+#pragma unroll
+          for (int kq = 0; kq < N; ++kq) plane(kq, std::true_type{});
         }
       }
       if (Op::INTEGRATE && !pre) {
@@ -576,11 +745,13 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
             if (active) bufQ[qidx(c, 0, kq)] = racc[c][kq];
       }
       group_sync<WM>();  // q-point results are in bufQ; everyone is done with the staged tables
-      if (pass == NPASS - 1) {
-        parity ^= 1u;
-        if (has_next) {
-          fence_proxy_async();
-          stage(gnext);
+      if constexpr (!SLICED) {
+        if (pass == NPASS - 1) {
+          parity ^= 1u;
+          if (has_next) {
+            fence_proxy_async();
+            stage(gnext);
+          }
         }
       }
       if (Op::INTEGRATE && !pre) {

@@ -264,6 +264,14 @@ int allreduce_sum_f64(b200mf_ctx *c, double *dptr, int n) {
   B2_NCCL(g_nccl.AllReduce(dptr, dptr, (size_t)n, ncclFloat64, ncclSum, p->comm->comm, c->stream));
   return 0;
 }
+// sum over ranks of a device counter (failure counts: every rank must take the same error path, or the peers of a
+// failing rank would walk into the next exchange alone)
+int allreduce_sum_u64(b200mf_ctx *c, unsigned long long *dptr, int n) {
+  b200mf_partitioner *p = c->part;
+  if (!p || p->comm->world == 1) return 0;
+  B2_NCCL(g_nccl.AllReduce(dptr, dptr, (size_t)n, ncclUint64, ncclSum, p->comm->comm, c->stream));
+  return 0;
+}
 }  // namespace b200mf
 
 extern "C" int b200mf_vec_update_ghost_values(b200mf_ctx *c, void *dvec) {

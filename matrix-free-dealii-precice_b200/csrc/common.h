@@ -54,6 +54,7 @@ int compress_add(b200mf_ctx *c, void *vec, cudaStream_t stream = nullptr);
 int zero_ghosts(b200mf_ctx *c, void *vec);
 bool has_neighbors(const b200mf_ctx *c);
 int allreduce_sum_f64(b200mf_ctx *c, double *dptr, int n);
+int allreduce_sum_u64(b200mf_ctx *c, unsigned long long *dptr, int n);
 
 }  // namespace b200mf
 
@@ -73,7 +74,7 @@ struct b200mf_ctx {
   int64_t n_boundary_groups;  // groups [0, n_boundary_groups) touch ghost nodes
   cudaStream_t comm_stream;   // exchanges that overlap the interior cells run here
   cudaEvent_t ev[4];
-  int overlap;                // 1: hide the exchanges behind interior cells (default when partitioned)
+  int overlap;                // 1: hide the exchanges behind interior cells (opt-in, default 0); -1: no exchange (measurement)
   double *scalars;            // a few device doubles for fused reductions (lazily allocated)
   void *mcell;           // T [cell][MC_COUNT] per-cell metric when every cell is affine, else null
   uint8_t *matid;        // [n_cells] or nullptr

@@ -5,6 +5,16 @@
 
 #include "kernels.h"
 
+#ifndef B200MF_MINB5
+#define B200MF_MINB5 6
+#endif
+#ifndef B200MF_MINB6
+#define B200MF_MINB6 2
+#endif
+#ifndef B200MF_MINB7
+#define B200MF_MINB7 2
+#endif
+
 namespace b200mf {
 
 // every translation unit owns a copy of the __constant__ 1-D matrices (cell_kernel.cuh)
@@ -76,7 +86,14 @@ static int launch_cell_loop(const b200mf_ctx *ctx, const T *src, T *dst, const t
   if constexpr (!Ly::WARP_MODE) {
     // scalar Q4 (6 cells per 160-thread group): cap the registers at two resident groups per SM - only one warp of a
     // group works during the plane phase, a second group keeps the FP64 pipe fed (B200: 0.94 -> 0.69 ms at 1.7e7 DoFs)
-    constexpr int MINB = (Op::NC == 1 && N == 5 && !DIAG) ? 2 : 1;
+    // vector operator, N >= 5 (sliced tables, several cells per block): cap the registers so that B200MF_MINB<N> blocks
+    // are resident per SM (N = 5: 6 x 64 threads at 168 registers)
+    constexpr bool VEC_VMULT = Op::NC == 3 && Op::INTEGRATE && !Op::PLAIN && !DIAG;
+    constexpr int MINB = (Op::NC == 1 && N == 5 && !DIAG) ? 2
+                         : (VEC_VMULT && N == 5)          ? B200MF_MINB5
+                         : (VEC_VMULT && N == 6)          ? B200MF_MINB6
+                         : (VEC_VMULT && N == 7)          ? B200MF_MINB7
+                                                          : 1;
     return launch_variant<T, N, Op, DIAG, 1, MINB>(ctx, src, dst, oa, g0, g1, stream, dot);
   } else {
     // warps per block, from the B200 sweep tools/gpu_gpb_sweep.sh (profiles/r01_v3_gpb_sweep.jsonl): shared memory
@@ -93,6 +110,11 @@ static int launch_cell_loop(const b200mf_ctx *ctx, const T *src, T *dst, const t
   }
 }
 
+#ifdef B200MF_ONLY_N  // tuning builds: instantiate one degree only
+#define B2_DISPATCH_N(N_, T_, ...)                                                                \
+  if ((N_) == B200MF_ONLY_N) { constexpr int N = B200MF_ONLY_N; using T = T_; __VA_ARGS__; }     \
+  else rc = set_error(B200MF_ERR_ARG, "tuning build: only degree %d is instantiated", B200MF_ONLY_N - 1);
+#else
 #define B2_DISPATCH_N(N_, T_, ...)                                                  \
   switch (N_) {                                                                      \
     case 2: { constexpr int N = 2; using T = T_; __VA_ARGS__; } break;                      \
@@ -103,5 +125,6 @@ static int launch_cell_loop(const b200mf_ctx *ctx, const T *src, T *dst, const t
     case 7: { constexpr int N = 7; using T = T_; __VA_ARGS__; } break;                      \
     default: rc = set_error(B200MF_ERR_ARG, "unsupported degree %d", (N_) - 1);      \
   }
+#endif
 
 }  // namespace b200mf

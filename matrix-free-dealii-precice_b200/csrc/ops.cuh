@@ -91,7 +91,8 @@ struct NHOp {
   using Ly = Layout<N, NC, sizeof(T) / 4>;
   using Args = NHArgs<T>;
   using CellState = NHCell<T>;
-  static constexpr int FS = N * Ly::L;
+  static constexpr int FS = Ly::FS;    // field stride of the staged tables
+  static constexpr int FSP = Ly::FSP;  // field stride of plain tables (big, pos) and the scratch
   static __device__ __forceinline__ void cell_begin(const Args &oa, int64_t cell, bool valid, int, CellState &st) {
     nh_cell_begin(oa, cell, valid, st);
   }
@@ -100,15 +101,14 @@ struct NHOp {
   // scalar_referential: second evaluate() on the cached cell-local displacement (:861-867)
   static __device__ __forceinline__ void load_pre(const Args &oa, int64_t group, int lane, bool active, int c, const uint32_t (&)[N],
                                                   T (&up)[N]) {
-    const T *p = oa.pos + ((size_t)group * 3 + c) * FS + lane;
+    const T *p = oa.pos + ((size_t)group * 3 + c) * FSP + lane;
 #pragma unroll
     for (int k = 0; k < N; ++k) up[k] = active ? __ldg(p + (size_t)k * Ly::L) : T(0);
   }
   // F = I + Grad u through the reference inverse Jacobian (:872-899), kept in shared memory for the main pass
-  static __device__ __forceinline__ void quad_pre(const Args &, const CellState &, bool active, const T *qs, T *scr,
+  static __device__ __forceinline__ void quad_pre(const Args &, const CellState &, bool active, const T *q, T *scr,
                                                   int64_t, int iq, int lane, const T (&)[NC], const T (&G)[NC][3]) {
     if (!active) return;
-    const T *q = qs + iq * Ly::L + lane;
     T K[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) K[i] = q[(MF_K + i) * FS];
@@ -117,10 +117,10 @@ struct NHOp {
     for (int c = 0; c < 3; ++c)
 #pragma unroll
       for (int e = 0; e < 3; ++e)
-        o[(c * 3 + e) * FS] = K[e * 3 + 0] * G[c][0] + K[e * 3 + 1] * G[c][1] + K[e * 3 + 2] * G[c][2] + (c == e ? T(1) : T(0));
+        o[(c * 3 + e) * FSP] = K[e * 3 + 0] * G[c][0] + K[e * 3 + 1] * G[c][1] + K[e * 3 + 2] * G[c][2] + (c == e ? T(1) : T(0));
   }
 
-  static __device__ __forceinline__ void quad(const Args &oa, const CellState &st, bool active, const T *qs, const T *qs2,
+  static __device__ __forceinline__ void quad(const Args &oa, const CellState &st, bool active, const T *q, const T *q2,
                                               const T *scr, int64_t group, int iq, int lane, const T (&v)[NC],
                                               const T (&G)[NC][3], T (&ov)[NC], T (&oG)[NC][3]) {
     if (!active) {
@@ -128,7 +128,6 @@ struct NHOp {
       for (int c = 0; c < NC; ++c) ov[c] = oG[c][0] = oG[c][1] = oG[c][2] = T(0);
       return;
     }
-    const T *q = qs + iq * Ly::L + lane;
     T K[9];  // inverse Jacobian of the frame the variant integrates on (QF_K == MF_K == 0)
 #pragma unroll
     for (int i = 0; i < 9; ++i) K[i] = q[i * FS];
@@ -212,13 +211,13 @@ struct NHOp {
       T sv[6];
 #pragma unroll
       for (int I = 0; I < 6; ++I) sv[I] = (I < 3) ? g[VI[I]][VJ[I]] : (g[VI[I]][VJ[I]] + g[VJ[I]][VI[I]]);  // off-diagonals counted twice
-      const T *C4 = oa.big + (size_t)group * Ly::table_stride(36) + iq * Ly::L + lane;
+      const T *C4 = oa.big + (size_t)group * Ly::plain_stride(36) + iq * Ly::L + lane;
       T cs6[6];
 #pragma unroll
       for (int I = 0; I < 6; ++I) {
         T a = T(0);
 #pragma unroll
-        for (int J = 0; J < 6; ++J) a += __ldg(C4 + (size_t)(I * 6 + J) * FS) * sv[J];
+        for (int J = 0; J < 6; ++J) a += __ldg(C4 + (size_t)(I * 6 + J) * FSP) * sv[J];
         cs6[I] = a;
       }
       const T Cs[3][3] = {{cs6[0], cs6[3], cs6[4]}, {cs6[3], cs6[1], cs6[5]}, {cs6[4], cs6[5], cs6[2]}};
@@ -228,7 +227,7 @@ struct NHOp {
         for (int e = 0; e < 3; ++e) sub[c][e] = Cs[c][e] + g[c][0] * Tm[0][e] + g[c][1] * Tm[1][e] + g[c][2] * Tm[2][e];
       vs = st.rho_alpha * c2;
     } else if constexpr (V == NHV_TENSOR4_NS) {  // :996-1010
-      const T *A4 = oa.big + (size_t)group * Ly::table_stride(81) + iq * Ly::L + lane;
+      const T *A4 = oa.big + (size_t)group * Ly::plain_stride(81) + iq * Ly::L + lane;
 #pragma unroll
       for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -237,18 +236,18 @@ struct NHOp {
 #pragma unroll
           for (int k = 0; k < 3; ++k)
 #pragma unroll
-            for (int l = 0; l < 3; ++l) a += __ldg(A4 + (size_t)(((i * 3 + j) * 3 + k) * 3 + l) * FS) * g[k][l];  // double_contract<2,0,3,1>
+            for (int l = 0; l < 3; ++l) a += __ldg(A4 + (size_t)(((i * 3 + j) * 3 + k) * 3 + l) * FSP) * g[k][l];  // double_contract<2,0,3,1>
           sub[i][j] = a;
         }
       vs = st.rho_alpha;
     } else {  // NHV_SCALAR_REF :848-943
-      const T cc = qs2[iq * Ly::L + lane];
+      const T cc = q2[0];
       const T *fp = scr + iq * Ly::L + lane;
       T F[3][3], Fa[3][3];
 #pragma unroll
       for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) F[i][j] = fp[(i * 3 + j) * FS];
+        for (int j = 0; j < 3; ++j) F[i][j] = fp[(i * 3 + j) * FSP];
       const T idet = T(1) / adj3(F, Fa);
       T gx[3][3];  // Grad v F^-1 :910-922
 #pragma unroll
@@ -306,7 +305,7 @@ struct NHCacheOp {
   static constexpr bool PLAIN = true, INTEGRATE = false, PRE = false, STORE_DOFS = (V == NHV_SCALAR_REF);
   using Ly = Layout<N, NC, sizeof(T) / 4>;
   using Args = NHCacheArgs<T>;
-  static constexpr size_t FS = (size_t)N * Ly::L;
+  static constexpr size_t FS = Ly::FS, FSP = Ly::FSP;
   struct CellState {
     T mu, lambda;
     bool real;
@@ -324,16 +323,15 @@ struct NHCacheOp {
 #pragma unroll
     for (int c = 0; c < NC; ++c)
 #pragma unroll
-      for (int k = 0; k < N; ++k) oa.pos[((size_t)group * 3 + c) * FS + (size_t)k * Ly::L + lane] = u[c][k];
+      for (int k = 0; k < N; ++k) oa.pos[((size_t)group * 3 + c) * FSP + (size_t)k * Ly::L + lane] = u[c][k];
   }
   static __device__ __forceinline__ void load_pre(const Args &, int64_t, int, bool, int, const uint32_t (&)[N], T (&)[N]) {}
   static __device__ __forceinline__ void quad_pre(const Args &, const CellState &, bool, const T *, T *, int64_t, int, int,
                                                   const T (&)[NC], const T (&)[NC][3]) {}
-  static __device__ __forceinline__ void quad(const Args &oa, const CellState &st, bool active, const T *qs, const T *, const T *,
+  static __device__ __forceinline__ void quad(const Args &oa, const CellState &st, bool active, const T *m, const T *, const T *,
                                               int64_t group, int iq, int lane, const T (&)[NC], const T (&G)[NC][3],
                                               T (&)[NC], T (&)[NC][3]) {
     if (!active) return;
-    const T *m = qs + iq * Ly::L + lane;
     T Kr[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) Kr[i] = m[(MF_K + i) * FS];
@@ -348,9 +346,9 @@ struct NHCacheOp {
     const T detF = adj3(F, Fi);
     if (st.real && !(detF > T(0))) atomicAdd(oa.n_bad, 1ull);  // :430-435
     const T idet = T(1) / detF;
-    const size_t qoff = (size_t)iq * Ly::L + lane;
+    const size_t qoff = (size_t)iq * Ly::L + lane;  // plain tables
     if constexpr (nhv_deformed(V)) {
-      T *q = oa.qd + (size_t)group * Ly::table_stride(nhv_staged_fields(V)) + qoff;
+      T *q = oa.qd + (size_t)group * Ly::table_stride(nhv_staged_fields(V)) + (size_t)iq * Ly::kq_stride(nhv_staged_fields(V)) + lane;
       // K_cur[e][f] = sum_m Finv[m][e] K_ref[m][f]   (invjac_cur = F^-T invjac_ref)
 #pragma unroll
       for (int e = 0; e < 3; ++e)
@@ -380,7 +378,7 @@ struct NHCacheOp {
         } else {
           q[QF4_C2 * FS] = idet;  // :485-486
           // cached_tensor4 = (2 scalar / J) S + (2 lambda / J) IxI as the 6x6 SymmetricTensor<4> :488-493
-          T *C4 = oa.big + (size_t)group * Ly::table_stride(36) + qoff;
+          T *C4 = oa.big + (size_t)group * Ly::plain_stride(36) + qoff;
           const T a = scalar * T(2) * idet, b = st.lambda * T(2) * idet;
 #pragma unroll
           for (int I = 0; I < 6; ++I)
@@ -389,14 +387,14 @@ struct NHCacheOp {
               const int i = I6[I], j = J6[I], k = I6[J], l = J6[J];
               const T S4 = T(0.5) * T((i == k && j == l) + (i == l && j == k));
               const T IxI = T(i == j && k == l);
-              C4[(size_t)(I * 6 + J) * FS] = a * S4 + b * IxI;
+              C4[(size_t)(I * 6 + J) * FSP] = a * S4 + b * IxI;
             }
         }
       }
     } else if constexpr (V == NHV_SCALAR_REF) {
-      oa.qd2[(size_t)group * Ly::table_stride(1) + qoff] = st.mu - T(2) * st.lambda * log(detF);  // :459-461
+      oa.qd2[(size_t)group * Ly::table_stride(1) + (size_t)iq * Ly::kq_stride(1) + lane] = st.mu - T(2) * st.lambda * log(detF);  // :459-461
     } else {  // NHV_TENSOR4_NS :497-514
-      T *A4 = oa.big + (size_t)group * Ly::table_stride(81) + qoff;
+      T *A4 = oa.big + (size_t)group * Ly::plain_stride(81) + qoff;
       const T lnJ = log(detF);
       T Fv[3][3];  // F^-1
 #pragma unroll
@@ -415,7 +413,7 @@ struct NHCacheOp {
               const T t1 = Fv[j][i] * Fv[l][k];  // outer_product(F^-T, F^-T)
               const T t2 = Fv[l][i] * Fv[j][k];  // outer_product_iljk(F^-T, F^-1), :23-46
               const T t3 = T(i == k && j == l);  // IxI_ikjl
-              A4[(size_t)(((i * 3 + j) * 3 + k) * 3 + l) * FS] = l2 * t1 + sc * t2 + st.mu * t3;
+              A4[(size_t)(((i * 3 + j) * 3 + k) * 3 + l) * FSP] = l2 * t1 + sc * t2 + st.mu * t3;
             }
     }
   }
@@ -445,21 +443,20 @@ struct LaplaceOp {
   static __device__ __forceinline__ void load_pre(const Args &, int64_t, int, bool, int, const uint32_t (&)[N], T (&)[N]) {}
   static __device__ __forceinline__ void quad_pre(const Args &, const CellState &, bool, const T *, T *, int64_t, int, int,
                                                   const T (&)[NC], const T (&)[NC][3]) {}
-  static __device__ __forceinline__ void quad(const Args &oa, const CellState &, bool active, const T *qs, const T *qs2, const T *,
-                                              int64_t, int iq, int lane, const T (&v)[NC], const T (&G)[NC][3],
+  static __device__ __forceinline__ void quad(const Args &oa, const CellState &, bool active, const T *m, const T *q2, const T *,
+                                              int64_t, int, int, const T (&v)[NC], const T (&G)[NC][3],
                                               T (&ov)[NC], T (&oG)[NC][3]) {
     if (!active) {
       ov[0] = oG[0][0] = oG[0][1] = oG[0][2] = T(0);
       return;
     }
-    constexpr int FS = N * Ly::L;
-    const T *m = qs + iq * Ly::L + lane;
+    constexpr int FS = Ly::FS;
     T K[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) K[i] = m[(MF_K + i) * FS];
     const T w = m[MF_W * FS];
     T k = oa.delta_t;
-    if (oa.stage2 != nullptr) k *= qs2[iq * Ly::L + lane];  // :245-247
+    if (oa.stage2 != nullptr) k *= q2[0];  // :245-247
     T g[3];
 #pragma unroll
     for (int e = 0; e < 3; ++e) g[e] = K[e * 3 + 0] * G[0][0] + K[e * 3 + 1] * G[0][1] + K[e * 3 + 2] * G[0][2];
@@ -493,12 +490,12 @@ struct LaplaceAffineOp {
   static __device__ __forceinline__ void load_pre(const Args &, int64_t, int, bool, int, const uint32_t (&)[N], T (&)[N]) {}
   static __device__ __forceinline__ void quad_pre(const Args &, const CellState &, bool, const T *, T *, int64_t, int, int,
                                                   const T (&)[NC], const T (&)[NC][3]) {}
-  static __device__ __forceinline__ void quad(const Args &oa, const CellState &st, bool active, const T *, const T *qs2, const T *,
-                                              int64_t, int iq, int lane, const T (&v)[NC], const T (&G)[NC][3],
+  static __device__ __forceinline__ void quad(const Args &oa, const CellState &st, bool active, const T *, const T *q2, const T *,
+                                              int64_t, int iq, int, const T (&v)[NC], const T (&G)[NC][3],
                                               T (&ov)[NC], T (&oG)[NC][3]) {
     const T wk = Shape<T, N>::W(iq);
     T k = wk;
-    if (oa.stage2 != nullptr && active) k *= qs2[iq * Ly::L + lane];  // coefficient(cell, q), heat_transfer.h:245-247
+    if (oa.stage2 != nullptr && active) k *= q2[0];  // coefficient(cell, q), heat_transfer.h:245-247
     oG[0][0] = k * (st.M[0] * G[0][0] + st.M[3] * G[0][1] + st.M[4] * G[0][2]);
     oG[0][1] = k * (st.M[3] * G[0][0] + st.M[1] * G[0][1] + st.M[5] * G[0][2]);
     oG[0][2] = k * (st.M[4] * G[0][0] + st.M[5] * G[0][1] + st.M[2] * G[0][2]);
@@ -531,7 +528,7 @@ struct NHResidualOp {
   static constexpr bool PLAIN = true, INTEGRATE = true, PRE = true, STORE_DOFS = false;
   using Ly = Layout<N, NC, sizeof(T) / 4>;
   using Args = NHResidualArgs<T>;
-  static constexpr int FS = N * Ly::L;
+  static constexpr int FS = Ly::FS;
   struct CellState {
     T mu, lambda, kappa, c_1, rho;
     bool real;
@@ -558,7 +555,7 @@ struct NHResidualOp {
 #pragma unroll
     for (int c = 0; c < 3; ++c) scr[(c * N + iq) * Ly::L + lane] = v[c];  // phi_acc.get_value(q)
   }
-  static __device__ __forceinline__ void quad(const Args &oa, const CellState &st, bool active, const T *qs, const T *, const T *scr,
+  static __device__ __forceinline__ void quad(const Args &oa, const CellState &st, bool active, const T *q, const T *, const T *scr,
                                               int64_t, int iq, int lane, const T (&)[NC], const T (&G)[NC][3], T (&ov)[NC],
                                               T (&oG)[NC][3]) {
     if (!active) {
@@ -566,7 +563,6 @@ struct NHResidualOp {
       for (int c = 0; c < NC; ++c) ov[c] = oG[c][0] = oG[c][1] = oG[c][2] = T(0);
       return;
     }
-    const T *q = qs + iq * Ly::L + lane;
     T K[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) K[i] = q[(MF_K + i) * FS];
@@ -644,15 +640,15 @@ struct LaplaceRhsOp {
   static __device__ __forceinline__ void load_pre(const Args &, int64_t, int, bool, int, const uint32_t (&)[N], T (&)[N]) {}
   static __device__ __forceinline__ void quad_pre(const Args &, const CellState &, bool, const T *, T *, int64_t, int, int,
                                                   const T (&)[NC], const T (&)[NC][3]) {}
-  static __device__ __forceinline__ void quad(const Args &oa, const CellState &st, bool active, const T *qs, const T *qs2, const T *,
-                                              int64_t, int iq, int lane, const T (&v)[NC], const T (&)[NC][3], T (&ov)[NC],
+  static __device__ __forceinline__ void quad(const Args &oa, const CellState &st, bool active, const T *q, const T *q2, const T *,
+                                              int64_t, int iq, int, const T (&v)[NC], const T (&)[NC][3], T (&ov)[NC],
                                               T (&oG)[NC][3]) {
     oG[0][0] = oG[0][1] = oG[0][2] = T(0);
     ov[0] = T(0);
     if (!active) return;
-    constexpr int FS = N * Ly::L;
-    const T w = AFFINE ? st.mw * Shape<T, N>::W(iq) : qs[MF_W * FS + iq * Ly::L + lane];
-    const T f = oa.stage2 != nullptr ? qs2[iq * Ly::L + lane] : oa.source_const;
+    constexpr int FS = Ly::FS;
+    const T w = AFFINE ? st.mw * Shape<T, N>::W(iq) : q[MF_W * FS];
+    const T f = oa.stage2 != nullptr ? q2[0] : oa.source_const;
     ov[0] = w * (v[0] + oa.delta_t * f);  // :607-611
   }
 };

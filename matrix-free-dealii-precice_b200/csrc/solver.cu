@@ -642,10 +642,18 @@ extern "C" int b200mf_chebyshev_step(b200mf_chebyshev *ch, void *dst, const void
 // MGTransferMatrixFree (A.8): uniformly refined parent/children, tensor-product 1-D embedding
 namespace b200mf {
 constexpr int MAXM = 2 * MAXN - 1;
-struct Embed {
-  float P[MAXM * MAXN];  // P[m][j] = l_j(x_m): fine patch node m (2p+1 per direction) <- coarse node j
-  float R[MAXN * MAXM];  // R[i][m]: coarse node i <- fine patch nodes (evaluation of the fine function at x_i)
+struct Embed {  // in the number type of the level vectors: an FP64 hierarchy / interpolate_to_mg is not truncated to FP32
+  double Pd[MAXM * MAXN];  // P[m][j] = l_j(x_m): fine patch node m (2p+1 per direction) <- coarse node j
+  double Rd[MAXN * MAXM];  // R[i][m]: coarse node i <- fine patch nodes (evaluation of the fine function at x_i)
+  float Pf[MAXM * MAXN];
+  float Rf[MAXN * MAXM];
+  template <typename S> __device__ __forceinline__ const S *P() const;
+  template <typename S> __device__ __forceinline__ const S *R() const;
 };
+template <> __device__ __forceinline__ const double *Embed::P<double>() const { return Pd; }
+template <> __device__ __forceinline__ const double *Embed::R<double>() const { return Rd; }
+template <> __device__ __forceinline__ const float *Embed::P<float>() const { return Pf; }
+template <> __device__ __forceinline__ const float *Embed::R<float>() const { return Rf; }
 
 // one block per parent cell; NC components one after the other through shared memory
 // MODE 0: prolongate (dst_fine = P src_coarse), 1: prolongate_and_add, 2: restrict_and_add (dst_coarse += P^T w.*src_fine),
@@ -653,64 +661,67 @@ struct Embed {
 template <typename T, int MODE>
 __global__ void transfer_kernel(int N, int NC, const uint32_t *__restrict__ cidx /*[cell][N^3]*/, const uint32_t *__restrict__ pidx /*[cell][M^3]*/,
                                 const float *__restrict__ wfine /*[fine node] 1/multiplicity*/, int64_t cstride_c, int64_t cstride_f,
-                                const T *__restrict__ src, T *__restrict__ dst, Embed E) {
-  extern __shared__ float sm[];
+                                const T *__restrict__ src, T *__restrict__ dst, const __grid_constant__ Embed E) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  using S = T;  // scratch and 1-D embedding in the number type of the level
+  S *sm = reinterpret_cast<S *>(sm_raw);
+  const S *EP = E.P<S>(), *ER = E.R<S>();
   const int M = 2 * N - 1;
   const int N3 = N * N * N, M3 = M * M * M;
-  float *a = sm;           // up to M^3
-  float *b = sm + M3;      // up to M^3
+  S *a = sm;           // up to M^3
+  S *b = sm + M3;      // up to M^3
   const int64_t cell = blockIdx.x;
   const uint32_t *ci = cidx + cell * N3, *pi = pidx + cell * M3;
   const bool up = (MODE == 0 || MODE == 1);
   for (int c = 0; c < NC; ++c) {
     if (up) {
       // gather coarse (constrained coarse DoFs hold 0 in level vectors; read plainly)
-      for (int i = threadIdx.x; i < N3; i += blockDim.x) a[i] = (float)src[(size_t)c * cstride_c + (ci[i] & NODE_MASK)];
+      for (int i = threadIdx.x; i < N3; i += blockDim.x) a[i] = (S)src[(size_t)c * cstride_c + (ci[i] & NODE_MASK)];
       __syncthreads();
       // x: [k][j][i] (N,N,N) -> (N,N,M)
       for (int o = threadIdx.x; o < N * N * M; o += blockDim.x) {
         const int m = o % M, r = o / M;
-        float s = 0.f;
-        for (int i = 0; i < N; ++i) s += E.P[m * N + i] * a[r * N + i];
+        S s = S(0);
+        for (int i = 0; i < N; ++i) s += EP[m * N + i] * a[r * N + i];
         b[o] = s;
       }
       __syncthreads();
       // y: (N,N,M) -> (N,M,M)
       for (int o = threadIdx.x; o < N * M * M; o += blockDim.x) {
         const int mx = o % M, my = (o / M) % M, k = o / (M * M);
-        float s = 0.f;
-        for (int j = 0; j < N; ++j) s += E.P[my * N + j] * b[(k * N + j) * M + mx];
+        S s = S(0);
+        for (int j = 0; j < N; ++j) s += EP[my * N + j] * b[(k * N + j) * M + mx];
         a[o] = s;
       }
       __syncthreads();
       // z: (N,M,M) -> (M,M,M), write
       for (int o = threadIdx.x; o < M3; o += blockDim.x) {
         const int mxy = o % (M * M), mz = o / (M * M);
-        float s = 0.f;
-        for (int k = 0; k < N; ++k) s += E.P[mz * N + k] * a[k * M * M + mxy];
+        S s = S(0);
+        for (int k = 0; k < N; ++k) s += EP[mz * N + k] * a[k * M * M + mxy];
         const uint32_t id = pi[o];
         if (!(id & node_flag(c))) {  // level Dirichlet DoFs stay zero
           T *p = dst + (size_t)c * cstride_f + (id & NODE_MASK);
           if (MODE == 0)
             *p = (T)s;  // every parent of a shared node writes the same value
           else
-            atomicAdd(p, (T)(s * wfine[id & NODE_MASK]));
+            atomicAdd(p, (T)(s * (S)wfine[id & NODE_MASK]));
         }
       }
       __syncthreads();
     } else {
       for (int o = threadIdx.x; o < M3; o += blockDim.x) {
         const uint32_t id = pi[o];
-        float v = (float)src[(size_t)c * cstride_f + (id & NODE_MASK)];
-        if (MODE == 2) v = (id & node_flag(c)) ? 0.f : v * wfine[id & NODE_MASK];
+        S v = (S)src[(size_t)c * cstride_f + (id & NODE_MASK)];
+        if (MODE == 2) v = (id & node_flag(c)) ? S(0) : v * (S)wfine[id & NODE_MASK];
         a[o] = v;
       }
       __syncthreads();
-      const float *Mx = (MODE == 2) ? E.P : E.R;  // restriction: P^T ; interpolation: R
+      const S *Mx = (MODE == 2) ? EP : ER;  // restriction: P^T ; interpolation: R
       // z: (M,M,M) -> (N,M,M)
       for (int o = threadIdx.x; o < N * M * M; o += blockDim.x) {
         const int mxy = o % (M * M), k = o / (M * M);
-        float s = 0.f;
+        S s = S(0);
         for (int mz = 0; mz < M; ++mz) s += (MODE == 2 ? Mx[mz * N + k] : Mx[k * M + mz]) * a[mz * M * M + mxy];
         b[o] = s;
       }
@@ -718,7 +729,7 @@ __global__ void transfer_kernel(int N, int NC, const uint32_t *__restrict__ cidx
       // y: (N,M,M) -> (N,N,M)
       for (int o = threadIdx.x; o < N * N * M; o += blockDim.x) {
         const int mx = o % M, j = (o / M) % N, k = o / (M * N);
-        float s = 0.f;
+        S s = S(0);
         for (int my = 0; my < M; ++my) s += (MODE == 2 ? Mx[my * N + j] : Mx[j * M + my]) * b[(k * M + my) * M + mx];
         a[o] = s;
       }
@@ -726,7 +737,7 @@ __global__ void transfer_kernel(int N, int NC, const uint32_t *__restrict__ cidx
       // x: (N,N,M) -> (N,N,N)
       for (int o = threadIdx.x; o < N3; o += blockDim.x) {
         const int i = o % N, r = o / N;
-        float s = 0.f;
+        S s = S(0);
         for (int mx = 0; mx < M; ++mx) s += (MODE == 2 ? Mx[mx * N + i] : Mx[i * M + mx]) * a[r * M + mx];
         const uint32_t id = ci[o];
         T *p = dst + (size_t)c * cstride_c + (id & NODE_MASK);
@@ -773,11 +784,11 @@ extern "C" int b200mf_mg_transfer_create(b200mf_mg_transfer **out, b200mf_ctx *c
   std::vector<double> xm(M);
   for (int m = 0; m < M; ++m) xm[m] = m <= p ? 0.5 * nd[m] : 0.5 + 0.5 * nd[m - p];
   for (int m = 0; m < M; ++m)
-    for (int j = 0; j < N; ++j) t->E.P[m * N + j] = (float)lagrange_1d(nd, N, j, xm[m]);
+    for (int j = 0; j < N; ++j) t->E.Pf[m * N + j] = (float)(t->E.Pd[m * N + j] = lagrange_1d(nd, N, j, xm[m]));
   for (int i = 0; i < N; ++i) {  // coarse node x_i lies in child ch; fine basis functions of that child evaluated there
     const int ch = (nd[i] <= 0.5) ? 0 : 1;
     const double xi = 2.0 * nd[i] - ch;  // child-local coordinate
-    for (int l = 0; l < N; ++l) t->E.R[i * M + ch * p + l] = (float)lagrange_1d(nd, N, l, xi);
+    for (int l = 0; l < N; ++l) t->E.Rf[i * M + ch * p + l] = (float)(t->E.Rd[i * M + ch * p + l] = lagrange_1d(nd, N, l, xi));
   }
   // patch index table: fine node of patch position (mx,my,mz) through the child that contains it
   std::vector<uint32_t> pidx((size_t)coarse->n_cells * M3);
@@ -849,11 +860,11 @@ extern "C" int b200mf_mg_transfer_destroy(b200mf_mg_transfer *t) {
 template <typename T, int MODE>
 static int transfer_launch(b200mf_mg_transfer *t, void *dst, const void *src) {
   const int N = t->coarse->N, M = 2 * N - 1;
-  const size_t smem = 2 * (size_t)M * M * M * sizeof(float);
+  const size_t smem = 2 * (size_t)M * M * M * sizeof(T);
   auto kern = transfer_kernel<T, MODE>;
   static bool attr = false;
   if (!attr) {
-    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * MAXM * MAXM * MAXM * (int)sizeof(float)));
+    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * MAXM * MAXM * MAXM * (int)sizeof(T)));
     attr = true;
   }
   if (t->n_coarse_cells == 0) return 0;
@@ -864,6 +875,10 @@ static int transfer_launch(b200mf_mg_transfer *t, void *dst, const void *src) {
 }
 template <int MODE>
 static int transfer_dispatch(b200mf_mg_transfer *t, void *dst, const void *src) {
+  // the exchanges of the coarse vector run on the coarse context's stream, the kernel on the fine one's: nothing orders two
+  // different streams here, so they must be one and the same (b200mf.h: b200mf_ctx_set_stream)
+  if (t->coarse->stream != t->fine->stream)
+    return set_error(B200MF_ERR_ARG, "MG transfer: the coarse and the fine context must use the same CUDA stream");
   return t->coarse->dtype == B200MF_F64 ? transfer_launch<double, MODE>(t, dst, src) : transfer_launch<float, MODE>(t, dst, src);
 }
 
@@ -971,7 +986,10 @@ extern "C" int b200mf_mg_vmult(b200mf_mg *mg, void *dst, const void *src) {
   const int64_t n = c->n_int;
   const unsigned g = vgrid(n, c);
   const bool lf = c->dtype == B200MF_F32, of = o->dtype == B200MF_F32;
-  // all levels share one stream with the outer context in practice; order level work after the outer stream's
+  // the V-cycle hands vectors from level to level and to the outer context without events: one stream for all of them
+  for (int l = 0; l <= top; ++l)
+    if (mg->smoother[l]->A.ctx->stream != o->stream)
+      return set_error(B200MF_ERR_ARG, "MG: level %d and the system context use different CUDA streams (b200mf_ctx_set_stream)", l);
   if (lf && !of)
     convert_kernel<float, double><<<g, 256, 0, c->stream>>>(n, (const double *)src, (float *)mg->defect[top]);
   else if (!lf && !of)

@@ -1,6 +1,9 @@
 #!/bin/bash
-# tuning: tools/build_variant.sh <name> <extra nvcc flags...>  -> gpurun_variants/libb200mf_<name>.so (separate object dir)
-name=$1; shift
-cd "$(dirname "$0")/../matrix-free-dealii-precice_b200/csrc"
-mkdir -p ../../gpurun_variants
-make -s BUILD=build_$name OUT=../../gpurun_variants/libb200mf_$name.so EXTRA="$*" 2>&1 | grep -v "^$" | head
+# Tuning builds: tools/build_variant.sh <tag> "<extra nvcc flags>"  ->  gpurun_variants/<tag>/libb200mf.so
+# (select at run time with B200MF_LIBRARY=gpurun_variants/<tag>/libb200mf.so)
+set -e
+tag=$1; shift
+root=$(cd "$(dirname "$0")/.." && pwd)
+mkdir -p "$root/gpurun_variants/$tag"
+make -C "$root/matrix-free-dealii-precice_b200/csrc" BUILD=build_$tag OUT="$root/gpurun_variants/$tag/libb200mf.so" EXTRA="$*" 2>&1 | grep -E "error|warning: v|Error" || true
+ls -la "$root/gpurun_variants/$tag/libb200mf.so"
