@@ -36,10 +36,28 @@ METRIC = "nh_tangent_vmult_dofs_per_s"
 QPOINT_VALUES = {"tensor2": 18, "scalar_referential": 14, "tensor4": 53, "tensor4_ns": 91, "form0": 20}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the cell-loop kernel from the committed
-# `ncu --set full` captures (profiles/r01_v3_ncu_summary.md), keyed by (degree, variant, dtype) at the default mesh
-NCU_TRAFFIC = {(2, "tensor2", "f64"): 9.95e9, (3, "tensor2", "f64"): 7.46e9, (4, "tensor2", "f64"): 6.81e9,
-               (3, "tensor2", "f32"): 3.63e9}
+# roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum per launch of the cell-loop kernel, read from the committed
+# `ncu --set full` raw page of the same workload (it cannot be measured inside a timed run); None if no capture is committed
+NCU_RAW = "profiles/r02_ncu_q{p}_raw.csv"
+
+
+def ncu_traffic(p, variant, dtype, default_mesh):
+    if variant != "tensor2" or dtype != "f64" or not default_mesh:
+        return None, None
+    import csv
+
+    path = os.path.join(ROOT, NCU_RAW.format(p=p))
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units, vals = rows[0], rows[1], rows[2]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+        tot = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(key)
+            tot += float(vals[i]) * scale[units[i]]
+        return tot, NCU_RAW.format(p=p)
+    except Exception:
+        return None, None
 
 
 def algorithmic_bytes_per_cell(p, esize=8, variant="tensor2"):
@@ -49,7 +67,7 @@ def algorithmic_bytes_per_cell(p, esize=8, variant="tensor2"):
     return 2 * esize * 3 * p**3 + 4 * n**3 + QPOINT_VALUES[variant] * esize * n**3
 
 
-def build_problem(p, ncell_dir, dtype="f64", comm=None, caching="tensor2", formulation=1):
+def build_problem(p, ncell_dir, dtype="f64", comm=None, caching="tensor2", formulation=1, numbering="lexicographic", curved=False):
     """One brick of ncell_dir^3 cells per rank (SURVEY.md §8d config 5: 1x1x1, 2x1x1, 2x2x1, 2x2x2 bricks);
     shared faces are exchanged through the library's partitioner (update_ghost_values / compress(add))."""
     from b200mf import MatrixFree, NeoHookOperator
@@ -63,8 +81,12 @@ def build_problem(p, ncell_dir, dtype="f64", comm=None, caching="tensor2", formu
         u = synthetic_displacement(m.node_coordinates(), 0.05)
         mf = MatrixFree.from_partition(m, comm, dtype=dtype)
     else:
-        m = StructuredMesh((ncell_dir,) * 3, p)
+        from b200mf.mesh import smooth_mapping
+
+        m = StructuredMesh((ncell_dir,) * 3, p, mapping=smooth_mapping(0.05) if curved else None)
         m.clamp([(0, 0)], 3)
+        if numbering == "cellwise_morton":
+            m.renumber_cellwise_morton()
         u = synthetic_displacement(m.node_coordinates(), 0.05)
         mf = MatrixFree.from_mesh(m, 3, dtype=dtype)
     op = NeoHookOperator()
@@ -215,6 +237,160 @@ def workload_config(p, nc, ngpus, caching="tensor2", formulation=1):
             "parallelism": f"dd{ngpus}", "l2": "vectors+tables per step >> 126 MB L2 (no flush needed)"}
 
 
+def roofline_of(p, es, variant, n_cells, kernel_ms, step_ms, peak):
+    alg = algorithmic_bytes_per_cell(p, es, variant) * n_cells
+    return alg, alg / (kernel_ms * 1e-3) / 1e9 / peak, alg / (step_ms * 1e-3) / 1e9 / peak
+
+
+def timed_vmults(torch, op, mf, src, dst, steps, stream, barrier):
+    """`steps` vmults between CUDA events on `stream`; the library brackets every cell-loop launch with its own event pair
+    (b200mf_ctx_time_kernels) -> (ms per step, cell-loop kernel ms per step, launches timed, per-step ms)."""
+    mf.time_kernels(True)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    # an untimed ~2 ms spin kernel in front of the first event lets the host run ahead, so that the timed region
+    # measures K steps of device work and not the host latency of enqueueing the first one after the barrier
+    torch.cuda._sleep(4_000_000)
+    ev[0].record(stream)
+    for i in range(steps):
+        op.vmult(dst, src)
+        ev[i + 1].record(stream)
+    barrier()
+    kernel_ms_total, kernel_launches = mf.kernel_time()
+    mf.time_kernels(False)
+    per_step = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(steps))
+    return ev[0].elapsed_time(ev[-1]) / steps, kernel_ms_total / steps, int(kernel_launches), per_step
+
+
+def degree_line(torch, q, nc, dtype, caching, formulation, variant, peak, stream_ptr, numbering="lexicographic", curved=False, steps=10):
+    """One (degree, mesh flavour) point of the metric on one GPU: device-resident DoFs/s, kernel-alone and whole-step
+    fraction of the measured HBM bandwidth."""
+    from b200mf import DeviceVector
+
+    es = 8 if dtype == "f64" else 4
+    mq, mfq, opq = build_problem(q, nc, dtype, None, caching, formulation, numbering, curved)
+    mfq.set_stream(stream_ptr)
+    nq = 3 * mq.n_nodes
+    sh = np.random.default_rng(q).uniform(-1, 1, nq)
+    sh[mq.constrained_dofs(3)] = 0.0
+    s, d = DeviceVector(mfq, sh), DeviceVector(mfq)
+    for _ in range(3):
+        opq.vmult(d, s)
+    torch.cuda.synchronize()
+    ms, kms, _, _ = timed_vmults(torch, opq, mfq, s, d, steps, torch.cuda.current_stream(), torch.cuda.synchronize)
+    alg, frac_k, frac_s = roofline_of(q, es, variant, mq.n_cells, kms, ms, peak)
+    out = {"dofs": nq, "cells_per_dir": nc, "ms_per_step": ms, "kernel_ms": kms, "dofs_per_s": nq / (ms * 1e-3),
+           "GB/s_kernel": alg / (kms * 1e-3) / 1e9, "frac_kernel": frac_k, "frac_step": frac_s,
+           "bytes_per_dof": algorithmic_bytes_per_cell(q, es, variant) / (3 * q**3)}
+    del s, d, opq, mfq, mq
+    return out
+
+
+def parity_block(torch, dist, comm, world, rank, p):
+    """Checker, not product: the (distributed) vmult on a reduced mesh of the same brick grid against the C oracle
+    (oracle/mf_oracle.c) applied to the undivided global mesh, relative l2 over all owned rows + two global checksums."""
+    from b200mf import DeviceVector, MatrixFree, NeoHookOperator
+    from b200mf.mesh import StructuredMesh, synthetic_displacement
+    from b200mf.partition import BrickPartition, weak_scaling_grid
+
+    grid = weak_scaling_grid(world)
+    nc = 5 if p <= 3 else 3
+    if world > 1:
+        pt = BrickPartition(grid, nc, p, rank)
+        pt.clamp_global_face(0, 0)
+        mf = MatrixFree.from_partition(pt, comm)
+        glob = pt.global_lex_node()
+        n_owned, n_loc = pt.n_owned, pt.n_dofs
+        coords = pt.node_coordinates()
+    else:
+        pt = StructuredMesh((nc,) * 3, p)
+        pt.clamp([(0, 0)], 3)
+        mf = MatrixFree.from_mesh(pt, 3)
+        glob = np.arange(pt.n_nodes)
+        n_owned = n_loc = 3 * pt.n_nodes
+        coords = pt.node_coordinates()
+    gdof = (3 * glob[:, None] + np.arange(3)[None, :]).reshape(-1)
+    n_glob_nodes = int(np.prod([g * nc * p + 1 for g in grid]))
+    gsrc = np.random.default_rng(7).uniform(-1, 1, 3 * n_glob_nodes)  # the same global vector on every rank
+    op = NeoHookOperator()
+    op.set_material(mf, dict(MAT))
+    op.initialize(DeviceVector(mf, synthetic_displacement(coords, 0.05)), "tensor2")
+    op.cache()
+    v = np.zeros(n_loc)
+    v[:n_owned] = gsrc[gdof[:n_owned]]
+    con = pt.constrained_dofs() if world > 1 else pt.constrained_dofs(3)
+    s, d = DeviceVector(mf, v), DeviceVector(mf)
+    op.vmult(d, s)
+    out = d.download()[:n_owned]
+    box = [None] * world
+    if dist is not None:
+        dist.all_gather_object(box, (gdof[:n_owned], out))
+    else:
+        box = [(gdof[:n_owned], out)]
+    if rank != 0:
+        return None
+    from oracle import c_oracle as CO
+
+    m = StructuredMesh(tuple(g * nc for g in grid), p, lower=(0, 0, 0), upper=grid)
+    m.clamp([(0, 0)], 3)
+    invjac, jxw = CO.q1_metric(m.vertices, p + 1)
+    mat = {k: v_ for k, v_ in MAT.items() if k != "formulation"}
+    ref_op = CO.NeoHookOperator(CO.Cells(p, p + 1, 3, m.dof_index(3), m.constrained_dofs(3), invjac, jxw), formulation=1, **mat)
+    ref_op.initialize(synthetic_displacement(m.node_coordinates(), 0.05), "tensor2")
+    ref_op.cache()
+    ref = np.zeros_like(gsrc)
+    ref_op.vmult(ref, gsrc)
+    got = np.full_like(gsrc, np.nan)
+    for idx, val in box:
+        got[idx] = val
+    assert not np.isnan(got).any(), "the owned rows of all ranks do not cover the global vector"
+    return {"rel_l2": float(np.linalg.norm(got - ref) / np.linalg.norm(ref)), "norm_dst": float(np.linalg.norm(got)),
+            "norm_dst_oracle": float(np.linalg.norm(ref)), "dst_dot_src": float(got @ gsrc), "dst_dot_src_oracle": float(ref @ gsrc),
+            "mesh": f"Q{p}, {grid[0]}x{grid[1]}x{grid[2]} bricks of {nc}^3 cells, {gsrc.size} DoFs, tensor2",
+            "checker": "oracle/mf_oracle.c on the undivided global mesh (test infrastructure; not on the measured path)"}
+
+
+def newton_block(stream_ptr, degree=3, coarse=5, levels=5, amplitude=0.01):
+    """BASELINE.json metric, second half: Newton-step time = update_matrix_free (cache + diagonals + interpolate_to_mg +
+    Chebyshev eigenvalue estimates on every level) + one GMG-CG solve to 1e-6 * ||rhs|| (mf_elasticity.h:1289-1353,
+    1981-2070), device-resident, wall clock between stream synchronisations."""
+    from b200mf import DeviceVector, lib as L_
+    from b200mf.mesh import StructuredMesh, synthetic_displacement
+    from b200mf.solid import Solid
+
+    meshes = []
+    for l in range(levels):
+        m = StructuredMesh((coarse * 2**l,) * 3, degree)
+        m.clamp([(0, 0)], 3)
+        meshes.append(m)
+    mat = {k: v for k, v in MAT.items() if k not in ("formulation", "alpha_1")}
+    sol = Solid(meshes, delta_t=0.01, **mat)
+    sol.mf.set_stream(stream_ptr)
+    for mf in sol.level_mf:
+        mf.set_stream(stream_ptr)
+    m = meshes[-1]
+    sol.total.upload(synthetic_displacement(m.node_coordinates(), amplitude))
+    b = np.random.default_rng(0).uniform(-1, 1, 3 * m.n_nodes)
+    b[m.constrained_dofs(3)] = 0.0
+    sol.rhs.upload(b)
+    nrm = sol.rhs.l2_norm()
+    sol.update_matrix_free()          # warm-up: allocations, first launches
+    sol.solve_linear_system(nrm)
+    sol.mf.synchronize()
+    launches0 = L_.load().b200mf_launch_count()
+    t0 = time.perf_counter()
+    sol.update_matrix_free()
+    sol.mf.synchronize()
+    t1 = time.perf_counter()
+    its = sol.solve_linear_system(nrm)
+    sol.mf.synchronize()
+    t2 = time.perf_counter()
+    return {"workload": f"neo-Hookean Newton step (update_matrix_free + GMG-CG to 1e-6), tensor2, Q{degree}, box {m.ncells[0]}^3 cells, "
+                        f"{3 * m.n_nodes} DoFs, {levels} levels (FP32 levels under FP64 CG)",
+            "n_dofs": 3 * m.n_nodes, "newton_step_s": t2 - t0, "update_matrix_free_s": t1 - t0, "cg_solve_s": t2 - t1,
+            "cg_iterations": int(its), "gpu_launches": int(L_.load().b200mf_launch_count() - launches0),
+            "level0": sol.eig[0], "level_top": sol.eig[-1]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -226,7 +402,8 @@ def main():
     ap.add_argument("--cpu-cells", type=int, default=None, help="cells per direction of the CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--sweep", action="store_true", help="also report Q1..Q6 device-resident rates")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sweep / numbering / newton_step / parity blocks (tuning runs)")
+    ap.add_argument("--sweep", action="store_true", help="report Q1..Q6 in the sweep block (default: Q2, Q3, Q4 = the metric)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--caching", default="tensor2", choices=["scalar_referential", "tensor2", "tensor4", "tensor4_ns"])
     ap.add_argument("--formulation", type=int, default=1, choices=[0, 1])
@@ -280,23 +457,10 @@ def main():
         op.vmult(dst, src)
     barrier()
     launches0 = L.b200mf_launch_count()
-    mf.time_kernels(True)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     with ClockSampler(local_rank) as clocks:
-        # an untimed ~2 ms spin kernel in front of the first event lets the host run ahead, so that the timed region
-        # measures K steps of device work and not the host latency of enqueueing the first one after the barrier
-        torch.cuda._sleep(4_000_000)
-        ev[0].record(stream)
-        for i in range(args.steps):
-            op.vmult(dst, src)
-            ev[i + 1].record(stream)
-        barrier()
+        ms_rank, kernel_ms, kernel_launches, step_ms = timed_vmults(torch, op, mf, src, dst, args.steps, stream, barrier)
     launches = L.b200mf_launch_count() - launches0
-    kernel_ms_total, kernel_launches = mf.kernel_time()
-    mf.time_kernels(False)
-    kernel_ms = kernel_ms_total / args.steps  # all cell-loop launches of one step (1 on one rank; interior/boundary/interior when partitioned)
-    total_ms = ev[0].elapsed_time(ev[-1])
-    step_ms = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps))  # this rank's per-step times (diagnostic)
+    total_ms = ms_rank * args.steps
     if dist is not None:
         t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -316,18 +480,30 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    alg_bytes = algorithmic_bytes_per_cell(p, es, variant) * m.n_cells  # per GPU (per launch of the cell kernel)
-    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    alg_bytes, frac_kernel, frac_step = roofline_of(p, es, variant, m.n_cells, kernel_ms, ms, peak)
+    traffic, traffic_src = ncu_traffic(p, variant, args.dtype, args.cells is None)
     roofline = {"bound": "hbm", "kernel": f"cell_loop_kernel<{'double' if es == 8 else 'float'}, {p + 1}, NHOp<{variant}>>",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": NCU_TRAFFIC.get((p, variant, args.dtype)) if args.cells is None else None,
+                "achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": frac_kernel,
+                "traffic": traffic, "traffic_source": (f"ncu --set full capture committed as {traffic_src} (dram__bytes_read.sum + "
+                                                       "dram__bytes_write.sum of one launch of this workload; not measured in this run)") if traffic_src else None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "algorithmic_bytes_per_dof": algorithmic_bytes_per_cell(p, es, variant) / (3 * p**3),
-                "kernel_ms": kernel_ms, "kernel_launches_timed": int(kernel_launches), "kernel_share_of_step": kernel_ms / ms,
-                "frac_whole_step": alg_bytes / (ms * 1e-3) / 1e9 / peak,
+                "kernel_ms": kernel_ms, "kernel_launches_timed": int(kernel_launches), "kernel_share_of_step": kernel_ms / ms_rank,
+                "frac_whole_step": frac_step,
                 "timed": "cell-loop kernel alone, CUDA events on its stream inside the timed region "
                          f"({kernel_launches // max(args.steps, 1)} launch(es) per step)"}
+
+    # ---- run-to-run reproducibility at bench size: the scatter is an atomic add (red.global.add.f64), so the summation
+    # order differs between launches; report the spread of two applications to the same vector
+    dst2 = DeviceVector(mf)
+    op.vmult(dst, src)
+    op.vmult(dst2, src)
+    a, b = dst.download()[:n_owned], dst2.download()[:n_owned]
+    run_to_run = {"max_abs_diff_over_max_abs": float(np.abs(a - b).max() / max(np.abs(a).max(), 1e-300)),
+                  "rel_l2_diff": float(np.linalg.norm(a - b) / max(np.linalg.norm(a), 1e-300)),
+                  "note": "two vmults of the same vector; differences come from the order of the atomic scatter-adds"}
+    del dst2, a, b
 
     # ---- N > 1: how much of the two ghost exchanges is exposed -----------
     exchange = None
@@ -377,28 +553,36 @@ def main():
             el = float(t.item())
         e2e = {"value": dofs_total * k / el, "unit": "DoFs/s", "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 8,
                "steps": k, "ms_per_step": 1e3 * el / k}
+        del hs, hd
 
-    sweep = None
-    if args.sweep and rank == 0:
+    # ---- parity of this very configuration (rank grid, exchange, kernel) on a reduced mesh against the C oracle
+    parity = None
+    if not args.no_extras and args.dtype == "f64":
+        parity = parity_block(torch, dist, comm, world, rank, p)
+
+    # ---- the other points of BASELINE.json's metric: Q2..Q4 (Q1..Q6 with --sweep), numbering / geometry flavours,
+    # Newton-step time.  One GPU (rank 0 keeps its device; the other ranks wait at the final barrier).
+    sweep = numbering = newton = None
+    if not args.no_extras and world == 1:
+        del src, dst, op, mf, m
+        sp = stream.cuda_stream
         sweep = {}
-        del src, dst, op, mf
-        for q in range(1, 7):
-            mq, mfq, opq = build_problem(q, CELLS_PER_DIR[q], args.dtype, None, args.caching, args.formulation)
-            nq = 3 * mq.n_nodes
-            s, d = DeviceVector(mfq, np.random.default_rng(q).uniform(-1, 1, nq)), DeviceVector(mfq)
-            for _ in range(3):
-                opq.vmult(d, s)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(10):
-                opq.vmult(d, s)
-            e1.record()
-            torch.cuda.synchronize()
-            msq = e0.elapsed_time(e1) / 10
-            gb = algorithmic_bytes_per_cell(q, es, variant) * mq.n_cells / (msq * 1e-3) / 1e9
-            sweep[f"Q{q}"] = {"dofs": nq, "ms": msq, "dofs_per_s": nq / (msq * 1e-3), "GB/s": gb, "frac": gb / peak}
-            del s, d, opq, mfq
+        for q in (range(1, 7) if args.sweep else (2, 3, 4)):
+            if q == p and args.cells is None:
+                sweep[f"Q{q}"] = {"dofs": n, "cells_per_dir": nc, "ms_per_step": ms, "kernel_ms": kernel_ms, "dofs_per_s": value,
+                                  "GB/s_kernel": roofline["achieved"], "frac_kernel": frac_kernel, "frac_step": frac_step,
+                                  "bytes_per_dof": roofline["algorithmic_bytes_per_dof"]}
+            else:
+                sweep[f"Q{q}"] = degree_line(torch, q, CELLS_PER_DIR[q], args.dtype, args.caching, args.formulation, variant, peak, sp)
+        numbering = {"lexicographic_box": sweep.get(f"Q{p}"),
+                     "cellwise_morton_box": degree_line(torch, p, nc, args.dtype, args.caching, args.formulation, variant, peak, sp,
+                                                        numbering="cellwise_morton"),
+                     "curved_cells_lexicographic": degree_line(torch, p, nc, args.dtype, args.caching, args.formulation, variant, peak, sp,
+                                                               curved=True),
+                     "note": "same Q%d workload; cellwise_morton = cells in z-curve order, nodes numbered cell by cell in first-touch "
+                             "order (deal.II-like, mf_elasticity.h:416-425, 667-669); curved = smooth non-affine vertex mapping" % p}
+        if args.dtype == "f64" and args.caching == "tensor2":
+            newton = newton_block(sp)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -413,13 +597,21 @@ def main():
             "data": "synthetic", "config": workload_config(p, nc, world, args.caching, args.formulation), "roofline": roofline, "cpu_baseline": cpu,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(),
             "step_ms_rank0": {"min": step_ms[0], "median": step_ms[len(step_ms) // 2], "max": step_ms[-1]},
+            "run_to_run": run_to_run,
         }
+        if parity:
+            line["parity"] = parity
         if exchange:
             line["ghost_exchange"] = exchange
         if sweep:
             line["sweep"] = sweep
+        if numbering:
+            line["numbering"] = numbering
+        if newton:
+            line["newton_step"] = newton
         print(json.dumps(line), flush=True)
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
 
 

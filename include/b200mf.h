@@ -240,6 +240,32 @@ int b200mf_laplace_assemble_rhs(b200mf_laplace *op, void *rhs_dvec, const void *
 int b200mf_laplace_diagonal(b200mf_laplace *op, const void **diag_dvec, const void **inv_diag_dvec);
 int b200mf_laplace_diagonal_host(b200mf_laplace *op, double *diag_host, double *inv_diag_host);
 
+/* ------------------------------------------------------------------------
+ * Interface faces of Solid::assemble_residual (include/solid_mechanics/mf_elasticity.h:1849-1897): the traction read
+ * from preCICE at the face quadrature points is pulled back (t_0 = |det F F^-T N| t) and integrated against the test
+ * functions.  A face set is built once from the boundary faces with id == interface_id (cases/case_base.h:25):
+ *   cells[f]          the caller's cell index of face f (cell order of b200mf_ctx_create)
+ *   face_no[f]        2*direction + side (deal.II's GeometryInfo face numbering)
+ *   cell_vertices     [n_faces][8][3] vertices of those cells (Q1 geometry of the reference configuration, vertex m at
+ *                     (m&1, m>>1&1, m>>2&1)), as b200mf_ctx_desc::vertices
+ * Quadrature points of a face normal to direction d are ordered q = q_t1 + nq*q_t2 with the tangential directions
+ * t1 < t2 (deal.II orders the y-faces (z, x): the shim permutes the preCICE data once per window).
+ * ------------------------------------------------------------------------ */
+typedef struct b200mf_face_set b200mf_face_set;
+int b200mf_face_set_create(b200mf_face_set **fs, b200mf_ctx *ctx, int64_t n_faces, const int64_t *cells, const int32_t *face_no,
+                           const double *cell_vertices);
+int b200mf_face_set_destroy(b200mf_face_set *fs);
+int64_t b200mf_face_set_n_q_points(const b200mf_face_set *fs); /* n_faces * nq^2 */
+/* [n_faces][nq^2][3] positions in the reference configuration: the interface mesh of Adapter::initialize
+ * (include/adapter/adapter.h: the read data lives on the face quadrature points) */
+int b200mf_face_set_quadrature_points(b200mf_face_set *fs, double *xyz_host);
+/* once per coupling window: traction_q [n_faces][nq^2][3] (precice_adapter->read_on_quadrature_point, :1876-1879) or,
+ * traction_q == NULL, one constant vector traction_const[3] */
+int b200mf_face_set_set_traction(b200mf_face_set *fs, const double *traction_q, const double *traction_const);
+/* every Newton iteration: rhs += face integrals (no compress(add), no set_zero - the caller does both after cells + faces,
+ * :1899-1905, with b200mf_vec_compress_add and b200mf_vec_set_zero_constrained) */
+int b200mf_face_set_assemble_traction(b200mf_face_set *fs, void *rhs_dvec, const void *total_displacement_dvec);
+
 b200mf_ctx *b200mf_nh_ctx(b200mf_nh *op);           /* the MatrixFree the operator was built on (data_in_use, :213) */
 b200mf_ctx *b200mf_laplace_ctx(b200mf_laplace *op); /* MatrixFreeOperators::Base::get_matrix_free */
 

@@ -129,6 +129,12 @@ SIGNATURES = {
     "b200mf_laplace_compute_diagonal": (_i32, [_vp]),
     "b200mf_laplace_diagonal": (_i32, [_vp, _PP, _PP]),
     "b200mf_laplace_diagonal_host": (_i32, [_vp, _vp, _vp]),
+    "b200mf_face_set_create": (_i32, [_PP, _vp, _i64, _vp, _vp, _vp]),
+    "b200mf_face_set_destroy": (_i32, [_vp]),
+    "b200mf_face_set_n_q_points": (_i64, [_vp]),
+    "b200mf_face_set_quadrature_points": (_i32, [_vp, _vp]),
+    "b200mf_face_set_set_traction": (_i32, [_vp, _vp, _vp]),
+    "b200mf_face_set_assemble_traction": (_i32, [_vp, _vp, _vp]),
     "b200mf_nh_ctx": (_vp, [_vp]),
     "b200mf_laplace_ctx": (_vp, [_vp]),
     "b200mf_vec_dot": (_i32, [_vp, _vp, _vp, C.POINTER(_dbl)]),

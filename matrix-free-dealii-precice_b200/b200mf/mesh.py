@@ -96,6 +96,37 @@ class StructuredMesh:
         self.constrained_nodes = None  # [n_nodes, ncomp] bool, set by clamp()
 
     # ------------------------------------------------------------------
+    def renumber_cellwise_morton(self):
+        """deal.II-like enumeration instead of the lexicographic tensor grid: cells in Morton (z-curve) order - the order
+        p4est / parallel::distributed::Triangulation walks them (mf_elasticity.h:416-425) - and nodes numbered cell by
+        cell in the order they are first touched (DoFHandler::distribute_dofs before Cuthill-McKee, :667-669).  Benchmarks
+        use it to show that the gather does not live off the lexicographic numbering.  Single-level meshes only
+        (children_of assumes lexicographic cells)."""
+        assert self.perm is None and self.dim == 3
+        key = np.zeros(self.n_cells, dtype=np.int64)
+        ijk = self.cell_ijk.astype(np.int64)
+        for b in range(21):
+            for d in range(3):
+                key |= ((ijk[:, d] >> b) & 1) << (3 * b + d)
+        order = np.argsort(key, kind="stable")
+        self.cell_ijk = self.cell_ijk[order]
+        self.vertices = self.vertices[order]
+        self.material_id = self.material_id[order]
+        nodes = self.cell_nodes[order]
+        flat = nodes.ravel()
+        _, first = np.unique(flat, return_index=True)  # first touch of every lexicographic node
+        touch_order = np.argsort(first, kind="stable")   # lexicographic node ids sorted by first touch
+        uniq = np.unique(flat)
+        perm = np.empty(self.n_nodes, dtype=np.int64)
+        perm[uniq[touch_order]] = np.arange(uniq.size)
+        self.perm = perm
+        self.cell_nodes = perm[nodes]
+        if self.constrained_nodes is not None:
+            out = np.empty_like(self.constrained_nodes)
+            out[perm] = self.constrained_nodes
+            self.constrained_nodes = out
+        return self
+
     def node_grid_index(self):
         """[n_nodes, dim] integer grid coordinates of every node (in the
         mesh's own numbering)."""

@@ -434,3 +434,57 @@ class LaplaceOperator:
         if getattr(self, "h", None):
             _l.load().b200mf_laplace_destroy(self.h)
             self.h = None
+
+
+class InterfaceTraction:
+    """Interface-face loop of Solid::assemble_residual (mf_elasticity.h:1849-1897) on a set of boundary faces.
+    faces: iterable of (direction, side) of a StructuredMesh (every cell face on that side of the box), or an explicit
+    list of (cell, face_no) pairs with face_no = 2*direction + side."""
+
+    def __init__(self, mf: MatrixFree, mesh, faces, explicit=None):
+        self.mf = mf
+        if explicit is None:
+            cells, fno = [], []
+            for d, side in faces:
+                on = np.flatnonzero(mesh.cell_ijk[:, d] == (0 if side == 0 else mesh.ncells[d] - 1))
+                cells.append(on)
+                fno.append(np.full(on.size, 2 * d + side))
+            cells = np.concatenate(cells) if cells else np.zeros(0, np.int64)
+            fno = np.concatenate(fno) if fno else np.zeros(0, np.int32)
+        else:
+            cells, fno = np.asarray(explicit[0]), np.asarray(explicit[1])
+        self.cells = np.ascontiguousarray(cells, dtype=np.int64)
+        self.face_no = np.ascontiguousarray(fno, dtype=np.int32)
+        vtx = np.ascontiguousarray(mesh.vertices[self.cells], dtype=np.float64)
+        h = C.c_void_p()
+        _l.check(_l.load().b200mf_face_set_create(C.byref(h), mf.h, int(self.cells.size), _ptr(self.cells), _ptr(self.face_no), _ptr(vtx)))
+        self.h = h
+        self._traction = None
+
+    def n_q_points(self):
+        return int(_l.load().b200mf_face_set_n_q_points(self.h))
+
+    def quadrature_points(self):
+        out = np.empty((self.n_q_points(), 3))
+        _l.check(_l.load().b200mf_face_set_quadrature_points(self.h, _ptr(out)))
+        return out
+
+    def set_traction(self, traction):
+        """traction: one vector (constant) or [n_faces * nq^2, 3] values at the face quadrature points."""
+        t = np.ascontiguousarray(traction, dtype=np.float64)
+        if t.size == 3:
+            _l.check(_l.load().b200mf_face_set_set_traction(self.h, None, _ptr(t)))
+        else:
+            assert t.size == 3 * self.n_q_points()
+            _l.check(_l.load().b200mf_face_set_set_traction(self.h, _ptr(t), None))
+        self._traction = t
+
+    def assemble(self, rhs, total_displacement, traction=None):
+        if traction is not None and (self._traction is None or not np.array_equal(np.ravel(traction), np.ravel(self._traction))):
+            self.set_traction(traction)
+        _l.check(_l.load().b200mf_face_set_assemble_traction(self.h, _dv(rhs), _dv(total_displacement)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            _l.load().b200mf_face_set_destroy(self.h)
+            self.h = None

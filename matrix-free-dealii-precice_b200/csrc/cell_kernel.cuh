@@ -131,6 +131,12 @@ __host__ __device__ constexpr int group_threads(int N, int NC) { return (group_c
 #ifndef B200MF_VAL_REGS
 #define B200MF_VAL_REGS 0
 #endif
+// the DoF gather of the next group: cp.async into a shared-memory buffer (no registers held across the integration half;
+// with a register cap the compiler used to spill the prefetched values right after the loads, i.e. wait for them) or,
+// 0, plain loads into registers
+#ifndef B200MF_ASYNC_GATHER
+#define B200MF_ASYNC_GATHER 1
+#endif
 __host__ __device__ constexpr bool table_sliced(int N, int NC) { return NC == 3 && N >= B200MF_SLICED_MINN; }
 // the z-swept nodal planes (column -> plane hand-off) live in field 0 of the q-point buffer: a plane task reads
 // its own plane completely before it writes it, so no second buffer is needed
@@ -163,6 +169,7 @@ struct Layout {
   static constexpr bool SLICED = table_sliced(N, NC);
   static constexpr bool ALIAS_Z = alias_z(N, NC);
   static constexpr int RING = B200MF_RING;
+  static constexpr bool ASYNC_GATHER = SLICED && B200MF_ASYNC_GATHER;
   using P = SmemPad3<WORDS, NC, N>;
   static constexpr int PL = P::PL;
   static constexpr int ZCOMP = N * PL + P::CCZ, ZCELL = NC * ZCOMP + P::CZ;
@@ -231,6 +238,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
   } while (!ok);
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- asynchronous element gather (cp.async, SASS: LDGSTS): global -> shared memory without a register in between;
+// valid = false writes a zero (constrained DoFs read as 0) -----------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void cp_async_elem(T *smem_dst, const T *gmem_src, bool valid) {
+  const unsigned sz = valid ? (unsigned)sizeof(T) : 0u;
+  if constexpr (sizeof(T) == 8)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(sz) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <typename T>
 struct CellArgs {
@@ -309,7 +329,9 @@ struct KernelSmem {
   static constexpr size_t ST2_BYTES = Ly::SLICED ? 0 : (Op::NF_IN2 ? Ly::table_stride(Op::NF_IN2) * sizeof(T) : 0);
   static constexpr size_t SCR_BYTES = Op::NF_SCRATCH ? Ly::plain_stride(Op::NF_SCRATCH) * sizeof(T) : 0;  // pre-pass -> main pass
   static constexpr size_t MBAR_BYTES = Ly::SLICED ? round_up(8 * Ly::RING, 16) : 16;
-  static constexpr size_t GROUP_BYTES = BUF_BYTES + ST1_BYTES + ST2_BYTES + SCR_BYTES + MBAR_BYTES;
+  // gathered nodal values of the next group [c][k][lane] (evaluation-only and diagonal passes gather synchronously / not at all)
+  static constexpr size_t GATHER_BYTES = (Ly::ASYNC_GATHER && Op::INTEGRATE && !DIAG) ? round_up((size_t)Op::NC * N * Ly::L * sizeof(T), 16) : 0;
+  static constexpr size_t GROUP_BYTES = BUF_BYTES + ST1_BYTES + ST2_BYTES + SCR_BYTES + MBAR_BYTES + GATHER_BYTES;
 };
 
 template <typename T, int N, class Op, int GPB, bool DIAG = false, int MINB = 1, bool DOT = false>
@@ -340,6 +362,8 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
   T *qs2 = reinterpret_cast<T *>(gbase + KS_::BUF_BYTES + KS_::ST1_BYTES);
   T *scr = reinterpret_cast<T *>(gbase + KS_::BUF_BYTES + KS_::ST1_BYTES + KS_::ST2_BYTES);
   uint64_t *mbar = reinterpret_cast<uint64_t *>(gbase + KS_::BUF_BYTES + KS_::ST1_BYTES + KS_::ST2_BYTES + KS_::SCR_BYTES);
+  constexpr bool AG = KS_::GATHER_BYTES != 0;  // next group's nodal values arrive through cp.async
+  T *ubuf = reinterpret_cast<T *>(gbase + KS_::BUF_BYTES + KS_::ST1_BYTES + KS_::ST2_BYTES + KS_::SCR_BYTES + KS_::MBAR_BYTES);
 
   if (lane == 0) {
 #pragma unroll
@@ -408,7 +432,7 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
     if constexpr (SLICED) {
       if (staged) {
         group_sync<WM>();  // every column thread is done with the slot
-        fence_proxy_async();
+        if (lane == 0) fence_proxy_async();
         ring_issue();
         if (++cslot == RING) {
           cslot = 0;
@@ -432,6 +456,20 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
         w[c][k] = skip ? T(0) : __ldg(base + (size_t)c * A.cstride);
       }
     }
+  };
+  // the same gather, asynchronously into ubuf[c][k][lane]: every thread later reads back only what it requested itself
+  // (after cp.async.wait_group), so no barrier is involved
+  auto gather_async = [&](const uint32_t(&id)[N]) {
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const T *base = A.src + (id[k] & NODE_MASK);
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+          cp_async_elem(ubuf + (c * N + k) * L + lane, base + (size_t)c * A.cstride, Op::PLAIN || (id[k] & node_flag(c)) == 0u);
+      }
+    }
+    cp_async_commit();
   };
 
   // column-thread offsets into the plane buffers
@@ -466,7 +504,10 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
       stage(group);
     }
     load_nid(group, nid);
-    if (!DIAG) gather(nid, u);
+    if constexpr (AG)
+      gather_async(nid);
+    else if (!DIAG)
+      gather(nid, u);
   }
 
   double dot_acc = 0.0;  // DOT: the fused p . Ap of SolverCG (a separate instantiation: the plain vmult pays nothing)
@@ -606,6 +647,11 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
           Op::load_pre(oa, group, lane, active, c, nid, up);
           sweep_S<T, N, false>(up, o);
         } else {
+          if constexpr (AG) {
+            if (c == 0) cp_async_wait_all();
+#pragma unroll
+            for (int k = 0; k < N; ++k) u[c][k] = active ? ubuf[(c * N + k) * L + lane] : T(0);
+          }
           sweep_S<T, N, false>(u[c], o);
         }
 #pragma unroll
@@ -716,14 +762,27 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
 #pragma unroll
               for (int c = 0; c < NC; ++c) {
 #pragma unroll
-                for (int m = 0; m < N; ++m) {
-                  racc[c][m] += crow[m] * oG[c][2];
-                  if (m == kq) racc[c][m] += ov[c];
-                }
+                for (int m = 0; m < N; ++m) racc[c][m] += crow[m] * oG[c][2];
+                if constexpr (decltype(STATIC)::value) racc[c][kq] += ov[c];
                 if (active) {
                   bufQ[qidx(c, 1, kq)] = oG[c][0];
                   bufQ[qidx(c, 2, kq)] = oG[c][1];
                 }
+              }
+            }
+          }
+          if constexpr (!decltype(STATIC)::value) {
+            if (Op::INTEGRATE && !pre) {  // racc[c][kq] += ov[c] with a run-time kq: one uniform branch instead of N selects per component
+              switch (kq) {
+#define B2_OV_CASE(M)                                     \
+  case M:                                                 \
+    if constexpr (M < N) {                                \
+      _Pragma("unroll") for (int c = 0; c < NC; ++c) racc[c][M] += ov[c]; \
+    }                                                     \
+    break;
+                B2_OV_CASE(0) B2_OV_CASE(1) B2_OV_CASE(2) B2_OV_CASE(3) B2_OV_CASE(4) B2_OV_CASE(5) B2_OV_CASE(6)
+#undef B2_OV_CASE
+                default: break;
               }
             }
           }
@@ -756,8 +815,12 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
       }
       if (Op::INTEGRATE && !pre) {
         // issue the next group's gather now; it completes under the integration half below
-        T u_next[NC][N];
-        if (!DIAG && has_next) gather(nid_next, u_next);
+        T u_next[AG ? 1 : NC][AG ? 1 : N];
+        if constexpr (AG) {
+          if (has_next) gather_async(nid_next);  // F1 of this group has consumed ubuf (same thread)
+        } else {
+          if (!DIAG && has_next) gather(nid_next, u_next);
+        }
         // ---- B2 (plane tasks): transposed x/y derivative and x, y sweeps ------------------------
 #pragma unroll 1
         for (int t0 = 0; t0 < NT; t0 += Ly::TPG) {
@@ -818,11 +881,13 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
               atomicAdd(A.dst + (size_t)c * A.cstride + (nid[k] & NODE_MASK), o[k]);
           }
         }
-        if (!DIAG && has_next) {
+        if constexpr (!AG) {
+          if (!DIAG && has_next) {
 #pragma unroll
-          for (int c = 0; c < NC; ++c)
+            for (int c = 0; c < NC; ++c)
 #pragma unroll
-            for (int k = 0; k < N; ++k) u[c][k] = u_next[c][k];
+              for (int k = 0; k < N; ++k) u[c][k] = u_next[c][k];
+          }
         }
         group_sync<WM>();  // bufZ is free for the next pass / group
       }

@@ -6,7 +6,7 @@
 #include "kernels.h"
 
 #ifndef B200MF_MINB5
-#define B200MF_MINB5 6
+#define B200MF_MINB5 5
 #endif
 #ifndef B200MF_MINB6
 #define B200MF_MINB6 2
@@ -100,13 +100,15 @@ static int launch_cell_loop(const b200mf_ctx *ctx, const T *src, T *dst, const t
     // (cell buffers + staged table) bounds the resident warps and small blocks pack an SM best; N = 2 has 8 cells
     // per warp and so little shared memory that the 32-blocks-per-SM limit binds first -> 4-warp blocks
     constexpr int GPB = (N == 2 ? 4 : N == 3 ? 2 : (N == 4 && sizeof(T) == 4) ? 2 : 1);
+    constexpr bool VEC_VMULT = Op::NC == 3 && Op::INTEGRATE && !Op::PLAIN && !DIAG;
+    constexpr int MINBW = (VEC_VMULT && N == 5 && GPB == 1) ? B200MF_MINB5 : 1;  // tuning builds with one N = 5 cell per warp
 #ifdef B200MF_GPB_SWEEP  // tuning builds only: B200MF_GPB=1|2|4 picks the block size at run time
     static const int gpb_env = getenv("B200MF_GPB") ? atoi(getenv("B200MF_GPB")) : 0;
     if (gpb_env == 1) return launch_variant<T, N, Op, DIAG, 1, 1>(ctx, src, dst, oa, g0, g1, stream, dot);
     if (gpb_env == 2) return launch_variant<T, N, Op, DIAG, 2, 1>(ctx, src, dst, oa, g0, g1, stream, dot);
     if (gpb_env == 4) return launch_variant<T, N, Op, DIAG, 4, 1>(ctx, src, dst, oa, g0, g1, stream, dot);
 #endif
-    return launch_variant<T, N, Op, DIAG, GPB, 1>(ctx, src, dst, oa, g0, g1, stream, dot);
+    return launch_variant<T, N, Op, DIAG, GPB, MINBW>(ctx, src, dst, oa, g0, g1, stream, dot);
   }
 }
 

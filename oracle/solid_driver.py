@@ -72,6 +72,59 @@ def interface_traction_rhs(mesh, total_displacement, traction, faces):
     return rhs
 
 
+def interface_traction_rhs_q1(mesh, total_displacement, traction_q, cells, face_no):
+    """The same face loop (:1849-1897) for general Q1 cells (mapped boxes, the tube) and a traction given per face
+    quadrature point: traction_q [n_faces, nq^2, dim] (or one vector).  Face f = (cells[f], face_no[f] = 2*direction + side);
+    quadrature points of a face are ordered q = q_t1 + nq*q_t2 with the tangential directions t1 < t2.  3-D only."""
+    dim, p, n = mesh.dim, mesh.p, mesh.p + 1
+    assert dim == 3
+    xq, wq = NO.gauss(n)
+    Vq, Dq = lagrange_table(p, xq)
+    rhs = np.zeros(mesh.n_nodes * dim)
+    u = total_displacement.reshape(mesh.n_nodes, dim)
+    traction_q = np.asarray(traction_q, dtype=float)
+    aidx = mesh.loc_ijk
+    for f, (c, fn) in enumerate(zip(cells, face_no)):
+        d, side = fn // 2, fn % 2
+        t1, t2 = [e for e in range(dim) if e != d]
+        Vs, Ds = lagrange_table(p, [float(side)])
+        verts = mesh.vertices[c]  # [8, 3], vertex m at (m&1, m>>1&1, m>>2&1)
+        uloc = u[mesh.cell_nodes[c]]
+        for q2 in range(n):
+            for q1 in range(n):
+                tabs = {d: (Vs[0], Ds[0]), t1: (Vq[q1], Dq[q1]), t2: (Vq[q2], Dq[q2])}
+                val = np.ones(n**dim)
+                grads = np.ones((dim, n**dim))
+                for e in range(dim):
+                    v1, d1 = tabs[e]
+                    val *= v1[aidx[:, e]]
+                    for g in range(dim):
+                        grads[g] *= (d1 if g == e else v1)[aidx[:, e]]
+                xi = np.zeros(dim)
+                xi[d], xi[t1], xi[t2] = side, xq[q1], xq[q2]
+                J = np.zeros((dim, dim))  # dx_e / dxi_f
+                for m in range(8):
+                    bits = [(m >> e) & 1 for e in range(dim)]
+                    l = [xi[e] if bits[e] else 1 - xi[e] for e in range(dim)]
+                    dl = [1.0 if bits[e] else -1.0 for e in range(dim)]
+                    g = np.array([dl[0] * l[1] * l[2], l[0] * dl[1] * l[2], l[0] * l[1] * dl[2]])
+                    J += np.outer(verts[m], g)
+                Jinv = np.linalg.inv(J)
+                nref = np.zeros(dim)
+                nref[d] = 1.0 if side else -1.0
+                nA = np.linalg.det(J) * Jinv.T @ nref  # Nanson: N dA on the reference configuration
+                dA = np.linalg.norm(nA)
+                N = nA / dA
+                gradu = (grads @ uloc).T @ Jinv  # du_c/dx_e = sum_f dU_c/dxi_f dxi_f/dx_e
+                F = np.eye(dim) + gradu
+                n_star = np.linalg.det(F) * np.linalg.inv(F).T @ N
+                t = traction_q if traction_q.ndim == 1 else traction_q[f, q1 + n * q2]
+                t0 = t * np.linalg.norm(n_star)
+                contrib = np.outer(val, t0) * (wq[q1] * wq[q2] * dA)
+                np.add.at(rhs, (dim * mesh.cell_nodes[c][:, None] + np.arange(dim)[None, :]).ravel(), contrib.ravel())
+    return rhs
+
+
 class SolidOracle:
     def __init__(self, meshes, mu, nu, rho, delta_t, formulation=1, caching="tensor2", body_force=None, traction=None,
                  traction_faces=(), preconditioner="gmg", relaxation=0.65, tol_lin=1e-6, tol_f=1e-9, tol_u=1e-6,
@@ -109,7 +162,7 @@ class SolidOracle:
         if len(meshes) > 1:
             self.transfers = [SO.MGTransfer(meshes[l - 1], meshes[l], self.dim, meshes[l - 1].constrained_dofs(self.dim),
                                             meshes[l].constrained_dofs(self.dim)) for l in range(1, len(meshes))]
-        self.cg_iterations, self.cg_solves, self.newton_iterations = 0, 0, []
+        self.cg_iterations, self.cg_solves, self.newton_iterations, self.cg_history = 0, 0, [], []
 
     def _cells(self, mm):
         nq = mm.p + 1
@@ -220,6 +273,7 @@ class SolidOracle:
             dx, its = self.solve_linear_system(rhs)
             self.cg_iterations += its
             self.cg_solves += 1
+            self.cg_history.append(its)
             err_upd = np.linalg.norm(dx)
             if it == 0:
                 err_upd0 = err_upd

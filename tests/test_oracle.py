@@ -171,3 +171,23 @@ def test_heat_rhs_cells_is_mass_action_plus_source():
     r2 = NO.heat_rhs_cells(cd, 0.1, u, np.full((cd.n_cells, cd.n_q), 2.0), 0.0)
     assert np.array_equal(r, r2)
 
+
+
+def test_interface_traction_general_geometry_matches_box_version():
+    """The Q1-geometry restatement of the interface-face loop (mf_elasticity.h:1849-1897) equals the axis-aligned one
+    that reproduces the reference's Turek-Hron goldens (tests/test_golden_turek.py runs it in 2-D), in 3-D on a box."""
+    from b200mf.mesh import StructuredMesh, synthetic_displacement
+    from oracle.solid_driver import interface_traction_rhs, interface_traction_rhs_q1
+
+    m = StructuredMesh((2, 2, 1), 2, upper=(1.0, 0.5, 0.25))
+    u = synthetic_displacement(m.node_coordinates(), 0.05).ravel()
+    faces = [(1, 1), (0, 0), (2, 1)]
+    t = np.array([0.3, -4.0, 1.5])
+    ref = interface_traction_rhs(m, u, t, faces)
+    cells, fno = [], []
+    for d, side in faces:
+        on = np.flatnonzero(m.cell_ijk[:, d] == (0 if side == 0 else m.ncells[d] - 1))
+        cells += list(on)
+        fno += [2 * d + side] * on.size
+    got = interface_traction_rhs_q1(m, u, t, cells, fno)
+    assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max()

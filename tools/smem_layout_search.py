@@ -29,7 +29,7 @@ def group_cells(N, NC):
     """mirror of group_cells() in csrc/cell_kernel.cuh"""
     if NC == 1:
         return {2: 8, 3: 7, 4: 8, 5: 6, 6: 4}.get(N, 2)
-    return 32 // (N * N) if N * N <= 16 else (2 if N == 5 else 1)
+    return 32 // (N * N) if N * N <= 16 else {5: 2, 6: 3, 7: 2}[N]
 
 
 def evaluate(N, NC, PL, CZ, CQ, ws, CCZ=0, CCQ=0, FQ=0, which="zq"):
