@@ -59,6 +59,7 @@ class Solid:
         self.n_global = getattr(m, "n_global_dofs", 3 * m.n_nodes)
         V = lambda: DeviceVector(self.mf)  # noqa: E731
         self.total, self.delta, self.newton_update = V(), V(), V()
+        self._cg = None
         self.velocity, self.velocity_old = V(), V()
         self.acceleration, self.acceleration_old = V(), V()
         self.rhs = V()
@@ -133,7 +134,10 @@ class Solid:
     def solve_linear_system(self, rhs_norm):
         x = self.newton_update
         x.set_zero()
-        cg = SolverCG(self.tol_lin * rhs_norm, int(self.n_global * self.max_cg_multiplier))
+        if self._cg is None:  # one solver object (its work vectors live on the device) for all Newton iterations
+            self._cg = SolverCG(0.0, int(self.n_global * self.max_cg_multiplier))
+        cg = self._cg
+        cg.tolerance = self.tol_lin * rhs_norm
         if self.precond == "gmg":
             P = self.mg
         elif self.precond == "jacobi":

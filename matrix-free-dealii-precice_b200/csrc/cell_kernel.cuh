@@ -80,8 +80,8 @@ struct Shape<float, N> {
 // Pads from tools/smem_layout_search.py (64-bit accesses are served per half-warp over 16 8-byte banks).
 template <int WORDS, int NC, int N>
 struct SmemPad3;
-#define B2_PAD3(W, NC_, N_, PL_, CZ_, CCZ_, CQ_, CCQ_, FQ_) \
-  template <> struct SmemPad3<W, NC_, N_> { static constexpr int PL = PL_, CZ = CZ_, CCZ = CCZ_, CQ = CQ_, CCQ = CCQ_, FQ = FQ_; };
+#define B2_PAD3(W, NC_, N_, PL_, CZ_, CCZ_, CQ_, CCQ_, FQ_, ORD_) \
+  template <> struct SmemPad3<W, NC_, N_> { static constexpr int PL = PL_, CZ = CZ_, CCZ = CCZ_, CQ = CQ_, CCQ = CCQ_, FQ = FQ_, ORD = ORD_; };
 #include "smem_pads.inc"
 #undef B2_PAD3
 
@@ -131,11 +131,21 @@ __host__ __device__ constexpr int group_threads(int N, int NC) { return (group_c
 #ifndef B200MF_VAL_REGS
 #define B200MF_VAL_REGS 0
 #endif
-// the DoF gather of the next group: cp.async into a shared-memory buffer (no registers held across the integration half;
-// with a register cap the compiler used to spill the prefetched values right after the loads, i.e. wait for them) or,
-// 0, plain loads into registers
+// the DoF gather of the next group (sliced kernels; the others prefetch into registers):
+//   0  plain loads into registers one group ahead (30-42 registers held across the integration half: under a register
+//      cap the compiler spills them right after the loads, i.e. waits for them - profiles/r02_*),
+//   1  cp.async into a shared-memory buffer (no registers, + NC*N*L elements of shared memory per group),
+//   2  prefetch.global.L2 of the next group's entries during the integration half, plain (L2-hit) loads at the start
+//      of the group: neither registers nor shared memory
 #ifndef B200MF_ASYNC_GATHER
-#define B200MF_ASYNC_GATHER 1
+#define B200MF_ASYNC_GATHER 2
+#endif
+#ifndef B200MF_PGE
+#define B200MF_PGE 0
+#endif
+// sliced kernels run the quadrature loop rolled (one small loop body, no load hoisting across planes: ~70 registers less)
+#ifndef B200MF_ROLLQ
+#define B200MF_ROLLQ 1
 #endif
 __host__ __device__ constexpr bool table_sliced(int N, int NC) { return NC == 3 && N >= B200MF_SLICED_MINN; }
 // the z-swept nodal planes (column -> plane hand-off) live in field 0 of the q-point buffer: a plane task reads
@@ -169,9 +179,24 @@ struct Layout {
   static constexpr bool SLICED = table_sliced(N, NC);
   static constexpr bool ALIAS_Z = alias_z(N, NC);
   static constexpr int RING = B200MF_RING;
-  static constexpr bool ASYNC_GATHER = SLICED && B200MF_ASYNC_GATHER;
+  static constexpr int GATHER_MODE = SLICED ? B200MF_ASYNC_GATHER : 0;
+  static constexpr bool ASYNC_GATHER = GATHER_MODE == 1;
   using P = SmemPad3<WORDS, NC, N>;
   static constexpr int PL = P::PL;
+  // plane task (cell, component, z-plane) of a lane: the enumeration is part of the bank-conflict-free layout (smem_pads.inc)
+  static constexpr int ORD = P::ORD;
+  static constexpr int PLANE_LANES = ORD == 1 ? CPG * 16 : NT;  // lanes the tasks are spread over (with gaps for ORD 1)
+  static_assert(ORD != 1 || NC * N <= 16, "slot enumeration needs NC*N <= 16");
+  __host__ __device__ static constexpr bool task_valid(int t) { return ORD == 1 ? (t % 16) < NC * N && t / 16 < CPG : t < NT; }
+  __host__ __device__ static constexpr int task_cell(int t) {
+    return ORD == 1 ? t / 16 : ORD == 2 ? (t / NC) % CPG : ORD == 3 ? t % CPG : t / (NC * N);
+  }
+  __host__ __device__ static constexpr int task_comp(int t) {
+    return ORD == 1 ? (t % 16) / N : ORD == 2 ? t % NC : ORD == 3 ? t / (CPG * N) : (t / N) % NC;
+  }
+  __host__ __device__ static constexpr int task_plane(int t) {
+    return ORD == 1 ? (t % 16) % N : ORD == 2 ? t / (NC * CPG) : ORD == 3 ? (t / CPG) % N : t % N;
+  }
   static constexpr int ZCOMP = N * PL + P::CCZ, ZCELL = NC * ZCOMP + P::CZ;
   static constexpr int QFIELD = N * PL + P::FQ, QCOMP = 3 * QFIELD + P::CCQ, QCELL = NC * QCOMP + P::CQ;
   static constexpr int ZSIZE = ALIAS_Z ? 0 : CPG * ZCELL;
@@ -237,6 +262,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
                  : "memory");
   } while (!ok);
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- asynchronous element gather (cp.async, SASS: LDGSTS): global -> shared memory without a register in between;
@@ -249,6 +277,7 @@ __device__ __forceinline__ void cp_async_elem(T *smem_dst, const T *gmem_src, bo
   else
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(sz) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -328,7 +357,7 @@ struct KernelSmem {
   static constexpr size_t ST1_BYTES = Ly::SLICED ? Ly::RING * SLOT_ELEMS * sizeof(T) : (Op::NF_IN ? Ly::table_stride(Op::NF_IN) * sizeof(T) : 0);
   static constexpr size_t ST2_BYTES = Ly::SLICED ? 0 : (Op::NF_IN2 ? Ly::table_stride(Op::NF_IN2) * sizeof(T) : 0);
   static constexpr size_t SCR_BYTES = Op::NF_SCRATCH ? Ly::plain_stride(Op::NF_SCRATCH) * sizeof(T) : 0;  // pre-pass -> main pass
-  static constexpr size_t MBAR_BYTES = Ly::SLICED ? round_up(8 * Ly::RING, 16) : 16;
+  static constexpr size_t MBAR_BYTES = Ly::SLICED ? round_up(8 * 2 * Ly::RING, 16) : 16;  // sliced: "full" and "empty" barrier per slot
   // gathered nodal values of the next group [c][k][lane] (evaluation-only and diagonal passes gather synchronously / not at all)
   static constexpr size_t GATHER_BYTES = (Ly::ASYNC_GATHER && Op::INTEGRATE && !DIAG) ? round_up((size_t)Op::NC * N * Ly::L * sizeof(T), 16) : 0;
   static constexpr size_t GROUP_BYTES = BUF_BYTES + ST1_BYTES + ST2_BYTES + SCR_BYTES + MBAR_BYTES + GATHER_BYTES;
@@ -368,6 +397,10 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
   if (lane == 0) {
 #pragma unroll
     for (int r = 0; r < (SLICED ? RING : 1); ++r) mbar_init(mbar + r, 1);
+    if constexpr (SLICED) {  // "slot r is free again": one arrival per warp of the group
+#pragma unroll
+      for (int r = 0; r < RING; ++r) mbar_init(mbar + RING + r, Ly::TPG / 32);
+    }
   }
   group_sync<WM>();
 
@@ -431,7 +464,13 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
   auto q_release = [&]() {
     if constexpr (SLICED) {
       if (staged) {
-        group_sync<WM>();  // every column thread is done with the slot
+        // every warp reports that it is done with the slot; only the producer lane waits for all of them (no block-wide
+        // barrier in the quadrature loop), then refills the slot
+        __syncwarp();
+        if constexpr (!WM) {
+          if ((lane & 31) == 0) mbar_arrive(mbar + RING + cslot);
+          if (lane == 0) mbar_wait(mbar + RING + cslot, cpar);
+        }
         if (lane == 0) fence_proxy_async();
         ring_issue();
         if (++cslot == RING) {
@@ -471,6 +510,22 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
     }
     cp_async_commit();
   };
+  // ... or only warm the L2 with the entries the next group will gather
+  constexpr bool PG = Ly::GATHER_MODE == 2 && Op::INTEGRATE && !DIAG;
+  // ... and (ops without a pre-pass) run F1 of the next group at the end of the current iteration: the gathered values are
+  // loaded before B1, so that the L2 latency hides behind it, and consumed right after it - no registers are carried
+  // around the loop
+  constexpr bool PGE = PG && !Op::PRE && B200MF_PGE;  // (measured slower on B200 at N = 5: 0.515 vs 0.548 of HBM; off by default)
+  auto gather_prefetch = [&](const uint32_t(&id)[N]) {
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const T *base = A.src + (id[k] & NODE_MASK);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) prefetch_l2(base + (size_t)c * A.cstride);
+      }
+    }
+  };
 
   // column-thread offsets into the plane buffers
   const int zoff = Ly::zplane(cw, 0, 0) + ji;
@@ -506,11 +561,14 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
     load_nid(group, nid);
     if constexpr (AG)
       gather_async(nid);
+    else if (PG)
+      gather_prefetch(nid);
     else if (!DIAG)
       gather(nid, u);
   }
 
   double dot_acc = 0.0;  // DOT: the fused p . Ap of SolverCG (a separate instantiation: the plain vmult pays nothing)
+  bool first_group = true;
   for (; group < A.n_groups; group += gstep) {
     const int64_t gnext = group + gstep;
     const bool has_next = gnext < A.n_groups;
@@ -639,6 +697,8 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
         }
       }
       // ---- F1 (column): z sweep of the nodal column, planes to bufZ ---------------------------
+      // (PGE: done at the end of the previous iteration for every group but the block's first one)
+      if (!(PGE && !first_group))
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         T o[N];
@@ -652,6 +712,9 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
 #pragma unroll
             for (int k = 0; k < N; ++k) u[c][k] = active ? ubuf[(c * N + k) * L + lane] : T(0);
           }
+          if constexpr (PG) {
+            if (c == 0) gather(nid, u);  // L2 hits after the prefetch (PGE: the block's first group only)
+          }
           sweep_S<T, N, false>(u[c], o);
         }
 #pragma unroll
@@ -662,10 +725,10 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
       group_sync<WM>();
       // ---- F2 (plane tasks): x, y sweeps; values, d/dx, d/dy at the q-points of the plane ------
 #pragma unroll 1
-      for (int t0 = 0; t0 < NT; t0 += Ly::TPG) {
+      for (int t0 = 0; t0 < Ly::PLANE_LANES; t0 += Ly::TPG) {
         const int t = t0 + lane;
-        if (t < NT) {
-          const int tcw = t / (NC * N), tc = (t / N) % NC, tk = t % N;
+        if (Ly::task_valid(t)) {
+          const int tcw = Ly::task_cell(t), tc = Ly::task_comp(t), tk = Ly::task_plane(t);
           const T *zp = bufZ + Ly::zplane(tcw, tc, tk);
           T a[N][N];  // a[j][i]
 #pragma unroll
@@ -714,7 +777,7 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
       {
         // the values of the column (for d/dz): registers, or - rolled loop - re-read from shared memory in every plane
         // (N^2 instead of N loads per component, 2 N NC fewer live registers)
-        constexpr bool VAL_REGS = !SLICED || B200MF_VAL_REGS;
+        constexpr bool VAL_REGS = !(SLICED && B200MF_ROLLQ) || B200MF_VAL_REGS;
         T val[NC][N];
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
@@ -788,7 +851,7 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
           }
           q_release();
         };
-        if constexpr (SLICED) {
+        if constexpr (SLICED && B200MF_ROLLQ) {
 #pragma unroll 1
           for (int kq = 0; kq < N; ++kq) plane(kq, std::false_type{});
         } else {
@@ -815,18 +878,20 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
       }
       if (Op::INTEGRATE && !pre) {
         // issue the next group's gather now; it completes under the integration half below
-        T u_next[AG ? 1 : NC][AG ? 1 : N];
+        T u_next[(AG || PG) ? 1 : NC][(AG || PG) ? 1 : N];
         if constexpr (AG) {
           if (has_next) gather_async(nid_next);  // F1 of this group has consumed ubuf (same thread)
+        } else if constexpr (PG) {
+          if (has_next) gather_prefetch(nid_next);
         } else {
           if (!DIAG && has_next) gather(nid_next, u_next);
         }
         // ---- B2 (plane tasks): transposed x/y derivative and x, y sweeps ------------------------
 #pragma unroll 1
-        for (int t0 = 0; t0 < NT; t0 += Ly::TPG) {
+        for (int t0 = 0; t0 < Ly::PLANE_LANES; t0 += Ly::TPG) {
           const int t = t0 + lane;
-          if (t < NT) {
-            const int tcw = t / (NC * N), tc = (t / N) % NC, tk = t % N;
+          if (Ly::task_valid(t)) {
+            const int tcw = Ly::task_cell(t), tc = Ly::task_comp(t), tk = Ly::task_plane(t);
             const T *qv = bufQ + Ly::qplane(tcw, tc, 0, tk), *qx_ = bufQ + Ly::qplane(tcw, tc, 1, tk), *qy_ = bufQ + Ly::qplane(tcw, tc, 2, tk);
             T a[N][N];  // a[qy][qx]
 #pragma unroll
@@ -868,6 +933,12 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
           }
         }
         group_sync<WM>();
+        // prefetch mode: the next group's entries are (about to be) in the L2 since the start of B2; load them now, so
+        // that the L2 latency hides behind B1 and the registers are only held across this light phase
+        T u_pg[PGE ? NC : 1][PGE ? N : 1];
+        if constexpr (PGE) {
+          if (has_next) gather(nid_next, u_pg);
+        }
         // ---- B1 (column): z sweep back + scatter-add -------------------------------------------
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
@@ -881,7 +952,7 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
               atomicAdd(A.dst + (size_t)c * A.cstride + (nid[k] & NODE_MASK), o[k]);
           }
         }
-        if constexpr (!AG) {
+        if constexpr (!AG && !PG) {
           if (!DIAG && has_next) {
 #pragma unroll
             for (int c = 0; c < NC; ++c)
@@ -889,12 +960,27 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
               for (int k = 0; k < N; ++k) u[c][k] = u_next[c][k];
           }
         }
-        group_sync<WM>();  // bufZ is free for the next pass / group
+        if constexpr (PGE) {  // F1 of the next group (own columns of bufZ, just read above by this very thread)
+          if (has_next) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+              T o[N];
+              sweep_S<T, N, false>(u_pg[c], o);
+#pragma unroll
+              for (int kq = 0; kq < N; ++kq)
+                if (active) bufZ[zidx(c, kq)] = o[kq];
+            }
+          }
+        }
+        // the next F1 (next group; a PRE op has no pass after this one) only overwrites the positions of bufZ this very
+        // thread has just read: with the z-swept planes aliased into field 0 no barrier is needed before it
+        if constexpr (!(Ly::ALIAS_Z && !Op::PRE)) group_sync<WM>();  // bufZ is free for the next pass / group
       }
     }  // pass
     if (!Op::INTEGRATE && has_next) gather(nid_next, u);  // evaluation-only ops (cache): plain prefetch
 #pragma unroll
     for (int k = 0; k < N; ++k) nid[k] = nid_next[k];
+    first_group = false;
   }
   if constexpr (DOT) {  // one atomic per warp and launch
 #pragma unroll

@@ -6,7 +6,7 @@
 #include "kernels.h"
 
 #ifndef B200MF_MINB5
-#define B200MF_MINB5 5
+#define B200MF_MINB5 6
 #endif
 #ifndef B200MF_MINB6
 #define B200MF_MINB6 2
