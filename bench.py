@@ -176,15 +176,30 @@ def cpu_oracle_rate(p, ncell_dir, min_seconds=10.0, max_reps=100000):
     n = 3 * m.n_nodes
     src = np.random.default_rng(0).uniform(-1, 1, n)
     dst = np.zeros(n)
-    op.vmult(dst, src)  # warm-up
+    apply = cpu_apply(op, dst, src)  # warm-up inside
     reps, t0 = 0, time.perf_counter()
     while True:
-        op.vmult(dst, src)
+        apply()
         reps += 1
         el = time.perf_counter() - t0
         if el > min_seconds or reps >= max_reps:
             break
     return n * reps / el, n, reps, CO.num_threads(), el / reps
+
+
+def cpu_apply(op, dst, src):
+    """The CPU arm's vmult: SIMD over cells (8 cells per batch, one lane per cell - deal.II's VectorizedArray scheme;
+    AVX-512 / AVX2 picked at run time) when the oracle has a batched form of the level, else the scalar loop."""
+    if op.vmult_simd(dst, src):
+        return lambda: op.vmult_simd(dst, src)
+    op.vmult(dst, src)
+    return lambda: op.vmult(dst, src)
+
+
+def cpu_arm_description():
+    from oracle import c_oracle as CO
+
+    return f"oracle/mf_oracle.c, OpenMP over cell batches, SIMD over cells ({CO.simd_isa()}), {CO.num_threads()} threads"
 
 
 def run_reference(args):
@@ -211,22 +226,29 @@ def run_reference(args):
     n = 3 * m.n_nodes
     src = np.random.default_rng(0).uniform(-1, 1, n)
     dst = np.zeros(n)
+    apply = cpu_apply(op, dst, src)
     for _ in range(args.warmup):
-        op.vmult(dst, src)
+        apply()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        op.vmult(dst, src)
+        apply()
     el = time.perf_counter() - t0
     val = n * args.steps / el
-    sample = f"Q{p} box {nc}^3 cells = {n} DoFs per step (bounded sample of the {CELLS_PER_DIR[p]}^3-cell workload)"
+    sample = (f"Q{p} box {nc}^3 cells = {n} DoFs per step (bounded sample of the {CELLS_PER_DIR[p]}^3-cell workload: the full mesh "
+              f"needs ~16 GB of host tables and minutes of set-up); {cpu_arm_description()}")
+    cfg = workload_config(p, CELLS_PER_DIR[p] if args.cells is None else args.cells, args.gpus)
+    cfg["workload"] += f" [CPU arm measured on a {nc}^3-cell sample of it]"
+    alg_gbs = val * algorithmic_bytes_per_cell(p) / (3 * p**3) / 1e9
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "DoFs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(p, CELLS_PER_DIR[p] if args.cells is None else args.cells, args.gpus),
-        "cpu_baseline": {"value": val, "unit": "DoFs/s", "cores": CO.num_threads(), "kind": "port", "sample": sample},
+        "config": cfg,
+        "cpu_baseline": {"value": val, "unit": "DoFs/s", "cores": CO.num_threads(), "kind": "port", "sample": sample,
+                         "algorithmic_GB/s": alg_gbs},
         "e2e": {"value": val, "unit": "DoFs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference needs deal.II>=9.6 + preCICE>=3 (absent): CPU arm = oracle/mf_oracle.c port, OpenMP over cells",
+        "note": "reference needs deal.II>=9.6 + preCICE>=3 (absent): CPU arm = oracle/mf_oracle.c port, vectorised over cells like "
+                "deal.II's MatrixFree (VectorizedArray), OpenMP over cell batches",
     }
     print(json.dumps(line), flush=True)
 
@@ -249,7 +271,8 @@ def timed_vmults(torch, op, mf, src, dst, steps, stream, barrier):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
     # an untimed ~2 ms spin kernel in front of the first event lets the host run ahead, so that the timed region
     # measures K steps of device work and not the host latency of enqueueing the first one after the barrier
-    torch.cuda._sleep(4_000_000)
+    with torch.cuda.stream(stream):
+        torch.cuda._sleep(4_000_000)
     ev[0].record(stream)
     for i in range(steps):
         op.vmult(dst, src)
@@ -259,6 +282,32 @@ def timed_vmults(torch, op, mf, src, dst, steps, stream, barrier):
     mf.time_kernels(False)
     per_step = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(steps))
     return ev[0].elapsed_time(ev[-1]) / steps, kernel_ms_total / steps, int(kernel_launches), per_step
+
+
+def graphed_vmults(torch, op, src, dst, steps, stream, barrier):
+    """The same `steps` vmults captured once into a CUDA graph and replayed inside the timed region: with several ranks
+    per host the Python/driver enqueue path of a rank is what occasionally starves its GPU (one 3.7 ms step among 1.57 ms
+    ones at 8 ranks in round 1); a graph replay takes the host out of the timed region.  Returns ms per step or None if the
+    capture is not possible."""
+    try:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream, capture_error_mode="thread_local"):
+            for _ in range(steps):
+                op.vmult(dst, src)
+    except Exception as e:  # noqa: BLE001
+        sys.stderr.write(f"[bench] CUDA graph capture failed ({e}); timing the plain loop\n")
+        return None
+    with torch.cuda.stream(stream):
+        g.replay()  # warm-up replay
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        torch.cuda._sleep(4_000_000)
+        e0.record(stream)
+        g.replay()
+        e1.record(stream)
+    barrier()
+    return e0.elapsed_time(e1) / steps
 
 
 def degree_line(torch, q, nc, dtype, caching, formulation, variant, peak, stream_ptr, numbering="lexicographic", curved=False, steps=10):
@@ -402,6 +451,7 @@ def main():
     ap.add_argument("--cpu-cells", type=int, default=None, help="cells per direction of the CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="N > 1: time the plain Python loop instead of a CUDA-graph replay of it")
     ap.add_argument("--no-extras", action="store_true", help="skip the sweep / numbering / newton_step / parity blocks (tuning runs)")
     ap.add_argument("--sweep", action="store_true", help="report Q1..Q6 in the sweep block (default: Q2, Q3, Q4 = the metric)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
@@ -441,7 +491,8 @@ def main():
     src_h = np.random.default_rng(rank).uniform(-1, 1, n)
     src_h[m.constrained_dofs(3) if world == 1 else m.constrained_dofs()] = 0.0
     src, dst = DeviceVector(mf, src_h), DeviceVector(mf)
-    stream = torch.cuda.current_stream()
+    # N > 1 runs on a side stream (the legacy default stream cannot be captured into a CUDA graph)
+    stream = torch.cuda.Stream() if world > 1 else torch.cuda.current_stream()
     mf.set_stream(stream.cuda_stream)
 
     def barrier():
@@ -460,6 +511,16 @@ def main():
     with ClockSampler(local_rank) as clocks:
         ms_rank, kernel_ms, kernel_launches, step_ms = timed_vmults(torch, op, mf, src, dst, args.steps, stream, barrier)
     launches = L.b200mf_launch_count() - launches0
+    graph_ms = None
+    if world > 1 and not args.no_graph:
+        graph_ms = graphed_vmults(torch, op, src, dst, args.steps, stream, barrier)
+        flags = torch.tensor([0.0 if graph_ms is None else 1.0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)  # all ranks or none
+        if float(flags.item()) == 0.0:
+            graph_ms = None
+    loop_ms_rank = ms_rank
+    if graph_ms is not None:
+        ms_rank = graph_ms
     total_ms = ms_rank * args.steps
     if dist is not None:
         t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
@@ -489,11 +550,12 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "algorithmic_bytes_per_dof": algorithmic_bytes_per_cell(p, es, variant) / (3 * p**3),
-                "kernel_ms": kernel_ms, "kernel_launches_timed": int(kernel_launches), "kernel_share_of_step": kernel_ms / ms_rank,
+                "kernel_ms": kernel_ms, "kernel_launches_timed": int(kernel_launches), "kernel_share_of_step": kernel_ms / loop_ms_rank,
                 "frac_whole_step": frac_step,
                 "timed": "cell-loop kernel alone, CUDA events on its stream inside the timed region "
                          f"({kernel_launches // max(args.steps, 1)} launch(es) per step)"}
 
+    mf_p2p = bool(world > 1 and mf.exchange_is_p2p())
     # ---- run-to-run reproducibility at bench size: the scatter is an atomic add (red.global.add.f64), so the summation
     # order differs between launches; report the spread of two applications to the same vector
     dst2 = DeviceVector(mf)
@@ -588,7 +650,8 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         v, ncpu, reps, threads, sec = cpu_oracle_rate(p, args.cpu_cells)
         cpu = {"value": v, "unit": "DoFs/s", "cores": threads, "kind": "port",
-               "sample": f"Q{p} box {args.cpu_cells}^3 cells = {ncpu} DoFs x {reps} vmults ({sec:.2f} s each), oracle/mf_oracle.c"}
+               "sample": f"Q{p} box {args.cpu_cells}^3 cells = {ncpu} DoFs x {reps} vmults ({sec:.2f} s each); {cpu_arm_description()}",
+               "algorithmic_GB/s": v * algorithmic_bytes_per_cell(p) / (3 * p**3) / 1e9}
 
     if rank == 0:
         line = {
@@ -599,6 +662,11 @@ def main():
             "step_ms_rank0": {"min": step_ms[0], "median": step_ms[len(step_ms) // 2], "max": step_ms[-1]},
             "run_to_run": run_to_run,
         }
+        if world > 1:
+            line["timed_region"] = ("CUDA-graph replay of the K vmults (captured once, untimed)" if graph_ms is not None
+                                    else "plain loop of K library calls") + "; step_ms_rank0 / kernel_ms are from the plain loop"
+            line["ms_per_step_plain_loop_rank0"] = loop_ms_rank
+            line["exchange_path"] = "p2p (CUDA IPC push/pull kernels over NVLink)" if mf_p2p else "nccl send/recv"
         if parity:
             line["parity"] = parity
         if exchange:

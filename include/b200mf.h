@@ -151,6 +151,9 @@ typedef struct { /* Utilities::MPI::Partitioner of MatrixFree::get_vector_partit
   const int64_t *ghost_counts;   /* [n_neighbors] */
 } b200mf_partitioner_desc;
 int b200mf_ctx_set_partitioner(b200mf_ctx *ctx, b200mf_comm *comm, const b200mf_partitioner_desc *desc);
+/* 1: the ghost exchanges of this context go peer to peer over NVLink (CUDA IPC exchange blocks, direct stores into the
+ * receiver's slot); 0: ncclSend/ncclRecv (peers not IPC-reachable, or B200MF_P2P=0 in the environment) */
+int b200mf_ctx_exchange_is_p2p(const b200mf_ctx *ctx);
 int b200mf_vec_update_ghost_values(b200mf_ctx *ctx, void *dvec);   /* Vector::update_ghost_values */
 int b200mf_vec_compress_add(b200mf_ctx *ctx, void *dvec);          /* Vector::compress(VectorOperation::add) */
 int b200mf_vec_zero_out_ghost_values(b200mf_ctx *ctx, void *dvec); /* Vector::zero_out_ghost_values */

@@ -92,6 +92,7 @@ SIGNATURES = {
     "b200mf_comm_create": (_i32, [_PP, _i32, _i32, _vp]),
     "b200mf_comm_destroy": (_i32, [_vp]),
     "b200mf_ctx_set_partitioner": (_i32, [_vp, _vp, C.POINTER(PartitionerDesc)]),
+    "b200mf_ctx_exchange_is_p2p": (_i32, [_vp]),
     "b200mf_vec_update_ghost_values": (_i32, [_vp, _vp]),
     "b200mf_vec_compress_add": (_i32, [_vp, _vp]),
     "b200mf_vec_zero_out_ghost_values": (_i32, [_vp, _vp]),

@@ -130,6 +130,10 @@ class MatrixFree:
         _l.check(_l.load().b200mf_ctx_set_partitioner(self.h, comm.h, C.byref(d)))
         self.comm = comm
 
+    def exchange_is_p2p(self):
+        """True: ghost exchanges run peer to peer over NVLink (CUDA IPC); False: ncclSend/ncclRecv."""
+        return bool(_l.load().b200mf_ctx_exchange_is_p2p(self.h))
+
     def set_stream(self, cuda_stream):
         _l.check(_l.load().b200mf_ctx_set_stream(self.h, C.c_void_p(cuda_stream)))
 

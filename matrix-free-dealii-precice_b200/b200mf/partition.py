@@ -140,6 +140,15 @@ class BrickPartition:
         self.vertices = verts
         self.material_id = np.zeros(self.n_cells, dtype=np.uint8)
         self.constrained_nodes = np.zeros((self.n_local_nodes, ncomp), dtype=bool)
+        # the attributes b200mf.mesh.children_of needs (local cells are lexicographic, x fastest, like StructuredMesh)
+        self.ncells = self.nc
+        self.cell_ijk = np.stack(cidx, axis=1)
+        # position in the global (deal.II: rank-contiguous) enumeration: owned DoFs of the lower ranks come first
+        def owned_of(r):
+            ob = brick_of(r, grid)
+            return int(np.prod([nn[k] - (1 if ob[k] > 0 else 0) for k in range(3)])) * ncomp
+        self.first_global_dof = sum(owned_of(r) for r in range(self.rank))
+        self.n_global_dofs = int(np.prod([grid[k] * nc[k] * p + 1 for k in range(3)])) * ncomp
 
     # owned index (in brick ob's local numbering) of grid nodes oi=(ix,iy,iz) of that brick
     def _owned_index_in(self, ob, oi):

@@ -119,12 +119,15 @@ class Solid:
         if not self.smoothers:
             for l, op in enumerate(self.level_ops):
                 n_level = 3 * self.meshes[l].n_nodes if not hasattr(self.meshes[l], "n_global_dofs") else self.meshes[l].n_global_dofs
+                first = getattr(self.meshes[l], "first_global_dof", 0)  # partitioned levels: this rank's offset in the global enumeration
                 if l == 0:  # :1154-1166 (Chebyshev as coarse solver: accurate eigenvalues, m() CG iterations)
                     self.smoothers.append(PreconditionChebyshev(op, degree=INVALID_UNSIGNED_INT, smoothing_range=1e-3,
-                                                                eig_cg_n_iterations=n_level, n_global_dofs=n_level))
+                                                                eig_cg_n_iterations=n_level, n_global_dofs=n_level,
+                                                                first_global_index=first))
                 else:       # :1168-1174
                     self.smoothers.append(PreconditionChebyshev(op, degree=5, smoothing_range=20.0,
-                                                                eig_cg_n_iterations=self.n_cheb_cg, n_global_dofs=n_level))
+                                                                eig_cg_n_iterations=self.n_cheb_cg, n_global_dofs=n_level,
+                                                                first_global_index=first))
             self.eig = [s.estimate_eigenvalues() for s in self.smoothers]
             self.mg = PreconditionMG(self.smoothers, self.transfers, self.mf)
         else:

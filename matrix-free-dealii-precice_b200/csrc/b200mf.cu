@@ -692,6 +692,7 @@ extern "C" int b200mf_ctx_destroy(b200mf_ctx *c) {
   cudaFree(c->constrained);
   cudaFree(c->stage);
   free_partitioner(c);
+  free_hostpipe(c);
   delete c->h_ext2int;
   delete c->h_cell_nodes;
   if (c->kernel_events) {
@@ -1101,12 +1102,207 @@ extern "C" int b200mf_nh_vmult_dot_host(b200mf_nh *op, void *dst, const void *sr
   return fused_dot_result(op->ctx, result_host);
 }
 
+// ---- host-vector vmult as a pipeline -----------------------------------------------------------------------------------
+// The host entry point (the "parity mode" of INTEGRATION.md: caller-owned host vectors) used to run upload -> vmult ->
+// download back to back: 2 x 8 B/DoF over PCIe, fully exposed.  The cell groups only need the source entries of their own
+// cells and finish their destination entries wave by wave, so the three stages overlap:
+//   h2d stream    : src[up_0..up_1)      src[up_1..up_2)      ...
+//   compute stream:       scatter+cells(wave 0)   scatter+cells(wave 1)   ...   (+ gather of the finished dst range)
+//   d2h stream    :                              dst[down_0..down_1)     dst[down_1..down_2) ...
+// up_w   = 1 + largest caller index any group of the waves <= w touches (prefix maximum: a contiguous slice of the host vector)
+// down_w = smallest caller index any group of a later wave touches (suffix minimum): everything below is final after wave w
+// For a locality-preserving numbering both frontiers advance with the waves; for an arbitrary numbering the first slice is
+// (nearly) the whole vector and the schedule degenerates to the serial one - still correct.
+struct b200mf_hostpipe {
+  int W = 0;
+  std::vector<int64_t> g, up, down;  // [W+1]
+  uint32_t *d_ext2int = nullptr;     // caller index -> internal index (0xffffffff: no internal slot)
+  double *stage_out = nullptr;       // finished dst entries in the caller's order
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  std::vector<cudaEvent_t> ev_up, ev_out;
+  cudaEvent_t ev_start = nullptr;
+};
+namespace b200mf {
+void free_hostpipe(b200mf_ctx *c) {
+  b200mf_hostpipe *hp = c->hostpipe;
+  if (!hp) return;
+  cudaFree(hp->d_ext2int);
+  cudaFree(hp->stage_out);
+  if (hp->h2d) cudaStreamDestroy(hp->h2d);
+  if (hp->d2h) cudaStreamDestroy(hp->d2h);
+  for (cudaEvent_t e : hp->ev_up) cudaEventDestroy(e);
+  for (cudaEvent_t e : hp->ev_out) cudaEventDestroy(e);
+  if (hp->ev_start) cudaEventDestroy(hp->ev_start);
+  delete hp;
+  c->hostpipe = nullptr;
+}
+template <typename T>
+__global__ void scatter_ext_range_kernel(int64_t a, int64_t b, const uint32_t *__restrict__ ext2int, const double *__restrict__ ext, T *__restrict__ in) {
+  const int64_t e = a + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < b) {
+    const uint32_t i = ext2int[e];
+    if (i != 0xffffffffu) in[i] = (T)ext[e];
+  }
+}
+template <typename T>
+__global__ void gather_ext_range_kernel(int64_t a, int64_t b, const uint32_t *__restrict__ ext2int, double *__restrict__ ext, const T *__restrict__ in) {
+  const int64_t e = a + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < b) {
+    const uint32_t i = ext2int[e];
+    ext[e] = i != 0xffffffffu ? (double)in[i] : 0.0;
+  }
+}
+// dst[c] += src[c] on the constrained rows whose caller index lies in [a, b) (mf_nh_operator.h:623-624, slice-wise)
+template <typename T>
+__global__ void constrained_identity_range_kernel(int64_t n, const uint32_t *__restrict__ idx, const int64_t *__restrict__ int2ext, int64_t a,
+                                                  int64_t b, T *__restrict__ dst, const T *__restrict__ src) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) {
+    const uint32_t i = idx[k];
+    const int64_t e = int2ext ? int2ext[i] : (int64_t)i;
+    if (e >= a && e < b) dst[i] += src[i];
+  }
+}
+}  // namespace b200mf
+
+static int build_hostpipe(b200mf_ctx *c) {
+  if (c->hostpipe) return 0;
+  std::unique_ptr<b200mf_hostpipe> hp(new b200mf_hostpipe());
+  const int N3 = c->N * c->N * c->N, NC = c->NC;
+  const int64_t ng = c->n_groups, nd = c->n_dofs;
+  hp->W = (int)std::max<int64_t>(1, std::min<int64_t>(16, ng / (4 * (int64_t)c->sm_count)));  // waves of >= 4 groups per SM
+  const int W = hp->W;
+  // caller index of every internal slot
+  std::vector<int64_t> int2ext;
+  if (c->h_ext2int) {
+    int2ext.assign(c->n_int, -1);
+    for (int64_t e = 0; e < nd; ++e)
+      if ((*c->h_ext2int)[e] >= 0) int2ext[(*c->h_ext2int)[e]] = e;
+  }
+  std::vector<int64_t> gmin(ng, nd), gmax(ng, -1);
+  const std::vector<uint32_t> &cn = *c->h_cell_nodes;
+  for (int64_t cell = 0; cell < c->n_cells; ++cell) {
+    const int64_t g = cell / c->cpg;  // no partitioner: library cell order == caller's
+    int64_t lo = gmin[g], hi = gmax[g];
+    for (int a = 0; a < N3; ++a) {
+      const int64_t node = cn[(size_t)cell * N3 + a] & NODE_MASK;
+      for (int cc = 0; cc < NC; ++cc) {
+        const int64_t in = cc * c->cstride + node, e = int2ext.empty() ? in : int2ext[in];
+        if (e < 0) continue;
+        lo = std::min(lo, e);
+        hi = std::max(hi, e);
+      }
+    }
+    gmin[g] = lo;
+    gmax[g] = hi;
+  }
+  hp->g.resize(W + 1);
+  hp->up.assign(W + 1, 0);
+  hp->down.assign(W + 1, 0);
+  for (int w = 0; w <= W; ++w) hp->g[w] = ng * w / W;
+  int64_t run = 0;
+  for (int w = 0; w < W; ++w) {
+    for (int64_t g = hp->g[w]; g < hp->g[w + 1]; ++g) run = std::max(run, gmax[g] + 1);
+    hp->up[w + 1] = run;
+  }
+  hp->up[W] = nd;
+  run = nd;
+  hp->down[W] = nd;
+  for (int w = W - 1; w >= 1; --w) {
+    for (int64_t g = hp->g[w]; g < hp->g[w + 1]; ++g) run = std::min(run, gmin[g]);
+    hp->down[w] = std::min(run, hp->up[w]);  // entries no cell touches wait for their source slice
+  }
+  hp->down[0] = 0;
+  // caller -> internal map on the device
+  std::vector<uint32_t> e2i(std::max<int64_t>(1, nd), 0xffffffffu);
+  for (int64_t e = 0; e < nd; ++e) {
+    const int64_t in = c->h_ext2int ? (*c->h_ext2int)[e] : e;
+    if (in >= 0) e2i[e] = (uint32_t)in;
+  }
+  B2_CUDA(cudaMalloc(&hp->d_ext2int, e2i.size() * sizeof(uint32_t)));
+  B2_CUDA(cudaMemcpy(hp->d_ext2int, e2i.data(), e2i.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  B2_CUDA(cudaMalloc(&hp->stage_out, std::max<int64_t>(1, nd) * sizeof(double)));
+  B2_CUDA(cudaStreamCreateWithFlags(&hp->h2d, cudaStreamNonBlocking));
+  B2_CUDA(cudaStreamCreateWithFlags(&hp->d2h, cudaStreamNonBlocking));
+  hp->ev_up.resize(W);
+  hp->ev_out.resize(W);
+  for (int w = 0; w < W; ++w) {
+    B2_CUDA(cudaEventCreateWithFlags(&hp->ev_up[w], cudaEventDisableTiming));
+    B2_CUDA(cudaEventCreateWithFlags(&hp->ev_out[w], cudaEventDisableTiming));
+  }
+  B2_CUDA(cudaEventCreateWithFlags(&hp->ev_start, cudaEventDisableTiming));
+  c->bytes += e2i.size() * sizeof(uint32_t) + (size_t)nd * sizeof(double);
+  c->hostpipe = hp.release();
+  return 0;
+}
+
+// launch(g0, g1) enqueues the cell loop over the groups [g0, g1) on the context's stream (dst = tmp_dst, src = tmp_src)
+template <typename T, class Launch>
+static int vmult_host_pipelined(b200mf_ctx *c, double *dst, const double *src, T *tmp_dst, T *tmp_src, Launch &&launch) {
+  B2_TRY(build_hostpipe(c));
+  b200mf_hostpipe *hp = c->hostpipe;
+  const int W = hp->W;
+  cudaStream_t cs = c->stream;
+  B2_CUDA(cudaMemsetAsync(tmp_dst, 0, c->n_int * sizeof(T), cs));
+  B2_CUDA(cudaEventRecord(hp->ev_start, cs));  // earlier work on the context's stream may still read the staging buffers
+  B2_CUDA(cudaStreamWaitEvent(hp->h2d, hp->ev_start, 0));
+  double *stage_in = (double *)c->stage;
+  for (int w = 0; w < W; ++w) {
+    const int64_t a = hp->up[w], b = hp->up[w + 1];
+    if (b > a) B2_CUDA(cudaMemcpyAsync(stage_in + a, src + a, (size_t)(b - a) * sizeof(double), cudaMemcpyHostToDevice, hp->h2d));
+    B2_CUDA(cudaEventRecord(hp->ev_up[w], hp->h2d));
+  }
+  for (int w = 0; w < W; ++w) {
+    const int64_t a = hp->up[w], b = hp->up[w + 1];
+    B2_CUDA(cudaStreamWaitEvent(cs, hp->ev_up[w], 0));
+    if (b > a) {
+      scatter_ext_range_kernel<T><<<nblocks(b - a, 256), 256, 0, cs>>>(a, b, hp->d_ext2int, stage_in, tmp_src);
+      B2_LAUNCHED();
+    }
+    B2_TRY(launch(hp->g[w], hp->g[w + 1]));
+    const int64_t da = hp->down[w], db = hp->down[w + 1];
+    if (db > da) {
+      if (c->n_constrained) {
+        constrained_identity_range_kernel<T><<<nblocks(c->n_constrained, 256), 256, 0, cs>>>(c->n_constrained, c->constrained, c->int2ext, da, db, tmp_dst, tmp_src);
+        B2_LAUNCHED();
+      }
+      gather_ext_range_kernel<T><<<nblocks(db - da, 256), 256, 0, cs>>>(da, db, hp->d_ext2int, hp->stage_out, tmp_dst);
+      B2_LAUNCHED();
+    }
+    B2_CUDA(cudaEventRecord(hp->ev_out[w], cs));
+    B2_CUDA(cudaStreamWaitEvent(hp->d2h, hp->ev_out[w], 0));
+    if (db > da) B2_CUDA(cudaMemcpyAsync(dst + da, hp->stage_out + da, (size_t)(db - da) * sizeof(double), cudaMemcpyDeviceToHost, hp->d2h));
+  }
+  B2_CUDA(cudaStreamSynchronize(hp->d2h));
+  B2_CUDA(cudaStreamSynchronize(cs));
+  return 0;
+}
+
+static bool host_pipeline_applies(const b200mf_ctx *c) {
+  static const bool off = getenv("B200MF_HOST_PIPELINE") && atoi(getenv("B200MF_HOST_PIPELINE")) == 0;
+  return !off && !c->part && !c->cell_order && c->n_groups >= 8 * (int64_t)c->sm_count;
+}
+
 extern "C" int b200mf_nh_vmult_host(b200mf_nh *op, double *dst, const double *src) {
   if (!op || !dst || !src) return set_error(B200MF_ERR_ARG, "null argument");
+  if (!op->cached) return set_error(B200MF_ERR_STATE, "vmult before cache()");
   B2_TRY(nh_tmp(op));
-  B2_TRY(b200mf_vec_upload_f64(op->ctx, op->tmp_src, src));
+  b200mf_ctx *c = op->ctx;
+  if (host_pipeline_applies(c)) {
+    if (c->dtype == B200MF_F64) {
+      const NHArgs<double> oa = nh_args<double>(op);
+      return vmult_host_pipelined<double>(c, dst, src, (double *)op->tmp_dst, (double *)op->tmp_src, [&](int64_t g0, int64_t g1) {
+        return run_nh<double>(c, op->variant, (const double *)op->tmp_src, (double *)op->tmp_dst, oa, g0, g1, c->stream, nullptr);
+      });
+    }
+    const NHArgs<float> oa = nh_args<float>(op);
+    return vmult_host_pipelined<float>(c, dst, src, (float *)op->tmp_dst, (float *)op->tmp_src, [&](int64_t g0, int64_t g1) {
+      return run_nh<float>(c, op->variant, (const float *)op->tmp_src, (float *)op->tmp_dst, oa, g0, g1, c->stream, nullptr);
+    });
+  }
+  B2_TRY(b200mf_vec_upload_f64(c, op->tmp_src, src));
   B2_TRY(nh_apply(op, op->tmp_dst, op->tmp_src, true));
-  return b200mf_vec_download_f64(op->ctx, dst, op->tmp_dst);
+  return b200mf_vec_download_f64(c, dst, op->tmp_dst);
 }
 
 // ---- cell part of Solid::assemble_residual (mf_elasticity.h:1764-1846) ------------------

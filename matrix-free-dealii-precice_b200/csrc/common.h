@@ -49,6 +49,7 @@ int kernel_event(b200mf_ctx *c, cudaStream_t s);  // b200mf.cu
 
 // comm.cu
 void free_partitioner(b200mf_ctx *c);
+void free_hostpipe(b200mf_ctx *c);  // b200mf.cu
 int update_ghost_values(b200mf_ctx *c, void *vec, cudaStream_t stream = nullptr);  // nullptr: the context's stream
 int compress_add(b200mf_ctx *c, void *vec, cudaStream_t stream = nullptr);
 int zero_ghosts(b200mf_ctx *c, void *vec);
@@ -88,4 +89,5 @@ struct b200mf_ctx {
   std::vector<int64_t> *h_ext2int;  // caller index -> internal index, nullptr when identity
   std::vector<cudaEvent_t> *kernel_events;  // non-null: event pairs recorded around every cell-loop launch (b200mf_ctx_time_kernels)
   std::vector<uint32_t> *h_cell_nodes;  // [n_cells][N^3] node | constrained flags (bits 29..31), caller's cell order (MG transfer set-up)
+  struct b200mf_hostpipe *hostpipe;     // lazily built schedule of the pipelined host-vector vmult (b200mf_*_vmult_host)
 };

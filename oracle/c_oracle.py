@@ -42,6 +42,11 @@ def lib():
         L.orc_laplace_vmult.argtypes = [vp, dbl, vp, vp, vp]
         L.orc_laplace_compute_diagonal.argtypes = [vp, dbl, vp, vp, vp]
         L.orc_num_threads.restype = i32
+        L.orc_nh_simd_create.restype = vp
+        L.orc_nh_simd_create.argtypes = [vp]
+        L.orc_nh_simd_destroy.argtypes = [vp]
+        L.orc_nh_vmult_simd.argtypes = [vp, vp, vp, vp]
+        L.orc_simd_isa.restype = C.c_char_p
         _LIB = L
     return _LIB
 
@@ -114,6 +119,17 @@ class NeoHookOperator:
 
     Tvmult = vmult
 
+    def vmult_simd(self, dst, src):
+        """Same operator, SIMD over cells (8 cells per batch, as deal.II's VectorizedArray); tensor2 / formulation 1 only.
+        Returns False if the operator has no batched form (other levels)."""
+        if getattr(self, "_simd", None) is None:
+            self._simd = lib().orc_nh_simd_create(self.h)
+        if not self._simd:
+            return False
+        src = np.ascontiguousarray(src, dtype=np.float64)
+        lib().orc_nh_vmult_simd(self.h, self._simd, _p(dst), _p(src))
+        return True
+
     def compute_diagonal(self):
         n = self.cells.n_dofs
         self.diagonal, self.inverse_diagonal = np.zeros(n), np.zeros(n)
@@ -121,9 +137,16 @@ class NeoHookOperator:
         return self.diagonal
 
     def __del__(self):
+        if getattr(self, "_simd", None):
+            lib().orc_nh_simd_destroy(self._simd)
+            self._simd = None
         if getattr(self, "h", None):
             lib().orc_nh_destroy(self.h)
             self.h = None
+
+
+def simd_isa():
+    return lib().orc_simd_isa().decode()
 
 
 class LaplaceOperator:
@@ -136,6 +159,17 @@ class LaplaceOperator:
         lib().orc_laplace_vmult(self.cells.h, self.delta_t, _p(self.coef), _p(dst), _p(src))
 
     Tvmult = vmult
+
+    def vmult_simd(self, dst, src):
+        """Same operator, SIMD over cells (8 cells per batch, as deal.II's VectorizedArray); tensor2 / formulation 1 only.
+        Returns False if the operator has no batched form (other levels)."""
+        if getattr(self, "_simd", None) is None:
+            self._simd = lib().orc_nh_simd_create(self.h)
+        if not self._simd:
+            return False
+        src = np.ascontiguousarray(src, dtype=np.float64)
+        lib().orc_nh_vmult_simd(self.h, self._simd, _p(dst), _p(src))
+        return True
 
     def compute_diagonal(self):
         n = self.cells.n_dofs

@@ -580,6 +580,244 @@ void orc_nh_vmult(const orc_nh *op, double *dst, const double *src)
   for (int64_t i = 0; i < cd->ndofs; ++i) if (cd->constrained[i]) dst[i] += src[i]; /* :623-624 */
 }
 
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * SIMD-over-cells variant of vmult for the benchmark level (tensor2 caching, formulation 1) - the way deal.II's
+ * MatrixFree runs the reference's operator on a CPU: VL cells per batch, one SIMD lane per cell (VectorizedArray<double>),
+ * every per-cell scalar of nh_cell_op becomes a lane array, tables stored [batch][q][field][lane].  Same arithmetic as
+ * orc_nh_vmult (tests/test_oracle.py compares the two); used by bench.py's CPU arms so that the reported baseline is a
+ * vectorised CPU implementation, not a scalar one.  GCC function multi-versioning picks AVX-512 / AVX2 / baseline code
+ * at run time (the library is built on a machine that may differ from the GPU box's host).
+ * Scatter: entries touched by the cells of one thread only are added plainly, the others atomically. */
+#define VL 8
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#define ORC_CLONES __attribute__((target_clones("avx512f", "avx2,fma", "default")))
+#else
+#define ORC_CLONES
+#endif
+
+typedef struct {
+  int64_t nbatch;
+  int nthreads;
+  double *tab;        /* [batch][q][NFB][VL]: K_cur (9), JxW_cur, c1, c2, T (9) */
+  uint8_t *shared;    /* [ndofs] 1: touched by cells of more than one thread */
+} orc_simd;
+enum { NFB = 21 };
+
+static inline void sweep_v(const double *M, int rows, int cols, int transpose, const double *in, double *out, const int *ext, int dir)
+{
+  int nin = ext[dir];
+  int nout = transpose ? cols : rows;
+  int stride = 1;
+  for (int d = 0; d < dir; ++d) stride *= ext[d];
+  int outer = 1;
+  for (int d = dir + 1; d < 3; ++d) outer *= ext[d];
+  for (int o = 0; o < outer; ++o)
+    for (int s = 0; s < stride; ++s) {
+      const double *pi = in + ((size_t)o * nin * stride + s) * VL;
+      double *po = out + ((size_t)o * nout * stride + s) * VL;
+      for (int r = 0; r < nout; ++r) {
+        double acc[VL];
+        for (int l = 0; l < VL; ++l) acc[l] = 0.0;
+        for (int k = 0; k < nin; ++k) {
+          const double mk = transpose ? M[k * cols + r] : M[r * cols + k];
+          const double *x = pi + (size_t)k * stride * VL;
+#pragma omp simd
+          for (int l = 0; l < VL; ++l) acc[l] += mk * x[l];
+        }
+        for (int l = 0; l < VL; ++l) po[(size_t)r * stride * VL + l] = acc[l];
+      }
+    }
+}
+
+ORC_CLONES
+static void nh_batch_tensor2(const orc_nh *op, const double *tab, const double *lam2 /*[VL] 2 lambda*/, const double *rha /*[VL] rho alpha*/,
+                             double (*u)[MAXP3 * VL], double (*r)[MAXP3 * VL], double *work)
+{
+  const orc_cells *cd = op->cd;
+  const int n = cd->n, nq = cd->nq, nq3 = nq * nq * nq;
+  double *val = work, *G = work + 3 * (size_t)MAXP3 * VL, *t1 = G + 9 * (size_t)MAXP3 * VL, *t2 = t1 + (size_t)MAXP3 * VL;
+  int e0[3] = {n, n, n}, e1[3] = {nq, n, n}, e2[3] = {nq, nq, n}, e3[3] = {nq, nq, nq};
+  for (int c = 0; c < 3; ++c) { /* evaluate(values | gradients) :697 */
+    double *v = val + (size_t)c * MAXP3 * VL;
+    sweep_v(cd->S, nq, n, 0, u[c], t1, e0, 0);
+    sweep_v(cd->S, nq, n, 0, t1, t2, e1, 1);
+    sweep_v(cd->S, nq, n, 0, t2, v, e2, 2);
+    for (int f = 0; f < 3; ++f) sweep_v(cd->C, nq, nq, 0, v, G + ((size_t)c * 3 + f) * MAXP3 * VL, e3, f);
+  }
+  for (int q = 0; q < nq3; ++q) { /* :945-974 */
+    const double *t = tab + (size_t)q * NFB * VL;
+    double g[9][VL], sg[9][VL];
+    for (int c = 0; c < 3; ++c)
+      for (int e = 0; e < 3; ++e) {
+#pragma omp simd
+        for (int l = 0; l < VL; ++l) {
+          double s = 0.0;
+          for (int f = 0; f < 3; ++f) s += t[(e * 3 + f) * VL + l] * G[(((size_t)c * 3 + f) * MAXP3 + q) * VL + l];
+          g[c * 3 + e][l] = s;
+        }
+      }
+    const double *jxw = t + 9 * VL, *c1 = t + 10 * VL, *c2 = t + 11 * VL, *T = t + 12 * VL;
+    double tmp[VL];
+#pragma omp simd
+    for (int l = 0; l < VL; ++l) tmp[l] = lam2[l] * c2[l] * (g[0][l] + g[4][l] + g[8][l]);
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+#pragma omp simd
+        for (int l = 0; l < VL; ++l) {
+          double s = 0.0;
+          for (int k = 0; k < 3; ++k) s += g[i * 3 + k][l] * T[(k * 3 + j) * VL + l];
+          sg[i * 3 + j][l] = c1[l] * 0.5 * (g[i * 3 + j][l] + g[j * 3 + i][l]) + (i == j ? tmp[l] : 0.0) + s;
+        }
+      }
+    for (int c = 0; c < 3; ++c) {
+      for (int f = 0; f < 3; ++f) {
+        double *o = G + (((size_t)c * 3 + f) * MAXP3 + q) * VL;
+#pragma omp simd
+        for (int l = 0; l < VL; ++l) {
+          double s = 0.0;
+          for (int e = 0; e < 3; ++e) s += t[(e * 3 + f) * VL + l] * sg[c * 3 + e][l];
+          o[l] = s * jxw[l];
+        }
+      }
+      double *v = val + ((size_t)c * MAXP3 + q) * VL;
+#pragma omp simd
+      for (int l = 0; l < VL; ++l) v[l] = v[l] * rha[l] * c2[l] * jxw[l];
+    }
+  }
+  for (int c = 0; c < 3; ++c) { /* integrate :1018 */
+    double *acc = val + (size_t)c * MAXP3 * VL;
+    for (int f = 0; f < 3; ++f) {
+      sweep_v(cd->C, nq, nq, 1, G + ((size_t)c * 3 + f) * MAXP3 * VL, t1, e3, f);
+      for (int i = 0; i < nq3 * VL; ++i) acc[i] += t1[i];
+    }
+    int x1[3] = {nq, nq, n}, x0[3] = {nq, n, n};
+    sweep_v(cd->S, nq, n, 1, acc, t1, e3, 2);
+    sweep_v(cd->S, nq, n, 1, t1, t2, x1, 1);
+    sweep_v(cd->S, nq, n, 1, t2, r[c], x0, 0);
+  }
+}
+
+/* batched tables + shared-entry flags; call after orc_nh_cache (tensor2, formulation 1, one material) */
+orc_simd *orc_nh_simd_create(const orc_nh *op)
+{
+  const orc_cells *cd = op->cd;
+  if (op->level != LVL_TENSOR2 || op->formulation != 1) return NULL;
+  const int nq3 = cd->nq * cd->nq * cd->nq, n3 = cd->n * cd->n * cd->n;
+  orc_simd *s = (orc_simd *)calloc(1, sizeof(orc_simd));
+  s->nbatch = (cd->ncell + VL - 1) / VL;
+#ifdef _OPENMP
+  s->nthreads = omp_get_max_threads();
+#else
+  s->nthreads = 1;
+#endif
+  s->tab = (double *)calloc((size_t)s->nbatch * nq3 * NFB * VL, sizeof(double));
+#pragma omp parallel for schedule(static)
+  for (int64_t b = 0; b < s->nbatch; ++b)
+    for (int l = 0; l < VL; ++l) {
+      int64_t cell = b * VL + l;
+      if (cell >= cd->ncell) cell = cd->ncell - 1; /* tail lanes repeat the last cell; their result is dropped */
+      for (int q = 0; q < nq3; ++q) {
+        const size_t iq = (size_t)cell * nq3 + q;
+        double *t = s->tab + ((size_t)b * nq3 + q) * NFB * VL + l;
+        for (int i = 0; i < 9; ++i) t[i * VL] = op->invjac_cur[iq * 9 + i];
+        t[9 * VL] = op->jxw_cur[iq];
+        t[10 * VL] = op->cached_scalar[iq];
+        t[11 * VL] = op->cached_second_scalar[iq];
+        for (int i = 0; i < 9; ++i) t[(12 + i) * VL] = op->cached_tensor2[iq * 9 + i];
+      }
+    }
+  /* entries touched by batches of different threads (static schedule: thread = batch / chunk) */
+  s->shared = (uint8_t *)calloc(cd->ndofs, 1);
+  int32_t *first = (int32_t *)malloc(sizeof(int32_t) * cd->ndofs);
+  for (int64_t i = 0; i < cd->ndofs; ++i) first[i] = -1;
+  const int64_t chunk = (s->nbatch + s->nthreads - 1) / s->nthreads;
+  for (int64_t cell = 0; cell < cd->ncell; ++cell) {
+    const int32_t th = (int32_t)((cell / VL) / chunk);
+    const uint32_t *idx = cd->dof_idx + cell * 3 * n3;
+    for (int a = 0; a < 3 * n3; ++a) {
+      if (first[idx[a]] < 0) first[idx[a]] = th;
+      else if (first[idx[a]] != th) s->shared[idx[a]] = 1;
+    }
+  }
+  free(first);
+  return s;
+}
+void orc_nh_simd_destroy(orc_simd *s) { if (s) { free(s->tab); free(s->shared); free(s); } }
+
+void orc_nh_vmult_simd(const orc_nh *op, const orc_simd *s, double *dst, const double *src)
+{
+  const orc_cells *cd = op->cd;
+  const int n3 = cd->n * cd->n * cd->n, nq3 = cd->nq * cd->nq * cd->nq;
+  memset(dst, 0, sizeof(double) * cd->ndofs);
+  const int64_t chunk = (s->nbatch + s->nthreads - 1) / s->nthreads;
+#pragma omp parallel num_threads(s->nthreads)
+  {
+    double (*u)[MAXP3 * VL] = (double (*)[MAXP3 * VL])aligned_alloc(64, sizeof(double) * 3 * MAXP3 * VL);
+    double (*r)[MAXP3 * VL] = (double (*)[MAXP3 * VL])aligned_alloc(64, sizeof(double) * 3 * MAXP3 * VL);
+    double *work = (double *)aligned_alloc(64, sizeof(double) * 14 * MAXP3 * VL);
+#ifdef _OPENMP
+    const int th = omp_get_thread_num();
+#else
+    const int th = 0;
+#endif
+    const int64_t b0 = th * chunk, b1 = (b0 + chunk < s->nbatch) ? b0 + chunk : s->nbatch;
+    for (int64_t b = b0; b < b1; ++b) {
+      for (int l = 0; l < VL; ++l) {
+        int64_t cell = b * VL + l;
+        if (cell >= cd->ncell) cell = cd->ncell - 1;
+        const uint32_t *idx = cd->dof_idx + cell * 3 * n3;
+        for (int c = 0; c < 3; ++c)
+          for (int a = 0; a < n3; ++a) {
+            const uint32_t d = idx[c * n3 + a];
+            u[c][(size_t)a * VL + l] = cd->constrained[d] ? 0.0 : src[d];
+          }
+      }
+      double lam2[VL], rha[VL];
+      for (int l = 0; l < VL; ++l) { /* material per cell (:656-658), one lane each */
+        int64_t cell = b * VL + l;
+        if (cell >= cd->ncell) cell = cd->ncell - 1;
+        const orc_mat *m = &op->mat[(cd->material_id && cd->material_id[cell] != 0) ? 1 : 0];
+        lam2[l] = 2.0 * m->lambda;
+        rha[l] = m->rho_alpha;
+      }
+      nh_batch_tensor2(op, s->tab + (size_t)b * nq3 * NFB * VL, lam2, rha, u, r, work);
+      for (int l = 0; l < VL; ++l) {
+        const int64_t cell = b * VL + l;
+        if (cell >= cd->ncell) break;
+        const uint32_t *idx = cd->dof_idx + cell * 3 * n3;
+        for (int c = 0; c < 3; ++c)
+          for (int a = 0; a < n3; ++a) {
+            const uint32_t d = idx[c * n3 + a];
+            if (cd->constrained[d]) continue;
+            const double v = r[c][(size_t)a * VL + l];
+            if (s->shared[d]) {
+#pragma omp atomic
+              dst[d] += v;
+            } else {
+              dst[d] += v;
+            }
+          }
+      }
+    }
+    free(u); free(r); free(work);
+  }
+  for (int64_t i = 0; i < cd->ndofs; ++i) if (cd->constrained[i]) dst[i] += src[i]; /* :623-624 */
+}
+
+/* which clone the dispatcher picks on this machine (reported next to the CPU baseline) */
+const char *orc_simd_isa(void)
+{
+#if defined(__x86_64__) && defined(__GNUC__)
+  __builtin_cpu_init();
+  if (__builtin_cpu_supports("avx512f")) return "avx512f (8 doubles per vector)";
+  if (__builtin_cpu_supports("avx2")) return "avx2+fma (4 doubles per vector)";
+  return "baseline x86-64 (as compiled)";
+#else
+  return "scalar";
+#endif
+}
+
 /* compute_diagonal (:1023-1060) via MatrixFreeTools::compute_diagonal semantics (A.4) */
 void orc_nh_compute_diagonal(orc_nh *op, double *diag, double *inv_diag)
 {

@@ -19,7 +19,8 @@ def _n_gpus():
         return 0
 
 
-def _worker(rank, world, port, grid, nc, p, q):
+def _worker(rank, world, port, grid, nc, p, q, p2p=1):
+    os.environ["B200MF_P2P"] = str(p2p)
     import faulthandler
     import sys as _sys
 
@@ -69,6 +70,11 @@ def _worker(rank, world, port, grid, nc, p, q):
             out = d.download()
             errs.append(rel(out[:pt.n_owned], gdst[g_owned]))
             assert np.all(out[pt.n_owned:] == 0.0)  # compress(add) zeroes the ghost entries
+        # vmult_add into a vector whose ghost entries hold stale values (they must not reach the owners)
+        d.upload(np.concatenate([gdst[g_owned], np.full(pt.n_dofs - pt.n_owned, 7.0)]))
+        op.vmult_add(d, s)
+        errs.append(rel(d.download()[:pt.n_owned], 2 * gdst[g_owned]))
+        assert mf.exchange_is_p2p() == (os.environ.get("B200MF_P2P", "1") != "0")
         op.compute_diagonal()
         diag = op.get_matrix_diagonal()
         q.put((rank, max(errs), diag[:pt.n_owned].min()))
@@ -79,9 +85,113 @@ def _worker(rank, world, port, grid, nc, p, q):
         dist.destroy_process_group()
 
 
+def _spawn(world, target, args):
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=target, args=(r, world, port) + tuple(args) + (q,)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    import queue as _queue
+
+    res = []
+    try:
+        for _ in range(world):
+            res.append(q.get(timeout=200))
+    except _queue.Empty:
+        pass  # a rank that raised leaves its peers waiting: report the ranks that did answer
+    for pr in procs:
+        pr.join(5)
+        if pr.is_alive():
+            pr.kill()
+    for r in res:
+        assert not isinstance(r[1], str), r[1]
+    assert len(res) == world, f"only {len(res)} of {world} ranks answered"
+    return sorted(res, key=lambda r: r[0])
+
+
+def _newton_worker(rank, world, port, grid, p, levels, q):
+    """Two Newmark steps of the solid solver (b200mf.solid.Solid) on one brick per rank: distributed residual, cache,
+    diagonals, interpolate_to_mg, Chebyshev estimates, GMG-preconditioned CG (mf_elasticity.h:1400-1491, 1981-2070)."""
+    import faulthandler
+    import sys as _sys
+
+    faulthandler.enable()
+    faulthandler.dump_traceback_later(150, exit=True, file=_sys.stderr)
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from b200mf import Communicator, MatrixFree
+        from b200mf.mesh import children_of
+        from b200mf.partition import BrickPartition
+        from b200mf.solid import Solid
+        from test_gpu_newton import MATERIAL
+
+        comm = Communicator.from_torch_distributed()
+        upper = tuple(float(g) for g in grid)
+        parts = []
+        for l in range(levels):
+            pt = BrickPartition(grid, 2**l, p, rank, upper=upper)
+            pt.clamp_global_face(0, 0)
+            parts.append(pt)
+        level_mf = [MatrixFree.from_partition(pt, comm, dtype="f32") for pt in parts]
+        sys_mf = MatrixFree.from_partition(parts[-1], comm)
+        sol = Solid(parts, delta_t=0.01, body_force=(0.0, -800.0, 200.0), n_cheb_cg=30, matrix_frees=(sys_mf, level_mf),
+                    children=[children_of(pt) for pt in parts[:-1]], **MATERIAL)
+        sol.run(2)
+        fine = parts[-1]
+        g_owned = (3 * fine.global_lex_node()[:, None] + np.arange(3)[None, :]).reshape(-1)[:fine.n_owned]
+        q.put((rank, (g_owned, sol.total_displacement()[:fine.n_owned]), list(sol.newton_iterations), list(sol.cg_history)))
+    except BaseException:
+        import traceback
+        q.put((rank, traceback.format_exc(), None, None))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,grid,p,levels", [(2, (2, 1, 1), 2, 2), (2, (2, 1, 1), 1, 3)])
+def test_distributed_newton_gmg(world, grid, p, levels):
+    """BASELINE config 4 in miniature: the GMG-preconditioned Newton step on more than one GPU (per-level brick partitions,
+    level vectors exchanged through the same partitioner) reproduces the one-GPU run of the same global mesh."""
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    from b200mf.mesh import StructuredMesh
+    from b200mf.solid import Solid
+    from test_gpu_newton import MATERIAL
+
+    res = _spawn(world, _newton_worker, (grid, p, levels))
+    meshes = []
+    for l in range(levels):
+        m = StructuredMesh(tuple(g * 2**l for g in grid), p, upper=tuple(float(g) for g in grid))
+        m.clamp([(0, 0)], 3)
+        meshes.append(m)
+    ref = Solid(meshes, delta_t=0.01, body_force=(0.0, -800.0, 200.0), n_cheb_cg=30, **MATERIAL)
+    ref.run(2)
+    u_ref = ref.total_displacement()
+    got = np.full_like(u_ref, np.nan)
+    for rank, (idx, val), newton, cg in res:
+        got[idx] = val
+        assert newton == ref.newton_iterations
+        # the deterministic Chebyshev start vector follows the (rank-contiguous) global enumeration, which differs from the
+        # one-rank numbering: eigenvalue estimates and hence CG counts may move by one
+        assert max(abs(a - b) for a, b in zip(cg, ref.cg_history)) <= 1, (cg, ref.cg_history)
+    assert not np.isnan(got).any()
+    assert np.abs(got - u_ref).max() <= 1e-7 * np.abs(u_ref).max()
+
+
+@pytest.mark.parametrize("p2p", [1, 0], ids=["p2p", "nccl"])
 @pytest.mark.parametrize("world,grid,nc,p", [(2, (2, 1, 1), (3, 2, 2), 2), (2, (1, 2, 1), (2, 2, 3), 3), (2, (1, 1, 2), (4, 4, 5), 4),
                                              (4, (2, 2, 1), (4, 3, 3), 2)])
-def test_distributed_vmult_two_gpus(world, grid, nc, p):
+def test_distributed_vmult_two_gpus(world, grid, nc, p, p2p):
     if _n_gpus() < world:
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
@@ -89,7 +199,7 @@ def test_distributed_vmult_two_gpus(world, grid, nc, p):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29600 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, world, port, grid, nc, p, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, grid, nc, p, q, p2p)) for r in range(world)]
     for pr in procs:
         pr.start()
     import queue as _queue

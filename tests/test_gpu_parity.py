@@ -397,3 +397,31 @@ def test_heat_rhs_cells(p, mapped):
         rhs = DeviceVector(mf)
         op.assemble_rhs(rhs, DeviceVector(mf, u_old), src_q, const)
         assert rel(rhs.download(), ref) < TOL64
+
+
+@pytest.mark.parametrize("p,ncells,numbering", [(2, (16, 16, 16), "lexicographic"), (2, (16, 16, 16), "random"),
+                                                (2, (16, 16, 16), "morton"), (4, (10, 10, 10), "lexicographic")])
+def test_nh_vmult_host_pipelined(p, ncells, numbering):
+    """The host-vector entry point on a mesh large enough for the pipelined schedule (sliced H2D || scatter + cell waves ||
+    sliced D2H, b200mf_nh_vmult_host): same result as the device-vector vmult and as the oracle, for a locality-preserving
+    numbering (frontiers advance with the waves), a cell-wise Morton numbering and a random one (degenerate schedule)."""
+    from b200mf.mesh import StructuredMesh
+
+    m = StructuredMesh(ncells, p, permute_seed=3 if numbering == "random" else None)
+    m.clamp([(0, 0), (1, 1)], 3)
+    if numbering == "morton":
+        m.renumber_cellwise_morton()
+    u = displacement(m)
+    src = np.random.default_rng(p).uniform(-1, 1, 3 * m.n_nodes)  # constrained entries non-zero: dst[c] = src[c] there
+    mf, op = gpu_nh(m, u)
+    out = np.zeros_like(src)
+    op.vmult(out, src)  # host entry point
+    s, d = DeviceVector(mf, src), DeviceVector(mf)
+    op.vmult(d, s)
+    assert rel(out, d.download()) < 1e-14
+    out2 = np.full_like(src, np.nan)
+    op.vmult(out2, src)  # staging buffers are reused
+    assert rel(out2, out) < 1e-14
+    ref = np.zeros_like(src)
+    oracle_nh(m, u).vmult(ref, src)
+    assert rel(out, ref) < TOL64

@@ -191,3 +191,26 @@ def test_interface_traction_general_geometry_matches_box_version():
         fno += [2 * d + side] * on.size
     got = interface_traction_rhs_q1(m, u, t, cells, fno)
     assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4])
+def test_simd_over_cells_vmult_equals_scalar_loop(p):
+    """The CPU arm of bench.py (8 cells per batch, one SIMD lane per cell, oracle/mf_oracle.c orc_nh_vmult_simd) is the
+    same operator as the scalar restatement; other cache levels report that they have no batched form."""
+    from common import MAT, c_cells, displacement, make_mesh
+    from oracle import c_oracle as CO
+
+    m = make_mesh(p, (3, 3, 2) if p < 4 else (2, 2, 1))
+    m.material_id[::3] = 1
+    op = CO.NeoHookOperator(c_cells(m), formulation=1, mu_inclusion=2.0e6, **MAT)
+    op.initialize(displacement(m), "tensor2")
+    op.cache()
+    src = np.random.default_rng(p).uniform(-1, 1, 3 * m.n_nodes)
+    a, b = np.zeros_like(src), np.zeros_like(src)
+    op.vmult(a, src)
+    assert op.vmult_simd(b, src)
+    assert np.linalg.norm(a - b) <= 1e-14 * np.linalg.norm(a)
+    op4 = CO.NeoHookOperator(c_cells(m), formulation=1, **MAT)
+    op4.initialize(displacement(m), "tensor4")
+    op4.cache()
+    assert not op4.vmult_simd(b, src)
