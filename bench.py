@@ -398,6 +398,37 @@ def parity_block(torch, dist, comm, world, rank, p):
             "checker": "oracle/mf_oracle.c on the undivided global mesh (test infrastructure; not on the measured path)"}
 
 
+def tube_block(stream_ptr, degree=3, levels=5, pressure=5.0e4):
+    """BASELINE.json configs[3] on ONE GPU: a Newmark step of the solid solver on the tube3d geometry (tube_3d.h:23-33, 74:
+    cylinder shell, curved cells -> full per-q-point metric; ends clamped; pressure-like traction on the inner wall pulled back
+    in every Newton iteration) with the reference's whole 35-coarse-cell multigrid hierarchy; every Newton iteration =
+    residual (cells + interface faces) + update_matrix_free + GMG-CG.  (The 8-GPU, 4e8-DoF size of the config needs the
+    coarse levels agglomerated below 8 axial cells per rank, which the brick partitioner does not do yet.)"""
+    from b200mf import lib as L_
+    from b200mf.mesh import tube_hierarchy, tube_pressure_traction
+    from b200mf.solid import Solid
+
+    meshes = tube_hierarchy(degree, levels)
+    sol = Solid(meshes, mu=115384.0, nu=0.3, rho=1200.0, delta_t=1e-4, n_cheb_cg=30,  # examples/tube3d/solid/tube3d.prm
+                traction=tube_pressure_traction(pressure), traction_faces=((2, 0),))
+    for mf in [sol.mf] + sol.level_mf:
+        mf.set_stream(stream_ptr)
+    m = meshes[-1]
+    sol.mf.synchronize()
+    launches0 = L_.load().b200mf_launch_count()
+    t0 = time.perf_counter()
+    its = sol.solve_nonlinear_timestep()
+    sol.advance_time_window()
+    sol.mf.synchronize()
+    t1 = time.perf_counter()
+    return {"workload": f"tube3d Newmark step: neo-Hookean, tensor2, Q{degree}, cylinder shell {m.ncells[0]}x{m.ncells[1]}x{m.ncells[2]} curved cells, "
+                        f"{3 * m.n_nodes} DoFs, {levels} levels, GMG-Chebyshev CG, interface traction on {sol.face_op.cells.size} faces",
+            "n_dofs": 3 * m.n_nodes, "time_step_s": t1 - t0, "newton_iterations": int(its), "cg_iterations": list(map(int, sol.cg_history)),
+            "seconds_per_newton_iteration": (t1 - t0) / max(1, len(sol.cg_history)),
+            "gpu_launches": int(L_.load().b200mf_launch_count() - launches0), "max_displacement": float(np.abs(sol.total_displacement()).max()),
+            "note": "first time step from rest: includes one-off allocations of the smoother / solver objects"}
+
+
 def newton_block(stream_ptr, degree=3, coarse=5, levels=5, amplitude=0.01):
     """BASELINE.json metric, second half: Newton-step time = update_matrix_free (cache + diagonals + interpolate_to_mg +
     Chebyshev eigenvalue estimates on every level) + one GMG-CG solve to 1e-6 * ||rhs|| (mf_elasticity.h:1289-1353,
@@ -440,6 +471,69 @@ def newton_block(stream_ptr, degree=3, coarse=5, levels=5, amplitude=0.01):
             "level0": sol.eig[0], "level_top": sol.eig[-1]}
 
 
+FP64_PEAK_TFLOPS = 33.9  # measured on this pool's B200: independent DFMA chains, tools/microbench/fp64_pipes.cu -> profiles/r01_fp64_pipes.jsonl
+
+
+def heat_block(torch, stream_ptr, degree=4, coarse=7, levels=5, dt=0.1):
+    """BASELINE.json configs[1]: backward-Euler heat step, Q4 cube, ~9e7 DoF, GMG-CG on one B200 (heat_transfer.h:577-812)
+    through b200mf.heat.HeatProblem, plus the FP64 system operator alone: on affine cells it streams ~41 B/DoF and does
+    ~293 flop/DoF, i.e. it is bound by the FP64 pipe, reported against the measured DFMA peak."""
+    from b200mf.heat import HeatProblem
+    from b200mf.mesh import StructuredMesh
+
+    faces = [(0, 0), (0, 1), (1, 0), (1, 1), (2, 0), (2, 1)]
+    meshes = []
+    for l in range(levels):
+        m = StructuredMesh((coarse * 2**l,) * 3, degree)
+        m.clamp(faces, 1)
+        meshes.append(m)
+    hp = HeatProblem(meshes, dt, source_const=1.0)
+    for mf in [hp.mf] + hp.level_mf:
+        mf.set_stream(stream_ptr)
+    m = meshes[-1]
+    x = m.node_coordinates()
+    u0 = np.prod(np.sin(np.pi * x), axis=1)
+    u0[m.constrained_dofs(1)] = 0.0
+    hp.solution.upload(u0)
+    hp.time_step()  # warm-up: allocations, smoother objects, first launches
+    hp.mf.synchronize()
+    t0 = time.perf_counter()
+    hp.solution_old.sadd(0.0, 1.0, hp.solution)
+    hp.assemble_rhs()
+    hp.mf.synchronize()
+    t1 = time.perf_counter()
+    hp.setup_preconditioner()
+    hp.mf.synchronize()
+    t2 = time.perf_counter()
+    res = hp.solve()
+    hp.mf.synchronize()
+    t3 = time.perf_counter()
+    # the FP64 system operator alone
+    n = m.n_nodes
+    y = hp.mf.initialize_dof_vector()
+    for _ in range(3):
+        hp.system_matrix.vmult(y, hp.solution)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        hp.system_matrix.vmult(y, hp.solution)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    nn, p = degree + 1, degree
+    flop_per_dof = (24 * nn**4 + 30 * nn**3) / p**3
+    tflops = n / (ms * 1e-3) * flop_per_dof / 1e12
+    return {"workload": f"heat: backward-Euler (M + dt K), Q{degree}, cube {m.ncells[0]}^3 affine cells, {n} DoFs, {levels} levels, dt={dt}",
+            "n_dofs": n, "time_step_s": t3 - t0, "assemble_rhs_s": t1 - t0, "diagonals_and_eigenvalues_s": t2 - t1,
+            "cg_solve_s": t3 - t2, "cg_iterations": int(res["iterations"]), "residual": res["residual"],
+            "system_vmult": {"ms": ms, "dofs_per_s": n / (ms * 1e-3),
+                             "roofline": {"bound": "fp64", "achieved": tflops, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                                          "frac": tflops / FP64_PEAK_TFLOPS, "flop_per_dof": flop_per_dof,
+                                          "peak_source": "measured DFMA peak, profiles/r01_fp64_pipes.jsonl",
+                                          "kernel": f"scalar_stack_kernel<double, {nn}, LaplaceAffineOp>"}}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -452,6 +546,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="N > 1: time the plain Python loop instead of a CUDA-graph replay of it")
+    ap.add_argument("--no-heat", action="store_true", help="skip the heat_step block (BASELINE configs[1])")
     ap.add_argument("--no-extras", action="store_true", help="skip the sweep / numbering / newton_step / parity blocks (tuning runs)")
     ap.add_argument("--sweep", action="store_true", help="report Q1..Q6 in the sweep block (default: Q2, Q3, Q4 = the metric)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
@@ -586,11 +681,12 @@ def main():
             return float(t.item())
 
         t_serial, t_overlap, t_none = timed(0), timed(1), timed(-1)
-        mf.set_overlap(0)  # library default
+        mf.set_overlap(1 if mf_p2p else 0)  # library default: overlapped with the peer-to-peer exchange, serial with NCCL
         exchange = {"ms_step_default": ms, "ms_overlapped_exchange": t_overlap, "ms_serial_exchange": t_serial,
                     "ms_no_exchange": t_none, "exposed_ms_overlapped": t_overlap - t_none, "exposed_ms_serial": t_serial - t_none,
-                    "note": "default (timed step) = serial = the reference's order update_ghost_values -> cells -> compress(add); "
-                            "overlapped = boundary cells first, exchanges on a second stream behind the interior cells (opt-in); "
+                    "note": "serial = the reference's order update_ghost_values -> cells -> compress(add); overlapped = boundary cells "
+                            "first, exchanges on a second stream behind the interior cells; the timed step uses the library default "
+                            "(overlapped with the peer-to-peer exchange, serial with NCCL); "
                             "no_exchange = rank-local cells only (measurement mode); 10 steps each after 3 warm-ups"}
 
     # ---- e2e: host buffers through the C-ABI host entry point ----------------------------------
@@ -624,7 +720,7 @@ def main():
 
     # ---- the other points of BASELINE.json's metric: Q2..Q4 (Q1..Q6 with --sweep), numbering / geometry flavours,
     # Newton-step time.  One GPU (rank 0 keeps its device; the other ranks wait at the final barrier).
-    sweep = numbering = newton = None
+    sweep = numbering = newton = heat = tube = None
     if not args.no_extras and world == 1:
         del src, dst, op, mf, m
         sp = stream.cuda_stream
@@ -645,6 +741,9 @@ def main():
                              "order (deal.II-like, mf_elasticity.h:416-425, 667-669); curved = smooth non-affine vertex mapping" % p}
         if args.dtype == "f64" and args.caching == "tensor2":
             newton = newton_block(sp)
+            if not args.no_heat:
+                heat = heat_block(torch, sp)
+                tube = tube_block(sp)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -677,6 +776,10 @@ def main():
             line["numbering"] = numbering
         if newton:
             line["newton_step"] = newton
+        if heat:
+            line["heat_step"] = heat
+        if tube:
+            line["tube3d_step"] = tube
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

@@ -1,14 +1,23 @@
 // b200mf_dealii.h — the deal.II-side shim over the C ABI of libb200mf (include/b200mf.h).
 //
-// STATUS: deal.II (>= 9.6), p4est, MPI and preCICE are not installed in the image this library is built and tested in,
-// so THIS HEADER HAS NEVER BEEN COMPILED.  It is the binding a maintainer of davidscn/matrix-free-dealii-precice adds on a
-// machine that has deal.II; the identical call sequence is what tests/ exercise through the ctypes mirror
-// (matrix-free-dealii-precice_b200/b200mf/operators.py).  It uses public deal.II API only.
+// STATUS: deal.II (>= 9.6), p4est, MPI and preCICE are not installed in the image this library is built and tested in, so
+// this header has never been compiled against deal.II.  tests/test_shim_syntax.py compiles it (g++ -fsyntax-only, every
+// template instantiated) against tests/mock_dealii/, a minimal stand-in that declares the deal.II classes and members used
+// here with deal.II's documented signatures - that catches syntax and type errors, not semantic drift.  It lives under
+// contrib/ (not include/) until a deal.II build compiles it in CI.  It is the binding a maintainer of
+// davidscn/matrix-free-dealii-precice adds; the identical call sequence is what tests/ exercise through the ctypes mirror
+// (matrix-free-dealii-precice_b200/b200mf/operators.py).  Public deal.II API only.
 //
-// It provides, with the member set the reference's solvers call (include/solid_mechanics/mf_nh_operator.h:102-173):
+// It provides, with the member set the reference's solvers call:
 //   B200MF::make_context(MatrixFree, comm)  -> b200mf_ctx*      arrays extracted once per (re)initialisation
-//   B200MF::NeoHookOperator<dim, Number>                         drop-in for ::NeoHookOperator<dim, Number>
-// LaplaceOperator (include/heat_transfer/heat_transfer.h:81-127) follows the same pattern on b200mf_laplace_*.
+//   B200MF::DeviceVector                                         RAII handle of a library-owned device vector (performance mode)
+//   B200MF::NeoHookOperator<dim, Number>    drop-in for ::NeoHookOperator<dim, Number> (include/solid_mechanics/mf_nh_operator.h:102-173)
+//   B200MF::LaplaceOperator<dim, Number>    drop-in for Heat_Transfer::LaplaceOperator (include/heat_transfer/heat_transfer.h:81-127,
+//                                           with the MatrixFreeOperators::Base surface the heat solver and mg::Matrix call)
+// Parity mode: deal.II's SolverCG / PreconditionChebyshev / Multigrid keep running on the host and call vmult with
+// LinearAlgebra::distributed::Vector; every operator keeps two pinned staging buffers, so a vmult allocates nothing.
+// Performance mode: the same operators applied to B200MF::DeviceVector, and b200mf_cg_solve / b200mf_mg_vmult on the
+// handles (handle()) replace the deal.II solver objects wholesale.
 #pragma once
 #include <deal.II/base/mpi.h>
 #include <deal.II/lac/diagonal_matrix.h>
@@ -17,6 +26,7 @@
 #include <deal.II/matrix_free/matrix_free.h>
 
 #include <b200mf.h>
+#include <cuda_runtime_api.h> // cudaMallocHost / cudaFreeHost for the pinned staging buffers
 
 #include <cstdint>
 #include <map>
@@ -181,9 +191,98 @@ namespace B200MF
   }
 
 
-  // Drop-in for ::NeoHookOperator<dim, Number> (mf_nh_operator.h:99-237), parity mode: deal.II's SolverCG / Chebyshev /
-  // Multigrid keep running on the host and call vmult with host vectors.  Performance mode replaces those solver objects by
-  // b200mf_cg_solve / b200mf_mg_vmult on device vectors.
+  // Library-owned device vector in the context's internal numbering (performance mode: vectors never leave the GPU
+  // between solver calls).  upload()/download() translate from/to the MatrixFree partitioner's local numbering
+  // [owned | ghosts] in double precision.
+  class DeviceVector
+  {
+  public:
+    explicit DeviceVector(b200mf_ctx *ctx_)
+      : ctx(ctx_)
+    {
+      check(b200mf_vec_create(ctx, &ptr));
+    }
+    DeviceVector(const DeviceVector &) = delete;
+    DeviceVector &
+    operator=(const DeviceVector &) = delete;
+    ~DeviceVector()
+    {
+      b200mf_vec_destroy(ctx, ptr);
+    }
+    template <typename VectorType>
+    void
+    upload(const VectorType &v, std::vector<double> &scratch)
+    {
+      scratch.assign(b200mf_ctx_n_dofs(ctx), 0.0);
+      for (unsigned int i = 0; i < v.locally_owned_size(); ++i)
+        scratch[i] = v.local_element(i);
+      check(b200mf_vec_upload_f64(ctx, ptr, scratch.data()));
+    }
+    template <typename VectorType>
+    void
+    download(VectorType &v, std::vector<double> &scratch) const
+    {
+      scratch.resize(b200mf_ctx_n_dofs(ctx));
+      check(b200mf_vec_download_f64(ctx, scratch.data(), ptr));
+      for (unsigned int i = 0; i < v.locally_owned_size(); ++i)
+        v.local_element(i) = typename VectorType::value_type(scratch[i]);
+    }
+    void *
+    data() const
+    {
+      return ptr;
+    }
+    double
+    l2_norm() const // LinearAlgebra::distributed::Vector::l2_norm over the owned entries of all ranks
+    {
+      double v = 0;
+      check(b200mf_vec_l2_norm(ctx, ptr, &v));
+      return v;
+    }
+    void
+    sadd(const double s, const double a, const DeviceVector &x) // *this = s * *this + a * x
+    {
+      check(b200mf_vec_sadd(ctx, ptr, s, a, x.ptr));
+    }
+
+  private:
+    b200mf_ctx *ctx;
+    void       *ptr = nullptr;
+  };
+
+  // Two pinned host buffers of the context's local vector size: the staging area of the host-vector entry points
+  // (b200mf_*_vmult_host pipelines H2D, the cell waves and D2H out of / into them).
+  struct PinnedStaging
+  {
+    double     *src = nullptr, *dst = nullptr;
+    std::size_t n   = 0;
+    void
+    reinit(const std::size_t n_)
+    {
+      release();
+      n = n_;
+      AssertThrow(cudaMallocHost(reinterpret_cast<void **>(&src), n * sizeof(double)) == cudaSuccess, dealii::ExcMessage("cudaMallocHost"));
+      AssertThrow(cudaMallocHost(reinterpret_cast<void **>(&dst), n * sizeof(double)) == cudaSuccess, dealii::ExcMessage("cudaMallocHost"));
+      for (std::size_t i = 0; i < n; ++i)
+        src[i] = dst[i] = 0.0;
+    }
+    void
+    release()
+    {
+      if (src)
+        cudaFreeHost(src);
+      if (dst)
+        cudaFreeHost(dst);
+      src = dst = nullptr;
+      n         = 0;
+    }
+    ~PinnedStaging()
+    {
+      release();
+    }
+  };
+
+  // Drop-in for ::NeoHookOperator<dim, Number> (mf_nh_operator.h:99-237).
   template <int dim, typename Number>
   class NeoHookOperator : public dealii::Subscriptor
   {
@@ -204,6 +303,7 @@ namespace B200MF
       b200mf_ctx_destroy(ctx);
       op  = nullptr;
       ctx = nullptr;
+      staging.release();
       diagonal_is_available = false;
     }
 
@@ -235,16 +335,44 @@ namespace B200MF
                                                           -1;
       AssertThrow(level >= 0, dealii::ExcMessage("Unknown caching")); // :385
       check(b200mf_nh_initialize(op, level));
+      staging.reinit(b200mf_ctx_n_dofs(ctx));
     }
 
     void
     cache() // :392-523; the debug assertion det F > 0 (:430-435) comes back as an error
     {
-      std::int64_t     n_bad = 0;
-      std::vector<double> u(displacement->locally_owned_size() + displacement->get_partitioner()->n_ghost_indices());
-      for (unsigned int i = 0; i < u.size(); ++i)
-        u[i] = displacement->local_element(i);
-      check(b200mf_nh_cache_host(op, u.data(), &n_bad));
+      std::int64_t n_bad = 0;
+      for (unsigned int i = 0; i < displacement->locally_owned_size(); ++i) // the library updates the ghosts itself
+        staging.src[i] = displacement->local_element(i);
+      check(b200mf_nh_cache_host(op, staging.src, &n_bad));
+    }
+    void
+    cache(const DeviceVector &displacement_on_device) // performance mode
+    {
+      std::int64_t n_bad = 0;
+      check(b200mf_nh_cache(op, displacement_on_device.data(), &n_bad));
+    }
+
+    // performance mode: the same operator on device vectors (no host copy, asynchronous on the context's stream)
+    void
+    vmult(DeviceVector &dst, const DeviceVector &src) const
+    {
+      check(b200mf_nh_vmult(op, dst.data(), src.data()));
+    }
+    void
+    vmult_add(DeviceVector &dst, const DeviceVector &src) const
+    {
+      check(b200mf_nh_vmult_add(op, dst.data(), src.data()));
+    }
+    void
+    Tvmult(DeviceVector &dst, const DeviceVector &src) const
+    {
+      check(b200mf_nh_Tvmult(op, dst.data(), src.data()));
+    }
+    void
+    precondition_Jacobi(DeviceVector &dst, const DeviceVector &src, const Number omega) const
+    {
+      check(b200mf_nh_precondition_jacobi(op, dst.data(), src.data(), omega));
     }
 
     void
@@ -276,13 +404,11 @@ namespace B200MF
       diagonal_entries         = std::make_shared<dealii::DiagonalMatrix<VectorType>>();
       data->initialize_dof_vector(inverse_diagonal_entries->get_vector());
       data->initialize_dof_vector(diagonal_entries->get_vector());
-      const unsigned int  n_local = b200mf_ctx_n_dofs(ctx);
-      std::vector<double> diag(n_local), inv(n_local);
-      check(b200mf_nh_diagonal_host(op, diag.data(), inv.data()));
+      check(b200mf_nh_diagonal_host(op, staging.src, staging.dst));
       for (unsigned int i = 0; i < data->get_vector_partitioner()->locally_owned_size(); ++i)
         {
-          diagonal_entries->get_vector().local_element(i)         = diag[i];
-          inverse_diagonal_entries->get_vector().local_element(i) = inv[i];
+          diagonal_entries->get_vector().local_element(i)         = Number(staging.src[i]);
+          inverse_diagonal_entries->get_vector().local_element(i) = Number(staging.dst[i]);
         }
       diagonal_entries->get_vector().update_ghost_values(); // :1056-1057
       inverse_diagonal_entries->get_vector().update_ghost_values();
@@ -342,13 +468,12 @@ namespace B200MF
     {
       // vectors may carry another ghost set than the MatrixFree partitioner (adjust_ghost_range_if_necessary, :76-90):
       // the library only needs the owned entries and does its own ghost exchange
-      const unsigned int  n_owned = data->get_vector_partitioner()->locally_owned_size(), n_local = b200mf_ctx_n_dofs(ctx);
-      std::vector<double> s(n_local, 0.0), d(n_local, 0.0);
+      const unsigned int n_owned = data->get_vector_partitioner()->locally_owned_size();
       for (unsigned int i = 0; i < n_owned; ++i)
-        s[i] = src.local_element(i);
-      check(b200mf_nh_vmult_host(op, d.data(), s.data()));
+        staging.src[i] = src.local_element(i);
+      check(b200mf_nh_vmult_host(op, staging.dst, staging.src)); // pinned buffers: H2D || cells || D2H pipeline inside
       for (unsigned int i = 0; i < n_owned; ++i)
-        dst.local_element(i) = (add ? dst.local_element(i) : Number(0)) + Number(d[i]);
+        dst.local_element(i) = (add ? dst.local_element(i) : Number(0)) + Number(staging.dst[i]);
     }
 
     std::shared_ptr<const dealii::MatrixFree<dim, Number>> data;
@@ -356,7 +481,187 @@ namespace B200MF
     b200mf_material                                         mat{}, incl{};
     b200mf_ctx                                             *ctx = nullptr;
     b200mf_nh                                              *op  = nullptr;
+    mutable PinnedStaging                                   staging;
     std::shared_ptr<dealii::DiagonalMatrix<VectorType>>     inverse_diagonal_entries, diagonal_entries;
     bool                                                    diagonal_is_available = false;
+  };
+
+
+  // Drop-in for Heat_Transfer::LaplaceOperator<dim, fe_degree, number> (heat_transfer.h:81-127): (M + dt c K) u with the
+  // MatrixFreeOperators::Base surface the heat solver, PreconditionChebyshev and mg::Matrix use.
+  template <int dim, typename Number>
+  class LaplaceOperator : public dealii::Subscriptor
+  {
+  public:
+    using value_type = Number;
+    using size_type  = dealii::types::global_dof_index;
+    using VectorType = dealii::LinearAlgebra::distributed::Vector<Number>;
+
+    ~LaplaceOperator()
+    {
+      clear();
+    }
+
+    void
+    clear() // Base::clear + :129-137
+    {
+      b200mf_laplace_destroy(op);
+      b200mf_ctx_destroy(ctx);
+      op  = nullptr;
+      ctx = nullptr;
+      staging.release();
+      inverse_diagonal_entries.reset();
+      diagonal_entries.reset();
+    }
+
+    // Base::initialize(data) (+ level variant: the caller hands the level MatrixFree) and evaluate_coefficient (:150-166):
+    // coefficient = [cell][q] values in FEEvaluation's cell/q order, or empty for Coefficient::value == 1 (:64-71)
+    void
+    initialize(std::shared_ptr<const dealii::MatrixFree<dim, Number>> data_,
+               const double                                           delta_t_,
+               const std::vector<double>                             &coefficient = {},
+               b200mf_comm                                           *comm        = nullptr)
+    {
+      clear();
+      data    = data_;
+      delta_t = delta_t_;
+      ctx     = make_context<dim, 1, Number>(*data, comm);
+      check(b200mf_laplace_create(&op, ctx, delta_t, coefficient.empty() ? nullptr : coefficient.data()));
+      staging.reinit(b200mf_ctx_n_dofs(ctx));
+    }
+
+    void
+    set_delta_t(const double delta_t_) // :141-146
+    {
+      delta_t = delta_t_;
+      check(b200mf_laplace_set_delta_t(op, delta_t));
+    }
+
+    void
+    vmult(VectorType &dst, const VectorType &src) const // Base::vmult -> apply_add (:194-201)
+    {
+      host_apply(dst, src, false);
+    }
+    void
+    Tvmult(VectorType &dst, const VectorType &src) const
+    {
+      host_apply(dst, src, false);
+    }
+    void
+    vmult_add(VectorType &dst, const VectorType &src) const
+    {
+      host_apply(dst, src, true);
+    }
+    void
+    Tvmult_add(VectorType &dst, const VectorType &src) const
+    {
+      host_apply(dst, src, true);
+    }
+    // mg::Matrix / MGInterfaceOperator: no refinement edges on globally refined meshes (heat_transfer.h:421-425) -> dst = 0
+    void
+    vmult_interface_down(VectorType &dst, const VectorType &) const
+    {
+      dst = Number(0);
+    }
+    void
+    vmult_interface_up(VectorType &dst, const VectorType &) const
+    {
+      dst = Number(0);
+    }
+
+    // performance mode
+    void
+    vmult(DeviceVector &dst, const DeviceVector &src) const
+    {
+      check(b200mf_laplace_vmult(op, dst.data(), src.data()));
+    }
+    void
+    vmult_add(DeviceVector &dst, const DeviceVector &src) const
+    {
+      check(b200mf_laplace_vmult_add(op, dst.data(), src.data()));
+    }
+
+    void
+    compute_diagonal() // :205-230
+    {
+      check(b200mf_laplace_compute_diagonal(op));
+      inverse_diagonal_entries = std::make_shared<dealii::DiagonalMatrix<VectorType>>();
+      diagonal_entries         = std::make_shared<dealii::DiagonalMatrix<VectorType>>();
+      data->initialize_dof_vector(inverse_diagonal_entries->get_vector());
+      data->initialize_dof_vector(diagonal_entries->get_vector());
+      check(b200mf_laplace_diagonal_host(op, staging.src, staging.dst));
+      for (unsigned int i = 0; i < data->get_vector_partitioner()->locally_owned_size(); ++i)
+        {
+          diagonal_entries->get_vector().local_element(i)         = Number(staging.src[i]);
+          inverse_diagonal_entries->get_vector().local_element(i) = Number(staging.dst[i]);
+        }
+    }
+
+    const std::shared_ptr<dealii::DiagonalMatrix<VectorType>> &
+    get_matrix_diagonal_inverse() const
+    {
+      return inverse_diagonal_entries;
+    }
+    const std::shared_ptr<dealii::DiagonalMatrix<VectorType>> &
+    get_matrix_diagonal() const
+    {
+      return diagonal_entries;
+    }
+
+    void
+    initialize_dof_vector(VectorType &vec) const // Base::initialize_dof_vector
+    {
+      data->initialize_dof_vector(vec);
+    }
+    std::shared_ptr<const dealii::MatrixFree<dim, Number>>
+    get_matrix_free() const
+    {
+      return data;
+    }
+
+    Number
+    el(const unsigned int row, const unsigned int col) const // Base::el: diagonal only
+    {
+      Assert(row == col, dealii::ExcNotImplemented());
+      (void)col;
+      double v = 0;
+      check(b200mf_laplace_el(op, row, &v));
+      return Number(v);
+    }
+    size_type
+    m() const
+    {
+      return data->get_vector_partitioner()->size();
+    }
+    size_type
+    n() const
+    {
+      return m();
+    }
+
+    b200mf_laplace *
+    handle() const // b200mf_cg_create_laplace(handle()), b200mf_chebyshev_create_laplace(handle(), ...)
+    {
+      return op;
+    }
+
+  private:
+    void
+    host_apply(VectorType &dst, const VectorType &src, const bool add) const
+    {
+      const unsigned int n_owned = data->get_vector_partitioner()->locally_owned_size();
+      for (unsigned int i = 0; i < n_owned; ++i)
+        staging.src[i] = src.local_element(i);
+      check(b200mf_laplace_vmult_host(op, staging.dst, staging.src));
+      for (unsigned int i = 0; i < n_owned; ++i)
+        dst.local_element(i) = (add ? dst.local_element(i) : Number(0)) + Number(staging.dst[i]);
+    }
+
+    std::shared_ptr<const dealii::MatrixFree<dim, Number>> data;
+    double                                                  delta_t = 0;
+    b200mf_ctx                                             *ctx     = nullptr;
+    b200mf_laplace                                         *op      = nullptr;
+    mutable PinnedStaging                                   staging;
+    std::shared_ptr<dealii::DiagonalMatrix<VectorType>>     inverse_diagonal_entries, diagonal_entries;
   };
 } // namespace B200MF

@@ -333,6 +333,12 @@ typedef struct b200mf_mg b200mf_mg;
 int b200mf_mg_create(b200mf_mg **mg, int n_levels, b200mf_chebyshev *const *smoothers /*[n_levels]*/,
                      b200mf_mg_transfer *const *transfers /*[n_levels-1]*/, b200mf_ctx *system_ctx);
 int b200mf_mg_destroy(b200mf_mg *mg);
+/* coarse-grid solver of the V-cycle.  kind 0 (default): the level-0 smoother applied as a solver (MGCoarseGridApplySmoother,
+ * 'MF Chebyshev coarse = true'); kind 1: SolverCG under ReductionControl(max_iterations, abs_tolerance, reduction) preconditioned
+ * with the level-0 smoother (MGCoarseGridIterativeSolver, include/solid_mechanics/mf_elasticity.h:1183-1198: max(m(), 100),
+ * 1e-10, 1e-3) */
+int b200mf_mg_set_coarse_solver(b200mf_mg *mg, int kind, int max_iterations, double abs_tolerance, double reduction);
+int b200mf_mg_coarse_iterations(const b200mf_mg *mg); /* CG iterations of the last coarse solve (kind 1) */
 int b200mf_mg_vmult(b200mf_mg *mg, void *dst_dvec, const void *src_dvec); /* system-context vectors (copy_to_mg / copy_from_mg inside) */
 
 /* ------------------------------------------------------------------------

@@ -278,3 +278,26 @@ def synthetic_displacement(coords, amplitude=0.05):
         e = (d + 1) % dim
         u[:, d] = amplitude * np.sin(np.pi * coords[:, d]) * np.cos(np.pi * coords[:, e])
     return u.reshape(-1)
+
+
+def tube_hierarchy(degree, n_levels, first_refinement=0):
+    """Multigrid hierarchy of the tube of include/cases/elasticity/tube_3d.h:23-33, 74: GridGenerator::cylinder_shell(length 5,
+    inner radius 0.5, outer radius 0.6, 5 cells around, 7 along the axis), scaled by 1e-2, one cell through the wall,
+    refined globally; both ends clamped (:47-63).  Direction 0 is the (periodic) angle, 1 the axis, 2 the radius: the inner
+    wall - the coupling interface - is the face (2, 0)."""
+    meshes = []
+    for r in range(first_refinement, first_refinement + n_levels):
+        m = StructuredMesh((5 * 2**r, 7 * 2**r, 2**r), degree, mapping=cylinder_shell_mapping(5.0, 0.5, 0.6, 1e-2), periodic_x=True)
+        m.clamp([(1, 0), (1, 1)], 3)
+        meshes.append(m)
+    return meshes
+
+
+def tube_pressure_traction(pressure):
+    """x -> traction of a uniform pressure on the inner wall (radially outward), the stand-in for the fluid load."""
+
+    def t(x):
+        r = np.hypot(x[1], x[2])
+        return np.array([0.0, pressure * x[1] / r, pressure * x[2] / r])
+
+    return t

@@ -44,7 +44,9 @@ class Solid:
         self.material = dict(mu=mu, nu=nu, rho=rho, alpha_1=self.a1, formulation=formulation)
         self.caching = caching
         self.body_force = (0.0, 0.0, 0.0) if body_force is None else tuple(float(x) for x in body_force)
-        self.traction = None if traction is None else tuple(float(x) for x in traction)
+        # a constant vector, or a callable x -> t(x) evaluated once at the face quadrature points (the role of the data the
+        # coupling partner writes on the interface mesh, adapter.h)
+        self.traction = traction if (traction is None or callable(traction)) else tuple(float(x) for x in traction)
         self.traction_faces = tuple(traction_faces)
         self.precond, self.relax, self.tol_lin = preconditioner, relaxation, tol_lin
         self.tol_f, self.tol_u, self.tol_f_abs, self.tol_u_abs, self.max_newton = tol_f, tol_u, tol_f_abs, tol_u_abs, max_newton
@@ -85,6 +87,11 @@ class Solid:
             from .operators import InterfaceTraction
 
             self.face_op = InterfaceTraction(self.mf, m, self.traction_faces)
+            if callable(self.traction):
+                pts = self.face_op.quadrature_points()
+                self.face_op.set_traction(np.array([self.traction(x) for x in pts], dtype=np.float64))
+            else:
+                self.face_op.set_traction(self.traction)
 
     # ---- update_acceleration (:1612-1620): a = a1*delta - a2*v_old - a3*a_old
     def update_acceleration(self):
@@ -99,7 +106,7 @@ class Solid:
         r.set_zero()
         self.op.assemble_residual(r, self.total, self.acceleration, self.body_force)
         if self.face_op is not None:
-            self.face_op.assemble(r, self.total, self.traction)  # :1849-1897
+            self.face_op.assemble(r, self.total)  # :1849-1897
         r.compress_add()          # :1899
         r.set_zero_constrained()  # :1905
         return r.l2_norm()        # :1907
@@ -120,7 +127,7 @@ class Solid:
             for l, op in enumerate(self.level_ops):
                 n_level = 3 * self.meshes[l].n_nodes if not hasattr(self.meshes[l], "n_global_dofs") else self.meshes[l].n_global_dofs
                 first = getattr(self.meshes[l], "first_global_dof", 0)  # partitioned levels: this rank's offset in the global enumeration
-                if l == 0:  # :1154-1166 (Chebyshev as coarse solver: accurate eigenvalues, m() CG iterations)
+                if l == 0 and self.coarse_solver == "chebyshev":  # :1154-1166 (accurate eigenvalues: m() CG iterations)
                     self.smoothers.append(PreconditionChebyshev(op, degree=INVALID_UNSIGNED_INT, smoothing_range=1e-3,
                                                                 eig_cg_n_iterations=n_level, n_global_dofs=n_level,
                                                                 first_global_index=first))
@@ -130,6 +137,9 @@ class Solid:
                                                                 first_global_index=first))
             self.eig = [s.estimate_eigenvalues() for s in self.smoothers]
             self.mg = PreconditionMG(self.smoothers, self.transfers, self.mf)
+            if self.coarse_solver == "cg":  # 'MF Chebyshev coarse = false': MGCoarseGridIterativeSolver (:1183-1198)
+                n0 = getattr(self.meshes[0], "n_global_dofs", 3 * self.meshes[0].n_nodes)
+                self.mg.set_coarse_solver_cg(max(n0, 100), 1e-10, 1e-3)
         else:
             self.eig = [s.estimate_eigenvalues() for s in self.smoothers]
 

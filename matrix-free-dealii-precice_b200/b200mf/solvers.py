@@ -102,6 +102,17 @@ class PreconditionMG:
     def vmult(self, dst, src):
         _l.check(_l.load().b200mf_mg_vmult(self.h, _dv(dst), _dv(src)))
 
+    def set_coarse_solver_cg(self, max_iterations, abs_tolerance=1e-10, reduction=1e-3):
+        """MGCoarseGridIterativeSolver: SolverCG + ReductionControl on level 0, preconditioned with the level-0 smoother
+        (mf_elasticity.h:1183-1198, 'MF Chebyshev coarse = false')."""
+        _l.check(_l.load().b200mf_mg_set_coarse_solver(self.h, 1, int(max_iterations), float(abs_tolerance), float(reduction)))
+
+    def set_coarse_solver_chebyshev(self):
+        _l.check(_l.load().b200mf_mg_set_coarse_solver(self.h, 0, 0, 0.0, 0.0))
+
+    def coarse_iterations(self):
+        return int(_l.load().b200mf_mg_coarse_iterations(self.h))
+
     def __del__(self):
         if getattr(self, "h", None):
             _l.load().b200mf_mg_destroy(self.h)

@@ -361,10 +361,10 @@ extern "C" int b200mf_ctx_create(b200mf_ctx **out, const b200mf_ctx_desc *d) {
   c->n_cells = d->n_cells;
   c->n_dofs = d->n_dofs;
   c->n_owned = d->n_owned;
-  // default: the reference's serial order update_ghost_values -> cells -> compress(add).  Hiding the exchanges behind the
-  // interior cells (b200mf_ctx_set_overlap(ctx, 1) / B200MF_OVERLAP=1) is implemented and parity-tested but measures
-  // ~60 us slower per vmult at 2 and 8 ranks on B200 today (three persistent launches instead of one)
-  c->overlap = getenv("B200MF_OVERLAP") ? atoi(getenv("B200MF_OVERLAP")) : 0;
+  // exchange schedule of vmult on a partitioned context: 0 = the reference's serial order update_ghost_values -> cells ->
+  // compress(add); 1 = exchanges on a second stream behind the interior cells.  b200mf_ctx_set_partitioner picks the
+  // default (1 with the peer-to-peer exchange, 0 with NCCL send/recv, comm.cu); b200mf_ctx_set_overlap overrides it
+  c->overlap = 0;
   const int N = c->N, N2 = N * N, N3 = N2 * N, NC = c->NC;
   c->cpg = group_cells(N, NC);
   c->L = c->cpg * N2;

@@ -407,6 +407,10 @@ extern "C" int b200mf_ctx_set_partitioner(b200mf_ctx *c, b200mf_comm *comm, cons
   B2_CUDA(cudaMalloc(&p->buf_recv, std::max<size_t>(8, ridx.size() * es)));
   B2_TRY(setup_p2p(c, p.get()));
   if (c->part) free_partitioner(c);
+  // with the peer-to-peer exchange the overlapped schedule (interior cells behind the exchanges) pays: measured on B200,
+  // Q3, 5e7 DoF per GPU: 1.425 vs 1.480 ms at 2 ranks, 1.437 vs 1.499 ms at 4 (profiles/r02_scale*.json); with NCCL
+  // send/recv it does not (round 1), so the serial order stays the default there
+  c->overlap = getenv("B200MF_OVERLAP") ? atoi(getenv("B200MF_OVERLAP")) : (p->p2p ? 1 : 0);
   c->part = p.release();
   return 0;
 }

@@ -46,9 +46,20 @@ int run_laplace<TT>(const b200mf_ctx *ctx, bool diag, const TT *src, TT *dst, co
     if (diag)
       rc = affine ? launch_cell_loop<T, N, LaplaceAffineOp<T, N>, true>(ctx, (const T *)nullptr, dst, oa)
                   : launch_cell_loop<T, N, LaplaceOp<T, N>, true>(ctx, (const T *)nullptr, dst, oa);
-    else
-      rc = affine ? launch_cell_loop<T, N, LaplaceAffineOp<T, N>>(ctx, src, dst, oa, g0, g1, stream, dot)
-                  : launch_cell_loop<T, N, LaplaceOp<T, N>>(ctx, src, dst, oa, g0, g1, stream, dot);
+    else if (affine) {
+      // N <= 5: one warp per cell group with stacked columns (scalar_kernel.cuh); B200MF_SCALAR_STACK=0 keeps the generic kernel
+      static const bool stack = !(getenv("B200MF_SCALAR_STACK") && atoi(getenv("B200MF_SCALAR_STACK")) == 0);
+      // measured on B200 (profiles/r02_laplace_stack_ab.jsonl): 1.48x at Q4 FP64, +8 % at Q3 FP32, slower at Q2 / Q3 FP64
+      if constexpr (N == 5 || (N == 4 && sizeof(T) == 4)) {
+        if (stack)
+          rc = launch_scalar_stack<T, N, LaplaceAffineOp<T, N>>(ctx, src, dst, oa, g0, g1, stream, dot);
+        else
+          rc = launch_cell_loop<T, N, LaplaceAffineOp<T, N>>(ctx, src, dst, oa, g0, g1, stream, dot);
+      } else {
+        rc = launch_cell_loop<T, N, LaplaceAffineOp<T, N>>(ctx, src, dst, oa, g0, g1, stream, dot);
+      }
+    } else
+      rc = launch_cell_loop<T, N, LaplaceOp<T, N>>(ctx, src, dst, oa, g0, g1, stream, dot);
   });
   return rc;
 }

@@ -4,6 +4,7 @@
 #include <cstdlib>
 
 #include "kernels.h"
+#include "scalar_kernel.cuh"
 
 #ifndef B200MF_MINB5
 #define B200MF_MINB5 6
@@ -110,6 +111,54 @@ static int launch_cell_loop(const b200mf_ctx *ctx, const T *src, T *dst, const t
 #endif
     return launch_variant<T, N, Op, DIAG, GPB, MINBW>(ctx, src, dst, oa, g0, g1, stream, dot);
   }
+}
+
+// ---- scalar operator on affine cells, N <= 5: one warp per cell group, stacked columns (scalar_kernel.cuh) ----------
+template <typename T, int N, class Op>
+static int launch_scalar_stack(const b200mf_ctx *ctx, const T *src, T *dst, const typename Op::Args &oa, int64_t g0, int64_t g1,
+                               cudaStream_t stream, double *dot) {
+  using G = StackGeom<T, N>;
+  constexpr int WPB = 2;
+  if (g1 < 0) g1 = ctx->n_groups;
+  if (!stream) stream = ctx->stream;
+  B2_TRY(ensure_shape_constants());
+  const size_t smem = WPB * G::WARP_BYTES;
+  static int occ[2] = {0, 0};
+  const int di = dot != nullptr;
+  auto k0 = scalar_stack_kernel<T, N, Op, WPB, false>;
+  auto k1 = scalar_stack_kernel<T, N, Op, WPB, true>;
+  if (occ[di] == 0) {
+    if (di) {
+      B2_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      B2_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[di], k1, 32 * WPB, smem));
+    } else {
+      B2_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      B2_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[di], k0, 32 * WPB, smem));
+    }
+    if (occ[di] < 1) return set_error(B200MF_ERR_CUDA, "stacked scalar kernel does not fit on an SM (N=%d, %zu B shared)", N, smem);
+  }
+  if (g1 <= g0) return 0;
+  CellArgs<T> A;
+  A.group_begin = g0;
+  A.n_groups = g1;
+  A.nidx = ctx->nidx;
+  A.src = src;
+  A.dst = dst;
+  A.cstride = ctx->cstride;
+  A.dot = dot;
+  const int64_t n_super = (g1 - g0 + G::GW - 1) / G::GW;
+  const int64_t want = (n_super + WPB - 1) / WPB, cap = (int64_t)ctx->sm_count * occ[di];
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min(want, cap));
+  B2_TRY(kernel_event(const_cast<b200mf_ctx *>(ctx), stream));
+  if (di)
+    k1<<<grid, 32 * WPB, smem, stream>>>(A, oa);
+  else
+    k0<<<grid, 32 * WPB, smem, stream>>>(A, oa);
+  B2_LAUNCHED();
+  B2_TRY(kernel_event(const_cast<b200mf_ctx *>(ctx), stream));
+  return 0;
 }
 
 #ifdef B200MF_ONLY_N  // tuning builds: instantiate one degree only

@@ -236,9 +236,10 @@ struct CGResult {
   std::vector<double> diag, offdiag;  // Lanczos tridiagonal (connect_eigenvalues_slot)
 };
 
+// reduction > 0: ReductionControl - also converged once the residual has dropped to reduction * (initial residual)
 template <typename T>
 static int cg_solve_t(LinOp &A, const CGPrecond &P, T *x, const T *b, double tol, int max_it, bool iteration_number_control,
-                      bool x_is_zero, void *const work[3], Scratch &sc, CGResult &res) {
+                      bool x_is_zero, void *const work[3], Scratch &sc, CGResult &res, double reduction = 0.0) {
   b200mf_ctx *c = A.ctx;
   const int64_t n = c->n_int;
   T *r = (T *)work[0], *p = (T *)work[1], *v = (T *)work[2];
@@ -259,6 +260,7 @@ static int cg_solve_t(LinOp &A, const CGPrecond &P, T *x, const T *b, double tol
   B2_TRY(fetch(c, sc, 1));
   double res_norm = std::sqrt(std::fabs(sc.h[0]));
   res.initial_residual = res_norm;
+  if (reduction > 0.0) tol = std::max(tol, reduction * res_norm);
   double rPr = 0.0, alpha = 0.0, beta = 0.0;
   int it = 0;
   auto done = [&](int step, double val) {
@@ -921,6 +923,12 @@ struct b200mf_mg {
   std::vector<b200mf_mg_transfer *> transfer; // [level-1]: level-1 <-> level
   std::vector<void *> defect, solution, t;
   b200mf_ctx *outer;  // context of the (FP64) system vectors handed to vmult
+  // coarse grid: 0 = the level-0 smoother as solver (MGCoarseGridApplySmoother), 1 = SolverCG under a ReductionControl,
+  // preconditioned with the level-0 smoother (MGCoarseGridIterativeSolver, mf_elasticity.h:1183-1198)
+  int coarse_kind = 0, coarse_max_it = 100, coarse_last_iterations = 0;
+  double coarse_abs_tol = 1e-10, coarse_reduction = 1e-3;
+  void *coarse_work[3] = {nullptr, nullptr, nullptr};
+  Scratch coarse_sc;
 };
 
 extern "C" int b200mf_mg_create(b200mf_mg **out, int n_levels, b200mf_chebyshev *const *smoothers, b200mf_mg_transfer *const *transfers,
@@ -956,16 +964,45 @@ extern "C" int b200mf_mg_destroy(b200mf_mg *mg) {
   for (void *p : mg->defect) cudaFree(p);
   for (void *p : mg->solution) cudaFree(p);
   for (void *p : mg->t) cudaFree(p);
+  for (void *p : mg->coarse_work) cudaFree(p);
   delete mg;
   return 0;
 }
+
+extern "C" int b200mf_mg_set_coarse_solver(b200mf_mg *mg, int kind, int max_iterations, double abs_tolerance, double reduction) {
+  if (!mg || kind < 0 || kind > 1) return set_error(B200MF_ERR_ARG, "bad argument");
+  mg->coarse_kind = kind;
+  if (kind == 1) {
+    mg->coarse_max_it = max_iterations;
+    mg->coarse_abs_tol = abs_tolerance;
+    mg->coarse_reduction = reduction;
+    for (void *&p : mg->coarse_work)
+      if (!p) B2_TRY(vec_alloc(mg->smoother[0]->A.ctx, &p));
+  }
+  return 0;
+}
+extern "C" int b200mf_mg_coarse_iterations(const b200mf_mg *mg) { return mg ? mg->coarse_last_iterations : -1; }
 
 template <typename T>
 static int mg_level_v_step(b200mf_mg *mg, int level) {
   b200mf_chebyshev *sm = mg->smoother[level];
   b200mf_ctx *c = sm->A.ctx;
   T *sol = (T *)mg->solution[level], *def = (T *)mg->defect[level], *t = (T *)mg->t[level];
-  if (level == 0) return cheb_apply_t<T>(sm, sol, def, true);  // coarse: Chebyshev as solver
+  if (level == 0) {
+    if (mg->coarse_kind == 1) {  // SolverCG(ReductionControl) preconditioned with the level-0 smoother, start vector 0
+      CGPrecond P;
+      P.kind = 2;
+      P.apply = [sm](void *d, const void *s) { return cheb_apply_t<T>(sm, (T *)d, (const T *)s, true); };
+      CGResult r;
+      B2_CUDA(cudaMemsetAsync(sol, 0, c->n_int * sizeof(T), c->stream));
+      B2_TRY(cg_solve_t<T>(sm->A, P, sol, def, mg->coarse_abs_tol, mg->coarse_max_it, false, true, mg->coarse_work, mg->coarse_sc, r,
+                           mg->coarse_reduction));
+      mg->coarse_last_iterations = r.iterations;
+      if (!r.converged) return set_error(B200MF_ERR_NUMERIC, "MG coarse solver did not converge in %d iterations", r.iterations);
+      return 0;
+    }
+    return cheb_apply_t<T>(sm, sol, def, true);  // coarse: Chebyshev as solver
+  }
   B2_TRY(cheb_apply_t<T>(sm, sol, def, true));                  // pre-smoothing (zero start)
   B2_TRY(sm->A.vmult(t, sol));
   axpby_kernel<T><<<vgrid(c->n_int, c), 256, 0, c->stream>>>(c->n_int, T(1), def, T(-1), t);  // t = defect - A sol

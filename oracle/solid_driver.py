@@ -74,15 +74,19 @@ def interface_traction_rhs(mesh, total_displacement, traction, faces):
 
 def interface_traction_rhs_q1(mesh, total_displacement, traction_q, cells, face_no):
     """The same face loop (:1849-1897) for general Q1 cells (mapped boxes, the tube) and a traction given per face
-    quadrature point: traction_q [n_faces, nq^2, dim] (or one vector).  Face f = (cells[f], face_no[f] = 2*direction + side);
-    quadrature points of a face are ordered q = q_t1 + nq*q_t2 with the tangential directions t1 < t2.  3-D only."""
+    quadrature point: traction_q [n_faces, nq^2, dim], one vector, or a callable x -> t(x) evaluated at the quadrature
+    point's position in the reference configuration (what the coupling partner's mapped data is).  Face f = (cells[f],
+    face_no[f] = 2*direction + side); quadrature points of a face are ordered q = q_t1 + nq*q_t2 with the tangential
+    directions t1 < t2.  3-D only."""
     dim, p, n = mesh.dim, mesh.p, mesh.p + 1
     assert dim == 3
     xq, wq = NO.gauss(n)
     Vq, Dq = lagrange_table(p, xq)
     rhs = np.zeros(mesh.n_nodes * dim)
     u = total_displacement.reshape(mesh.n_nodes, dim)
-    traction_q = np.asarray(traction_q, dtype=float)
+    tfun = traction_q if callable(traction_q) else None
+    if tfun is None:
+        traction_q = np.asarray(traction_q, dtype=float)
     aidx = mesh.loc_ijk
     for f, (c, fn) in enumerate(zip(cells, face_no)):
         d, side = fn // 2, fn % 2
@@ -103,12 +107,14 @@ def interface_traction_rhs_q1(mesh, total_displacement, traction_q, cells, face_
                 xi = np.zeros(dim)
                 xi[d], xi[t1], xi[t2] = side, xq[q1], xq[q2]
                 J = np.zeros((dim, dim))  # dx_e / dxi_f
+                xpos = np.zeros(dim)
                 for m in range(8):
                     bits = [(m >> e) & 1 for e in range(dim)]
                     l = [xi[e] if bits[e] else 1 - xi[e] for e in range(dim)]
                     dl = [1.0 if bits[e] else -1.0 for e in range(dim)]
                     g = np.array([dl[0] * l[1] * l[2], l[0] * dl[1] * l[2], l[0] * l[1] * dl[2]])
                     J += np.outer(verts[m], g)
+                    xpos += l[0] * l[1] * l[2] * verts[m]
                 Jinv = np.linalg.inv(J)
                 nref = np.zeros(dim)
                 nref[d] = 1.0 if side else -1.0
@@ -118,7 +124,7 @@ def interface_traction_rhs_q1(mesh, total_displacement, traction_q, cells, face_
                 gradu = (grads @ uloc).T @ Jinv  # du_c/dx_e = sum_f dU_c/dxi_f dxi_f/dx_e
                 F = np.eye(dim) + gradu
                 n_star = np.linalg.det(F) * np.linalg.inv(F).T @ N
-                t = traction_q if traction_q.ndim == 1 else traction_q[f, q1 + n * q2]
+                t = np.asarray(tfun(xpos), dtype=float) if tfun is not None else (traction_q if traction_q.ndim == 1 else traction_q[f, q1 + n * q2])
                 t0 = t * np.linalg.norm(n_star)
                 contrib = np.outer(val, t0) * (wq[q1] * wq[q2] * dA)
                 np.add.at(rhs, (dim * mesh.cell_nodes[c][:, None] + np.arange(dim)[None, :]).ravel(), contrib.ravel())
@@ -128,7 +134,8 @@ def interface_traction_rhs_q1(mesh, total_displacement, traction_q, cells, face_
 class SolidOracle:
     def __init__(self, meshes, mu, nu, rho, delta_t, formulation=1, caching="tensor2", body_force=None, traction=None,
                  traction_faces=(), preconditioner="gmg", relaxation=0.65, tol_lin=1e-6, tol_f=1e-9, tol_u=1e-6,
-                 tol_f_abs=2e-9, tol_u_abs=5e-15, max_newton=10, n_cheb_cg=30, level_dtype=np.float32, max_cg_multiplier=1):
+                 tol_f_abs=2e-9, tol_u_abs=5e-15, max_newton=10, n_cheb_cg=30, level_dtype=np.float32, max_cg_multiplier=1,
+                 coarse_solver="chebyshev"):
         """meshes: level hierarchy (coarsest first, finest = active mesh) of StructuredMesh with clamp() applied"""
         self.meshes, self.mesh = meshes, meshes[-1]
         m = self.mesh
@@ -149,6 +156,7 @@ class SolidOracle:
         self.tol_f, self.tol_u, self.tol_f_abs, self.tol_u_abs, self.max_newton = tol_f, tol_u, tol_f_abs, tol_u_abs, max_newton
         self.n_cheb_cg, self.level_dtype = n_cheb_cg, level_dtype
         self.max_cg_multiplier = max_cg_multiplier  # 'Max iteration multiplier' (parameter_handling.h:203-207)
+        self.coarse_solver = coarse_solver  # 'MF Chebyshev coarse' (mf_elasticity.h:1147): "chebyshev" | "cg"
         self.cells = [self._cells(mm) for mm in meshes]
         n = m.n_nodes * self.dim
         self.con = m.constrained_dofs(self.dim)
@@ -172,7 +180,16 @@ class SolidOracle:
     # ---- assemble_residual -------------------------------------------------------------------
     def assemble_residual(self):
         rhs = NO.nh_residual(self.cells[-1], self.material, self.total, self.acceleration, self.body_force)
-        if self.traction is not None:
+        if self.traction is not None and (callable(self.traction) or self.mesh.mapping is not None):
+            cells, fno = [], []
+            for d, side in self.traction_faces:
+                on = np.flatnonzero(self.mesh.cell_ijk[:, d] == (0 if side == 0 else self.mesh.ncells[d] - 1))
+                cells += list(on)
+                fno += [2 * d + side] * on.size
+            t = interface_traction_rhs_q1(self.mesh, self.total, self.traction, cells, fno)
+            t[self.con] = 0.0
+            rhs += t
+        elif self.traction is not None:
             t = interface_traction_rhs(self.mesh, self.total, self.traction, self.traction_faces)
             t[self.con] = 0.0  # distribute_local_to_global skips constrained rows
             rhs += t
@@ -207,13 +224,16 @@ class SolidOracle:
 
             As.append(A)
             con = self.meshes[l].constrained_dofs(self.dim)
-            if l == 0:  # mf_elasticity.h:1154-1166: solver mode, accurate eigenvalues -> m() CG iterations
+            if l == 0 and self.coarse_solver == "chebyshev":  # mf_elasticity.h:1154-1166: solver mode, accurate eigenvalues -> m() CG iterations
                 sms.append(SO.PreconditionChebyshev(A, 1.0 / d, con, degree=SO.INVALID_UNSIGNED_INT, smoothing_range=1e-3,
                                                     eig_cg_n_iterations=d.size, dtype=T))
             else:       # :1168-1174
                 sms.append(SO.PreconditionChebyshev(A, 1.0 / d, con, degree=5, smoothing_range=20.0,
                                                     eig_cg_n_iterations=self.n_cheb_cg, dtype=T))
-        self.mg = SO.PreconditionMG(As, sms, self.transfers, dtype=T)
+        coarse_cg = None
+        if self.coarse_solver == "cg":  # MGCoarseGridIterativeSolver + ReductionControl(max(m(), 100), 1e-10, 1e-3), :1183-1198
+            coarse_cg = (max(self.meshes[0].n_nodes * self.dim, 100), 1e-10, 1e-3)
+        self.mg = SO.PreconditionMG(As, sms, self.transfers, dtype=T, coarse_cg=coarse_cg)
 
     def _A(self, dst, src):
         self.op.vmult(dst, src)

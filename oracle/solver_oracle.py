@@ -279,13 +279,22 @@ class MGTransfer:
 # ---------------------------------------------------------------------------
 # Multigrid V-cycle + PreconditionMG (A.7)
 class PreconditionMG:
-    def __init__(self, level_ops, smoothers, transfers, dtype=np.float64):
-        """level_ops[l](dst, src); smoothers[l] PreconditionChebyshev (l = 0: coarse solver); transfers[l-1]: l-1 <-> l"""
-        self.A, self.S, self.Tr, self.dtype = level_ops, smoothers, transfers, dtype
+    def __init__(self, level_ops, smoothers, transfers, dtype=np.float64, coarse_cg=None):
+        """level_ops[l](dst, src); smoothers[l] PreconditionChebyshev (l = 0: coarse solver); transfers[l-1]: l-1 <-> l.
+        coarse_cg = (max_it, abs_tol, reduction): MGCoarseGridIterativeSolver - SolverCG under a ReductionControl,
+        preconditioned with the level-0 smoother (mf_elasticity.h:1183-1198, 'MF Chebyshev coarse = false')."""
+        self.A, self.S, self.Tr, self.dtype, self.coarse_cg = level_ops, smoothers, transfers, dtype, coarse_cg
+        self.coarse_iterations = []
 
     def _v(self, level, defect):
         sol = np.zeros_like(defect)
         if level == 0:
+            if self.coarse_cg is not None:
+                max_it, abs_tol, reduction = self.coarse_cg
+                tol = max(abs_tol, reduction * float(np.linalg.norm(defect.astype(np.float64))))  # ReductionControl
+                r = solver_cg(self.A[0], sol, defect, self.S[0].vmult, tol, max_it, dtype=self.dtype)
+                self.coarse_iterations.append(r.iterations)
+                return sol
             self.S[0].vmult(sol, defect)
             return sol
         self.S[level].vmult(sol, defect)

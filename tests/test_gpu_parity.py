@@ -425,3 +425,66 @@ def test_nh_vmult_host_pipelined(p, ncells, numbering):
     ref = np.zeros_like(src)
     oracle_nh(m, u).vmult(ref, src)
     assert rel(out, ref) < TOL64
+
+
+@pytest.mark.parametrize("p", [5, 6])
+@pytest.mark.parametrize("level,formulation", [("tensor2", 1), ("scalar_referential", 1), ("tensor2", 0)])
+def test_nh_diagonal_high_degree(p, level, formulation):
+    """compute_diagonal at Q5/Q6 (sliced tables: the diagonal pass streams the q-planes once per component)."""
+    m = make_mesh(p, (2, 1, 1))
+    u = displacement(m)
+    d = oracle_nh(m, u, level, formulation).compute_diagonal()
+    mf, op = gpu_nh(m, u, level=level, formulation=formulation)
+    op.compute_diagonal()
+    assert rel(op.get_matrix_diagonal(), d) < TOL64
+    assert rel(op.get_matrix_diagonal_inverse(), 1.0 / d) < TOL64
+
+
+@pytest.mark.parametrize("p", [2, 4, 5])
+@pytest.mark.parametrize("level,formulation", VARIANTS)
+def test_nh_cache_tables_all_variants(p, level, formulation):
+    """cache() tables of every MF caching level against the numpy twin (mf_nh_operator.h:392-523), both table layouts
+    (plain for p <= 3, sliced for p >= 4): cached_scalar / cached_second_scalar / cached_tensor2 / cached_tensor4 / cached_tensor4_ns
+    and, for the deformed-frame levels, the metric J_cur = F J_ref."""
+    from common import np_cells
+    from oracle import np_oracle as NO
+
+    m = make_mesh(p, NCELLS[p])
+    u = displacement(m)
+    nq3 = (p + 1) ** 3
+    nop = NO.NeoHookOperator(np_cells(m), NO.Material(formulation=formulation, **MAT))
+    nop.initialize(u, level)
+    nop.cache()
+    mf, op = gpu_nh(m, u, level=level, formulation=formulation)
+    q = lambda i: op.qdata(i)  # noqa: E731
+    sym = [(0, 0), (1, 1), (2, 2), (0, 1), (0, 2), (1, 2)]
+    if formulation == 0:  # K (9), JxW, J^(-1/3), F (9)
+        K = np.stack([q(i) for i in range(9)], -1).reshape(m.n_cells, nq3, 3, 3)
+        assert rel(K, nop.invjac_cur) < TOL64 and rel(q(9), nop.JxW_cur) < TOL64
+        assert rel(q(10), nop.cached_scalar) < TOL64
+        F = np.stack([q(11 + i) for i in range(9)], -1).reshape(m.n_cells, nq3, 3, 3)
+        assert rel(F, nop.cached_tensor2) < TOL64
+    elif level == "tensor2":
+        assert rel(q(10), nop.cached_scalar) < TOL64 and rel(q(11), nop.cached_second_scalar) < TOL64
+        for s, (i, j) in enumerate(sym):
+            assert rel(q(12 + s), nop.cached_tensor2[..., i, j]) < 1e-11
+    elif level == "tensor4":  # K (9), JxW, c2, T (6), then the 6x6 table
+        assert rel(q(10), nop.cached_second_scalar) < TOL64
+        for s, (i, j) in enumerate(sym):
+            assert rel(q(11 + s), nop.cached_tensor2[..., i, j]) < 1e-11
+        for I, (i, j) in enumerate(sym):
+            for J, (k, l) in enumerate(sym):
+                assert np.abs(q(17 + I * 6 + J) - nop.cached_tensor4[..., i, j, k, l]).max() <= 1e-11 * np.abs(nop.cached_tensor4).max()
+    elif level == "tensor4_ns":  # reference metric is not a cached table: the 81 entries only
+        assert op_n_fields(op) == 81
+        A = np.stack([q(i) for i in range(81)], -1).reshape(m.n_cells, nq3, 3, 3, 3, 3)
+        assert np.abs(A - nop.cached_tensor4_ns).max() <= 1e-11 * np.abs(nop.cached_tensor4_ns).max()
+    else:  # scalar_referential: c = mu - 2 lambda ln J
+        assert op_n_fields(op) == 1
+        assert rel(q(0), nop.cached_scalar) < TOL64
+
+
+def op_n_fields(op):
+    from b200mf import lib as L_
+
+    return L_.load().b200mf_nh_n_qfields(op.h)

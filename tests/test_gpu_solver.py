@@ -240,3 +240,52 @@ def test_cg_reports_no_convergence():
     x, rhs = DeviceVector(mf), DeviceVector(mf, b)
     with pytest.raises(B200mfError, match="no convergence"):
         SolverCG(1e-14 * np.linalg.norm(b), 3).solve(op, x, rhs, None, x_is_zero=True)
+
+
+@pytest.mark.parametrize("level_dtype", ["f64", "f32"])
+def test_gmg_cg_with_cg_coarse_solver(level_dtype):
+    """'MF Chebyshev coarse = false' (mf_elasticity.h:1183-1198, 1217-1224): MGCoarseGridIterativeSolver - SolverCG under
+    ReductionControl(max(m(), 100), 1e-10, 1e-3) on level 0, preconditioned with the level-0 smoother (a degree-5 Chebyshev
+    smoother in this mode) - against the same option of the oracle's V-cycle."""
+    p = 2
+    meshes = hierarchy(p, (2, 2, 1), 3, 1, clamp=ALL_FACES)
+    m = meshes[-1]
+    # oracle: every level (level 0 included) gets the smoother parameters of the non-Chebyshev-coarse branch
+    As, sms_ref, trs_ref = [], [], []
+    for l, mm in enumerate(meshes):
+        _, A, inv = laplace_level(mm)
+        As.append(A)
+        con = mm.constrained_dofs(1)
+        sms_ref.append(SO.PreconditionChebyshev(A, inv, con, degree=5, smoothing_range=20.0, eig_cg_n_iterations=30))
+        if l > 0:
+            trs_ref.append(SO.MGTransfer(meshes[l - 1], mm, 1, meshes[l - 1].constrained_dofs(1), con))
+    n0 = meshes[0].n_nodes
+    mg_ref = SO.PreconditionMG(As, sms_ref, trs_ref, coarse_cg=(max(n0, 100), 1e-10, 1e-3))
+    b = np.random.default_rng(1).uniform(-1, 1, m.n_nodes)
+    b[m.constrained_dofs(1)] = 0
+    tol = 1e-10 * np.linalg.norm(b)
+    x_ref = np.zeros(m.n_nodes)
+    r_ref = SO.solver_cg(As[-1], x_ref, b, mg_ref.vmult, tol, 200)
+    # device
+    mfs, ops, sms, trs = [], [], [], []
+    for l, mm in enumerate(meshes):
+        mf, op = gpu_laplace_level(mm, level_dtype)
+        mfs.append(mf)
+        ops.append(op)
+        sms.append(PreconditionChebyshev(op, degree=5, smoothing_range=20.0, eig_cg_n_iterations=30))
+        if l > 0:
+            trs.append(MGTransferMatrixFree(mfs[l - 1], mf, children_of(meshes[l - 1])))
+    sys_mf = MatrixFree.from_mesh(m, 1)
+    sys_op = LaplaceOperator(sys_mf, 0.1)
+    mg = PreconditionMG(sms, trs, sys_mf)
+    mg.set_coarse_solver_cg(max(n0, 100), 1e-10, 1e-3)
+    x, rhs = DeviceVector(sys_mf), DeviceVector(sys_mf, b)
+    info = SolverCG(tol, 200).solve(sys_op, x, rhs, mg, x_is_zero=True)
+    assert info["converged"]
+    assert abs(info["iterations"] - r_ref.iterations) <= 1, (info, r_ref.iterations)
+    assert abs(mg.coarse_iterations() - mg_ref.coarse_iterations[-1]) <= 1
+    assert rel(x.download(), x_ref) < 1e-7
+    # back to the smoother-as-solver coarse grid: still converges
+    mg.set_coarse_solver_chebyshev()
+    x.set_zero()
+    assert SolverCG(tol, 200).solve(sys_op, x, rhs, mg, x_is_zero=True)["converged"]
