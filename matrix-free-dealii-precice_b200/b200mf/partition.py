@@ -37,7 +37,9 @@ class BrickPartition:
     """Local view of rank `rank` of a box of grid[0] x grid[1] x grid[2] bricks with nc^3 cells of degree p each
     (nc may be a 3-tuple).  The global box is [0, grid] scaled to `lower`/`upper`."""
 
-    def __init__(self, grid, nc, p, rank, ncomp=3, lower=(0.0, 0.0, 0.0), upper=None):
+    def __init__(self, grid, nc, p, rank, ncomp=3, lower=(0.0, 0.0, 0.0), upper=None, periodic0=False, mapping=None):
+        """periodic0: direction 0 is periodic (grid[0] must be 1: the periodic direction is never split), e.g. the angle of
+        the tube; mapping: vectorised map of the box vertices (b200mf.mesh.cylinder_shell_mapping), Q1 geometry inside a cell."""
         self.grid = tuple(int(g) for g in grid)
         self.nc = (int(nc),) * 3 if np.isscalar(nc) else tuple(int(c) for c in nc)
         self.p, self.rank, self.ncomp = int(p), int(rank), int(ncomp)
@@ -45,7 +47,9 @@ class BrickPartition:
         self.b = brick_of(rank, self.grid)
         p, nc, b, grid = self.p, self.nc, self.b, self.grid
         self.n = p + 1
-        self.nn_dir = tuple(c * p + 1 for c in nc)  # local node grid
+        self.periodic0, self.mapping = bool(periodic0), mapping
+        assert not periodic0 or self.grid[0] == 1, "the periodic direction must not be split"
+        self.nn_dir = tuple(c * p + (0 if (periodic0 and d == 0) else 1) for d, c in enumerate(nc))  # local node grid
         nn = self.nn_dir
         self.n_cells = int(np.prod(nc))
         self.n_local_nodes = int(np.prod(nn))
@@ -127,7 +131,10 @@ class BrickPartition:
         lex = np.zeros((self.n_cells, n**3), dtype=np.int64)
         stride = 1
         for d in range(3):
-            lex += (cidx[d][:, None] * p + loc[d][None, :]) * stride
+            g1 = cidx[d][:, None] * p + loc[d][None, :]
+            if periodic0 and d == 0:
+                g1 = g1 % nn[0]
+            lex += g1 * stride
             stride *= nn[d]
         self.cell_nodes = local_of_lex[lex]
         # vertices (global box coordinates)
@@ -137,7 +144,7 @@ class BrickPartition:
         for m in range(8):
             for d in range(3):
                 verts[:, m, d] = self.lower[d] + h[d] * (b[d] * nc[d] + cidx[d] + ((m >> d) & 1))
-        self.vertices = verts
+        self.vertices = verts if mapping is None else mapping(verts)
         self.material_id = np.zeros(self.n_cells, dtype=np.uint8)
         self.constrained_nodes = np.zeros((self.n_local_nodes, ncomp), dtype=bool)
         # the attributes b200mf.mesh.children_of needs (local cells are lexicographic, x fastest, like StructuredMesh)
@@ -148,7 +155,7 @@ class BrickPartition:
             ob = brick_of(r, grid)
             return int(np.prod([nn[k] - (1 if ob[k] > 0 else 0) for k in range(3)])) * ncomp
         self.first_global_dof = sum(owned_of(r) for r in range(self.rank))
-        self.n_global_dofs = int(np.prod([grid[k] * nc[k] * p + 1 for k in range(3)])) * ncomp
+        self.n_global_dofs = int(np.prod([grid[k] * nc[k] * p + (0 if (periodic0 and k == 0) else 1) for k in range(3)])) * ncomp
 
     # owned index (in brick ob's local numbering) of grid nodes oi=(ix,iy,iz) of that brick
     def _owned_index_in(self, ob, oi):
@@ -181,10 +188,21 @@ class BrickPartition:
     def global_lex_node(self):
         """index of every local node in a global StructuredMesh(grid*nc, p) (lexicographic, unpermuted)."""
         g = self.global_grid_index()
-        gn = [self.grid[d] * self.nc[d] * self.p + 1 for d in range(3)]
+        gn = [self.grid[d] * self.nc[d] * self.p + (0 if (self.periodic0 and d == 0) else 1) for d in range(3)]
         return (g[:, 2] * gn[1] + g[:, 1]) * gn[0] + g[:, 0]
 
     def node_coordinates(self):
+        if self.mapping is not None or self.periodic0:
+            # Q1 map of the (mapped) cell vertices at the GLL points, as StructuredMesh.node_coordinates
+            x1 = _gll(self.p)
+            lin = np.stack([1.0 - x1, x1], axis=1)
+            Nv = lin
+            for _ in range(2):
+                Nv = np.kron(lin, Nv)
+            coords = np.zeros((self.n_local_nodes, 3))
+            pts = np.einsum("am,cme->cae", Nv, self.vertices)
+            coords[self.cell_nodes.ravel()] = pts.reshape(-1, 3)
+            return coords
         g = self.global_grid_index()
         x1 = _gll(self.p)
         out = np.empty((self.n_local_nodes, 3))
@@ -229,3 +247,21 @@ class BrickPartition:
         return dict(ranks=ranks, send_offsets=np.asarray(send_off, dtype=np.int64),
                     send_indices=send_idx.astype(np.uint32), ghost_offsets=np.asarray(ghost_off, dtype=np.int64),
                     ghost_counts=np.asarray(ghost_cnt, dtype=np.int64))
+
+
+def tube_partitions(degree, first_refinement, n_levels, world, rank):
+    """Level hierarchy of the tube (b200mf.mesh.tube_hierarchy: 5 x 7 x 1 coarse cells, direction 0 = periodic angle, 1 = axis,
+    2 = radius) cut into `world` axial slabs, one per rank: refinement r has 7 * 2^r axial cells, so world = 8 needs
+    first_refinement >= 3.  Both ends clamped (tube_3d.h:47-63)."""
+    from .mesh import cylinder_shell_mapping
+
+    parts = []
+    for r in range(first_refinement, first_refinement + n_levels):
+        axial = 7 * 2**r
+        assert axial % world == 0, f"{axial} axial cells do not split into {world} slabs"
+        pt = BrickPartition((1, world, 1), (5 * 2**r, axial // world, 2**r), degree, rank, upper=(1.0, 1.0, 1.0), periodic0=True,
+                            mapping=cylinder_shell_mapping(5.0, 0.5, 0.6, 1e-2))
+        pt.clamp_global_face(1, 0)
+        pt.clamp_global_face(1, 1)
+        parts.append(pt)
+    return parts

@@ -158,6 +158,69 @@ def _newton_worker(rank, world, port, grid, p, levels, q):
         dist.destroy_process_group()
 
 
+def _tube_worker(rank, world, port, p, first_refinement, levels, q):
+    """The tube of cases/elasticity/tube_3d.h split into `world` axial slabs (periodic around the axis inside every rank)."""
+    import faulthandler
+    import sys as _sys
+
+    faulthandler.enable()
+    faulthandler.dump_traceback_later(150, exit=True, file=_sys.stderr)
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from b200mf import Communicator, MatrixFree
+        from b200mf.mesh import children_of, tube_pressure_traction
+        from b200mf.partition import tube_partitions
+        from b200mf.solid import Solid
+
+        comm = Communicator.from_torch_distributed()
+        parts = tube_partitions(p, first_refinement, levels, world, rank)
+        level_mf = [MatrixFree.from_partition(pt, comm, dtype="f32") for pt in parts]
+        sys_mf = MatrixFree.from_partition(parts[-1], comm)
+        sol = Solid(parts, mu=115384.0, nu=0.3, rho=1200.0, delta_t=1e-4, n_cheb_cg=30, matrix_frees=(sys_mf, level_mf),
+                    children=[children_of(pt) for pt in parts[:-1]], traction=tube_pressure_traction(5.0e4), traction_faces=((2, 0),))
+        sol.run(1)
+        fine = parts[-1]
+        g_owned = (3 * fine.global_lex_node()[:, None] + np.arange(3)[None, :]).reshape(-1)[:fine.n_owned]
+        q.put((rank, (g_owned, sol.total_displacement()[:fine.n_owned]), list(sol.newton_iterations), list(sol.cg_history)))
+    except BaseException:
+        import traceback
+        q.put((rank, traceback.format_exc(), None, None))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_distributed_tube_newton():
+    """BASELINE configs[3] in miniature on 2 GPUs: tube geometry (curved cells, periodic around the axis), interface traction
+    on the inner wall, GMG-preconditioned Newton step, against the one-GPU run of the same hierarchy."""
+    world, p, r0, levels = 2, 2, 1, 2
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    from b200mf.mesh import tube_hierarchy, tube_pressure_traction
+    from b200mf.solid import Solid
+
+    res = _spawn(world, _tube_worker, (p, r0, levels))
+    meshes = tube_hierarchy(p, levels, first_refinement=r0)
+    ref = Solid(meshes, mu=115384.0, nu=0.3, rho=1200.0, delta_t=1e-4, n_cheb_cg=30, traction=tube_pressure_traction(5.0e4),
+                traction_faces=((2, 0),))
+    ref.run(1)
+    u_ref = ref.total_displacement()
+    got = np.full_like(u_ref, np.nan)
+    for rank, (idx, val), newton, cg in res:
+        got[idx] = val
+        assert newton == ref.newton_iterations
+        assert max(abs(a - b) for a, b in zip(cg, ref.cg_history)) <= 1, (cg, ref.cg_history)
+    assert not np.isnan(got).any()
+    assert np.abs(got - u_ref).max() <= 1e-7 * np.abs(u_ref).max()
+
+
 @pytest.mark.parametrize("world,grid,p,levels", [(2, (2, 1, 1), 2, 2), (2, (2, 1, 1), 1, 3)])
 def test_distributed_newton_gmg(world, grid, p, levels):
     """BASELINE config 4 in miniature: the GMG-preconditioned Newton step on more than one GPU (per-level brick partitions,

@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[3]: tube3d-geometry neo-Hookean Newton step with GMG-Chebyshev on N GPUs (one axial slab per rank,
+NVLink ghost exchange).  Launch:
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 \
+      tools/bench_tube_multi.py --degree 3 --first 3 --levels 4
+The reference's hierarchy goes down to 35 cells (p4est leaves ranks empty on coarse levels); the brick partitioner keeps
+every level on every rank, so the coarsest level is refinement `--first` (>= 3 for 8 ranks) and the coarse-grid Chebyshev
+solver works on that level."""
+import argparse, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "matrix-free-dealii-precice_b200")):
+    sys.path.insert(0, p)
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--degree", type=int, default=3)
+ap.add_argument("--first", type=int, default=3)
+ap.add_argument("--levels", type=int, default=3)
+ap.add_argument("--pressure", type=float, default=5.0e4)
+ap.add_argument("--coarse", default="chebyshev", choices=["chebyshev", "cg"])
+a = ap.parse_args()
+world, rank, lr = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(lr)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+from b200mf import Communicator, MatrixFree, lib as L_
+from b200mf.mesh import children_of, tube_pressure_traction
+from b200mf.partition import tube_partitions
+from b200mf.solid import Solid
+
+comm = Communicator.from_torch_distributed()
+parts = tube_partitions(a.degree, a.first, a.levels, world, rank)
+level_mf = [MatrixFree.from_partition(pt, comm, dtype="f32") for pt in parts]
+sys_mf = MatrixFree.from_partition(parts[-1], comm)
+sol = Solid(parts, mu=115384.0, nu=0.3, rho=1200.0, delta_t=1e-4, n_cheb_cg=30, matrix_frees=(sys_mf, level_mf),
+            children=[children_of(pt) for pt in parts[:-1]], traction=tube_pressure_traction(a.pressure), traction_faces=((2, 0),),
+            coarse_solver=a.coarse)
+dist.barrier(); torch.cuda.synchronize()
+launches0 = L_.load().b200mf_launch_count()
+t0 = time.perf_counter()
+its = sol.solve_nonlinear_timestep()
+sol.advance_time_window()
+sol.mf.synchronize(); dist.barrier()
+t1 = time.perf_counter()
+# a second step: objects exist now
+t2 = time.perf_counter()
+its2 = sol.solve_nonlinear_timestep()
+sol.advance_time_window()
+sol.mf.synchronize(); dist.barrier()
+t3 = time.perf_counter()
+umax = torch.tensor([float(np.abs(sol.total_displacement()[:parts[-1].n_owned]).max())], device="cuda", dtype=torch.float64)
+dist.all_reduce(umax, op=dist.ReduceOp.MAX)
+if rank == 0:
+    fine = parts[-1]
+    n_newton2 = len(sol.cg_history) - its
+    print(json.dumps({"workload": f"tube3d Newmark step, neo-Hookean tensor2, Q{a.degree}, {fine.grid[1]} axial slabs of {fine.nc} curved cells, "
+                                  f"{fine.n_global_dofs} DoFs, levels r={a.first}..{a.first + a.levels - 1}, GMG-Chebyshev CG, coarse={a.coarse}",
+                      "n_gpus": world, "n_dofs": fine.n_global_dofs, "first_step_s": t1 - t0, "second_step_s": t3 - t2,
+                      "newton_iterations": [int(its), int(its2)], "cg_iterations": list(map(int, sol.cg_history)),
+                      "seconds_per_newton_iteration_step2": (t3 - t2) / max(1, n_newton2), "level0": sol.eig[0], "level_top": sol.eig[-1],
+                      "gpu_launches_rank0": int(L_.load().b200mf_launch_count() - launches0), "max_displacement": float(umax.item()),
+                      "exchange_path": "p2p" if sys_mf.exchange_is_p2p() else "nccl"}), flush=True)
+dist.barrier()
+dist.destroy_process_group()
