@@ -398,7 +398,7 @@ def parity_block(torch, dist, comm, world, rank, p):
             "checker": "oracle/mf_oracle.c on the undivided global mesh (test infrastructure; not on the measured path)"}
 
 
-def tube_block(stream_ptr, degree=3, levels=5, pressure=5.0e4):
+def tube_block(stream_ptr, degree=3, levels=5, pressure=5.0e3):
     """BASELINE.json configs[3] on ONE GPU: a Newmark step of the solid solver on the tube3d geometry (tube_3d.h:23-33, 74:
     cylinder shell, curved cells -> full per-q-point metric; ends clamped; pressure-like traction on the inner wall pulled back
     in every Newton iteration) with the reference's whole 35-coarse-cell multigrid hierarchy; every Newton iteration =
@@ -614,8 +614,15 @@ def main():
         if float(flags.item()) == 0.0:
             graph_ms = None
     loop_ms_rank = ms_rank
+    use_graph = False
     if graph_ms is not None:
-        ms_rank = graph_ms
+        # both are K vmults of the same library calls; report the faster execution mode (decided on the max over ranks): the
+        # graph wins when NCCL's proxy thread jitters (35 ms outlier steps at 8 ranks), the plain loop with the p2p exchange
+        t2 = torch.tensor([graph_ms, ms_rank], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        use_graph = float(t2[0].item()) < float(t2[1].item())
+        if use_graph:
+            ms_rank = graph_ms
     total_ms = ms_rank * args.steps
     if dist is not None:
         t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
@@ -762,9 +769,10 @@ def main():
             "run_to_run": run_to_run,
         }
         if world > 1:
-            line["timed_region"] = ("CUDA-graph replay of the K vmults (captured once, untimed)" if graph_ms is not None
+            line["timed_region"] = ("CUDA-graph replay of the K vmults (captured once, untimed)" if use_graph
                                     else "plain loop of K library calls") + "; step_ms_rank0 / kernel_ms are from the plain loop"
             line["ms_per_step_plain_loop_rank0"] = loop_ms_rank
+            line["ms_per_step_graph_replay_rank0"] = graph_ms
             line["exchange_path"] = "p2p (CUDA IPC push/pull kernels over NVLink)" if mf_p2p else "nccl send/recv"
         if parity:
             line["parity"] = parity

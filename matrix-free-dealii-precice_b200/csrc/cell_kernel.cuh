@@ -146,6 +146,9 @@ __host__ __device__ constexpr int group_threads(int N, int NC) { return (group_c
 #ifndef B200MF_EMPTY_MBAR
 #define B200MF_EMPTY_MBAR 0
 #endif
+#ifndef B200MF_PLANE_SPREAD
+#define B200MF_PLANE_SPREAD 0
+#endif
 // sliced kernels run the quadrature loop rolled (one small loop body, no load hoisting across planes: ~70 registers less)
 #ifndef B200MF_ROLLQ
 #define B200MF_ROLLQ 1
@@ -188,17 +191,20 @@ struct Layout {
   static constexpr int PL = P::PL;
   // plane task (cell, component, z-plane) of a lane: the enumeration is part of the bank-conflict-free layout (smem_pads.inc)
   static constexpr int ORD = P::ORD;
-  static constexpr int PLANE_LANES = ORD == 1 ? CPG * 16 : NT;  // lanes the tasks are spread over (with gaps for ORD 1)
+  // slot width of ORD 1: 16 lanes per cell (all tasks of two cells in one warp) or, tuning builds with B200MF_PLANE_SPREAD,
+  // 32 (one warp per cell: no warp idles during the plane phases, at 15 of 32 lanes each)
+  static constexpr int SLOT = B200MF_PLANE_SPREAD ? 32 : 16;
+  static constexpr int PLANE_LANES = ORD == 1 ? CPG * SLOT : NT;  // lanes the tasks are spread over (with gaps for ORD 1)
   static_assert(ORD != 1 || NC * N <= 16, "slot enumeration needs NC*N <= 16");
-  __host__ __device__ static constexpr bool task_valid(int t) { return ORD == 1 ? (t % 16) < NC * N && t / 16 < CPG : t < NT; }
+  __host__ __device__ static constexpr bool task_valid(int t) { return ORD == 1 ? (t % SLOT) < NC * N && t / SLOT < CPG : t < NT; }
   __host__ __device__ static constexpr int task_cell(int t) {
-    return ORD == 1 ? t / 16 : ORD == 2 ? (t / NC) % CPG : ORD == 3 ? t % CPG : t / (NC * N);
+    return ORD == 1 ? t / SLOT : ORD == 2 ? (t / NC) % CPG : ORD == 3 ? t % CPG : t / (NC * N);
   }
   __host__ __device__ static constexpr int task_comp(int t) {
-    return ORD == 1 ? (t % 16) / N : ORD == 2 ? t % NC : ORD == 3 ? t / (CPG * N) : (t / N) % NC;
+    return ORD == 1 ? (t % SLOT) / N : ORD == 2 ? t % NC : ORD == 3 ? t / (CPG * N) : (t / N) % NC;
   }
   __host__ __device__ static constexpr int task_plane(int t) {
-    return ORD == 1 ? (t % 16) % N : ORD == 2 ? t / (NC * CPG) : ORD == 3 ? (t / CPG) % N : t % N;
+    return ORD == 1 ? (t % SLOT) % N : ORD == 2 ? t / (NC * CPG) : ORD == 3 ? (t / CPG) % N : t % N;
   }
   static constexpr int ZCOMP = N * PL + P::CCZ, ZCELL = NC * ZCOMP + P::CZ;
   static constexpr int QFIELD = N * PL + P::FQ, QCOMP = 3 * QFIELD + P::CCQ, QCELL = NC * QCOMP + P::CQ;
@@ -786,12 +792,15 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
         // the values of the column (for d/dz): registers, or - rolled loop - re-read from shared memory in every plane
         // (N^2 instead of N loads per component, 2 N NC fewer live registers)
         constexpr bool VAL_REGS = !(SLICED && B200MF_ROLLQ) || B200MF_VAL_REGS;
+        // sliced kernels (multi-warp groups): a lane without a column only takes part in the slot hand-over - it must not
+        // mirror lane 0's shared-memory reads (a formal write-after-read hazard with lane 0's stores, compute-sanitizer)
+        const bool work = !SLICED || active;
         T val[NC][N];
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
 #pragma unroll
           for (int kq = 0; kq < N; ++kq) {
-            if (VAL_REGS) val[c][kq] = bufQ[qidx(c, 0, kq)];
+            if (VAL_REGS) val[c][kq] = work ? bufQ[qidx(c, 0, kq)] : T(0);
             racc[c][kq] = T(0);
           }
         }
@@ -803,21 +812,25 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
           T crow[N];
 #pragma unroll
           for (int m = 0; m < N; ++m) crow[m] = Sh::C(kq, m);
+          if (work) {
 #pragma unroll
-          for (int c = 0; c < NC; ++c) {
-            if constexpr (decltype(STATIC)::value)
-              v[c] = val[c][kq];
-            else
-              v[c] = bufQ[qidx(c, 0, kq)];
-            G[c][0] = bufQ[qidx(c, 1, kq)];
-            G[c][1] = bufQ[qidx(c, 2, kq)];
-            T acc = T(0);
+            for (int c = 0; c < NC; ++c) {
+              if constexpr (decltype(STATIC)::value)
+                v[c] = val[c][kq];
+              else
+                v[c] = bufQ[qidx(c, 0, kq)];
+              G[c][0] = bufQ[qidx(c, 1, kq)];
+              G[c][1] = bufQ[qidx(c, 2, kq)];
+              T acc = T(0);
 #pragma unroll
-            for (int m = 0; m < N; ++m) acc += crow[m] * (VAL_REGS ? val[c][m] : bufQ[qidx(c, 0, m)]);
-            G[c][2] = acc;
+              for (int m = 0; m < N; ++m) acc += crow[m] * (VAL_REGS ? val[c][m] : bufQ[qidx(c, 0, m)]);
+              G[c][2] = acc;
+            }
           }
           q_acquire(kq);
-          if (pre) {
+          if (!work) {
+            // hand-over only
+          } else if (pre) {
             Op::quad_pre(oa, st, active, q1p, scr, group, kq, lane, v, G);
           } else {
             Op::quad(oa, st, active, q1p, q2p, scr, group, kq, lane, v, G, ov, oG);
@@ -843,7 +856,7 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
             }
           }
           if constexpr (!decltype(STATIC)::value) {
-            if (Op::INTEGRATE && !pre) {  // racc[c][kq] += ov[c] with a run-time kq: one uniform branch instead of N selects per component
+            if (Op::INTEGRATE && !pre && work) {  // racc[c][kq] += ov[c] with a run-time kq: one uniform branch instead of N selects per component
               switch (kq) {
 #define B2_OV_CASE(M)                                     \
   case M:                                                 \
@@ -948,6 +961,7 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
           if (has_next) gather(nid_next, u_pg);
         }
         // ---- B1 (column): z sweep back + scatter-add -------------------------------------------
+        if (!SLICED || active)
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           T col[N], o[N];

@@ -185,3 +185,42 @@ def test_gloo_world2_vmult():
     for rank, err, dot, ref in res:
         assert err < 1e-13
         assert abs(dot - ref) < 1e-12 * ref
+
+
+@pytest.mark.parametrize("world,p", [(2, 2), (4, 1)])
+def test_tube_partition_matches_global_periodic_mesh(world, p):
+    """Axial slabs of the tube (cases/elasticity/tube_3d.h geometry; direction 0 periodic inside every rank): local nodes,
+    coordinates and cell connectivity agree with the undivided periodic mesh, every global node is owned exactly once, and
+    what a rank sends is what its neighbour expects as ghosts."""
+    from b200mf.mesh import tube_hierarchy
+    from b200mf.partition import tube_partitions
+
+    r = 2 if world == 4 else 1
+    g = tube_hierarchy(p, 1, first_refinement=r)[0]
+    gc = g.node_coordinates()
+    owner = np.full(g.n_nodes, -1)
+    parts = [tube_partitions(p, r, 1, world, rank)[0] for rank in range(world)]
+    for rank, pt in enumerate(parts):
+        gl = pt.global_lex_node()
+        assert np.allclose(pt.node_coordinates(), gc[gl])
+        assert (owner[gl[:pt.n_owned_nodes]] == -1).all()
+        owner[gl[:pt.n_owned_nodes]] = rank
+        axial = pt.nc[1]
+        for c in range(pt.n_cells):
+            i, j, k = pt.cell_ijk[c]
+            gcell = (k * g.ncells[1] + (j + axial * rank)) * g.ncells[0] + i
+            assert (gl[pt.cell_nodes[c]] == g.cell_nodes[gcell]).all()
+        # clamped ends: first and last rank only
+        con = pt.constrained_nodes[:, 0]
+        assert con.any() == (rank in (0, world - 1))
+        assert (g.constrained_nodes[gl, 0] == con).all()
+    assert (owner >= 0).all()
+    for rank, pt in enumerate(parts):
+        gl = pt.global_lex_node()
+        for nb in pt.neighbors:
+            other = parts[nb["rank"]]
+            back = [o for o in other.neighbors if o["rank"] == rank][0]
+            sent = gl[nb["send_nodes"]]
+            expect = other.global_lex_node()[back["ghost_start"]:back["ghost_start"] + back["ghost_count"]]
+            assert (np.sort(sent) == np.sort(expect)).all() and (sent == expect).all()
+    assert sum(pt.n_owned for pt in parts) == 3 * g.n_nodes == parts[0].n_global_dofs
