@@ -425,8 +425,18 @@ def tube_block(stream_ptr, degree=3, levels=5, pressure=5.0e3):
                         f"{3 * m.n_nodes} DoFs, {levels} levels, GMG-Chebyshev CG, interface traction on {sol.face_op.cells.size} faces",
             "n_dofs": 3 * m.n_nodes, "time_step_s": t1 - t0, "newton_iterations": int(its), "cg_iterations": list(map(int, sol.cg_history)),
             "seconds_per_newton_iteration": (t1 - t0) / max(1, len(sol.cg_history)),
-            "gpu_launches": int(L_.load().b200mf_launch_count() - launches0), "max_displacement": float(np.abs(sol.total_displacement()).max()),
+            "gpu_launches": int(L_.load().b200mf_launch_count() - launches0), "mg_graph": mg_graph_note(sol.mg),
+            "max_displacement": float(np.abs(sol.total_displacement()).max()),
             "note": "first time step from rest: includes one-off allocations of the smoother / solver objects"}
+
+
+def mg_graph_note(mg):
+    """How the V-cycle's lower levels ran: kernels replayed from the recorded CUDA graph count in `gpu_launches` like single launches."""
+    if mg is None:
+        return None
+    gi = mg.graph_info()
+    gi["note"] = "levels 0..top_level of every V-cycle are one cudaGraphLaunch of launches_per_replay kernels; state 1 = replaying"
+    return gi
 
 
 def newton_block(stream_ptr, degree=3, coarse=5, levels=5, amplitude=0.01):
@@ -468,7 +478,7 @@ def newton_block(stream_ptr, degree=3, coarse=5, levels=5, amplitude=0.01):
                         f"{3 * m.n_nodes} DoFs, {levels} levels (FP32 levels under FP64 CG)",
             "n_dofs": 3 * m.n_nodes, "newton_step_s": t2 - t0, "update_matrix_free_s": t1 - t0, "cg_solve_s": t2 - t1,
             "cg_iterations": int(its), "gpu_launches": int(L_.load().b200mf_launch_count() - launches0),
-            "level0": sol.eig[0], "level_top": sol.eig[-1]}
+            "level0": sol.eig[0], "level_top": sol.eig[-1], "mg_graph": mg_graph_note(sol.mg)}
 
 
 FP64_PEAK_TFLOPS = 33.9  # measured on this pool's B200: independent DFMA chains, tools/microbench/fp64_pipes.cu -> profiles/r01_fp64_pipes.jsonl
@@ -527,6 +537,7 @@ def heat_block(torch, stream_ptr, degree=4, coarse=7, levels=5, dt=0.1):
     return {"workload": f"heat: backward-Euler (M + dt K), Q{degree}, cube {m.ncells[0]}^3 affine cells, {n} DoFs, {levels} levels, dt={dt}",
             "n_dofs": n, "time_step_s": t3 - t0, "assemble_rhs_s": t1 - t0, "diagonals_and_eigenvalues_s": t2 - t1,
             "cg_solve_s": t3 - t2, "cg_iterations": int(res["iterations"]), "residual": res["residual"],
+            "mg_graph": mg_graph_note(getattr(hp, "mg", None)),
             "system_vmult": {"ms": ms, "dofs_per_s": n / (ms * 1e-3),
                              "roofline": {"bound": "fp64", "achieved": tflops, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
                                           "frac": tflops / FP64_PEAK_TFLOPS, "flop_per_dof": flop_per_dof,

@@ -339,6 +339,13 @@ int b200mf_mg_destroy(b200mf_mg *mg);
  * 1e-10, 1e-3) */
 int b200mf_mg_set_coarse_solver(b200mf_mg *mg, int kind, int max_iterations, double abs_tolerance, double reduction);
 int b200mf_mg_coarse_iterations(const b200mf_mg *mg); /* CG iterations of the last coarse solve (kind 1) */
+/* Levels 0..top_level of the V-cycle are recorded once as a CUDA graph and replayed by every further b200mf_mg_vmult until a
+ * smoother is re-estimated or an operator/context of those levels is reconfigured (then recorded again).  Default: n_levels-2
+ * (everything below the finest level; those levels are launch-bound), -1 = plain launches (also: environment B200MF_MG_GRAPH=0).
+ * Not used with coarse solver kind 1 (its convergence check synchronises).  graph_info: state 0 = nothing recorded yet,
+ * 1 = replaying, -1 = recording failed and the levels run as plain launches; launches = kernels per replay. */
+int b200mf_mg_set_graph_levels(b200mf_mg *mg, int top_level);
+int b200mf_mg_graph_info(const b200mf_mg *mg, int *top_level, int *state, int64_t *records, int64_t *replays, int64_t *launches);
 int b200mf_mg_vmult(b200mf_mg *mg, void *dst_dvec, const void *src_dvec); /* system-context vectors (copy_to_mg / copy_from_mg inside) */
 
 /* ------------------------------------------------------------------------

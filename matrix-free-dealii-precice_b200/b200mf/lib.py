@@ -160,6 +160,8 @@ SIGNATURES = {
     "b200mf_mg_vmult": (_i32, [_vp, _vp, _vp]),
     "b200mf_mg_set_coarse_solver": (_i32, [_vp, _i32, _i32, _dbl, _dbl]),
     "b200mf_mg_coarse_iterations": (_i32, [_vp]),
+    "b200mf_mg_set_graph_levels": (_i32, [_vp, _i32]),
+    "b200mf_mg_graph_info": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "b200mf_cg_create_nh": (_i32, [_PP, _vp]),
     "b200mf_cg_create_laplace": (_i32, [_PP, _vp]),
     "b200mf_cg_destroy": (_i32, [_vp]),

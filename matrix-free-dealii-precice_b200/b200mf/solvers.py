@@ -113,6 +113,16 @@ class PreconditionMG:
     def coarse_iterations(self):
         return int(_l.load().b200mf_mg_coarse_iterations(self.h))
 
+    def set_graph_levels(self, top_level):
+        """Levels 0..top_level replayed from a CUDA graph (default n_levels-2; -1 = plain launches)."""
+        _l.check(_l.load().b200mf_mg_set_graph_levels(self.h, int(top_level)))
+
+    def graph_info(self):
+        top, state = C.c_int(), C.c_int()
+        rec, rep, ln = C.c_int64(), C.c_int64(), C.c_int64()
+        _l.check(_l.load().b200mf_mg_graph_info(self.h, C.byref(top), C.byref(state), C.byref(rec), C.byref(rep), C.byref(ln)))
+        return dict(top_level=top.value, state=state.value, records=rec.value, replays=rep.value, launches_per_replay=ln.value)
+
     def __del__(self):
         if getattr(self, "h", None):
             _l.load().b200mf_mg_destroy(self.h)

@@ -15,6 +15,7 @@ namespace b200mf {
 
 thread_local std::string g_last_error;
 std::atomic<int64_t> g_launches{0};
+std::atomic<uint64_t> g_config_epoch{1};
 
 int set_error(int code, const char *fmt, ...) {
   char buf[1024];
@@ -679,6 +680,7 @@ extern "C" int b200mf_ctx_create(b200mf_ctx **out, const b200mf_ctx_desc *d) {
 }
 
 extern "C" int b200mf_ctx_destroy(b200mf_ctx *c) {
+  g_config_epoch.fetch_add(1);
   if (!c) return 0;
   cudaFree(c->nidx);
   cudaFree(c->mref);
@@ -704,6 +706,7 @@ extern "C" int b200mf_ctx_destroy(b200mf_ctx *c) {
 }
 
 extern "C" int b200mf_ctx_set_stream(b200mf_ctx *c, void *s) {
+  g_config_epoch.fetch_add(1);
   if (!c) return set_error(B200MF_ERR_ARG, "null ctx");
   c->stream = (cudaStream_t)s;
   return 0;
@@ -715,6 +718,7 @@ extern "C" int b200mf_ctx_synchronize(b200mf_ctx *c) {
 }
 // Measurement aid (bench.py roofline): CUDA events on the launching stream around every cell-loop launch.
 extern "C" int b200mf_ctx_time_kernels(b200mf_ctx *c, int on) {
+  g_config_epoch.fetch_add(1);
   if (!c) return set_error(B200MF_ERR_ARG, "null ctx");
   if (c->kernel_events) {
     for (cudaEvent_t e : *c->kernel_events) cudaEventDestroy(e);
@@ -750,6 +754,7 @@ int kernel_event(b200mf_ctx *c, cudaStream_t s) {
 }
 }  // namespace b200mf
 extern "C" int b200mf_ctx_set_overlap(b200mf_ctx *c, int on) {
+  g_config_epoch.fetch_add(1);
   if (!c) return set_error(B200MF_ERR_ARG, "null ctx");
   c->overlap = on < 0 ? -1 : on ? 1 : 0;
   return 0;
@@ -882,6 +887,7 @@ static void nh_free_tables(b200mf_nh *op) {
 }
 
 extern "C" int b200mf_nh_destroy(b200mf_nh *op) {
+  g_config_epoch.fetch_add(1);
   if (!op) return 0;
   nh_free_tables(op);
   cudaFree(op->n_bad);
@@ -894,6 +900,7 @@ extern "C" int b200mf_nh_destroy(b200mf_nh *op) {
 }
 
 extern "C" int b200mf_nh_initialize(b200mf_nh *op, int caching) {
+  g_config_epoch.fetch_add(1);
   if (!op) return set_error(B200MF_ERR_ARG, "null op");
   if (caching < B200MF_CACHE_SCALAR_REFERENTIAL || caching > B200MF_CACHE_TENSOR4_NS)
     return set_error(B200MF_ERR_ARG, "Unknown caching");  // mf_nh_operator.h:385
@@ -982,6 +989,7 @@ extern "C" int b200mf_nh_cache(b200mf_nh *op, const void *disp, int64_t *n_bad_o
   unsigned long long bad = 0;
   B2_TRY(read_failure_count(c, op->n_bad, &bad));
   if (n_bad_out) *n_bad_out = (int64_t)bad;
+  if (op->cached != (bad == 0)) g_config_epoch.fetch_add(1);  // a recorded launch sequence must not outlive the tables' validity
   op->cached = (bad == 0);  // tables built from det F <= 0 must not be applied (the reference asserts, :430-435)
   op->have_diag = false;
   if (bad) return set_error(B200MF_ERR_NUMERIC, "det_F is not positive at %llu quadrature points", bad);  // :430-435
@@ -1546,6 +1554,7 @@ extern "C" int b200mf_laplace_create(b200mf_laplace **out, b200mf_ctx *ctx, doub
 }
 
 extern "C" int b200mf_laplace_destroy(b200mf_laplace *op) {
+  g_config_epoch.fetch_add(1);
   if (!op) return 0;
   cudaFree(op->coef);
   cudaFree(op->n_bad);
@@ -1559,6 +1568,7 @@ extern "C" int b200mf_laplace_destroy(b200mf_laplace *op) {
 
 extern "C" b200mf_ctx *b200mf_laplace_ctx(b200mf_laplace *op) { return op ? op->ctx : nullptr; }
 extern "C" int b200mf_laplace_set_delta_t(b200mf_laplace *op, double dt) {
+  g_config_epoch.fetch_add(1);
   if (!op) return set_error(B200MF_ERR_ARG, "null op");
   op->delta_t = dt;
   op->have_diag = false;

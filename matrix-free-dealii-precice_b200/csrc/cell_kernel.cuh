@@ -146,6 +146,13 @@ __host__ __device__ constexpr int group_threads(int N, int NC) { return (group_c
 #ifndef B200MF_EMPTY_MBAR
 #define B200MF_EMPTY_MBAR 0
 #endif
+// Sliced kernels, lanes without a column (lane >= L): 1 = they skip the plane body and only take part in the slot hand-over
+// (compute-sanitizer racecheck reports 0 hazards); 0 = they mirror lane 0's shared-memory reads and discard the values
+// (racecheck flags those reads against lane 0's later stores - harmless, and branch-free: Q4 0.551 vs 0.529, Q6 0.292 vs
+// 0.270 of HBM; Q5 0.455 vs 0.460); -1 = per degree what measured faster (guard for N = 6 only).  profiles/r02_racecheck.txt
+#ifndef B200MF_GUARD_IDLE
+#define B200MF_GUARD_IDLE -1
+#endif
 #ifndef B200MF_PLANE_SPREAD
 #define B200MF_PLANE_SPREAD 0
 #endif
@@ -379,7 +386,7 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
   using Ly = Layout<N, NC, sizeof(T) / 4>;
   using Sh = Shape<T, N>;
   using KS_ = KernelSmem<T, N, Op, DIAG>;
-  constexpr int N2 = Ly::N2, L = Ly::L, PL = Ly::PL, NT = Ly::NT;
+  constexpr int N2 = Ly::N2, L = Ly::L, PL = Ly::PL;
   constexpr bool WM = Ly::WARP_MODE;
   constexpr bool SLICED = Ly::SLICED;
   constexpr int RING = Ly::RING;
@@ -792,9 +799,10 @@ __global__ void __launch_bounds__(Layout<N, Op::NC>::TPG *GPB, MINB)
         // the values of the column (for d/dz): registers, or - rolled loop - re-read from shared memory in every plane
         // (N^2 instead of N loads per component, 2 N NC fewer live registers)
         constexpr bool VAL_REGS = !(SLICED && B200MF_ROLLQ) || B200MF_VAL_REGS;
-        // sliced kernels (multi-warp groups): a lane without a column only takes part in the slot hand-over - it must not
-        // mirror lane 0's shared-memory reads (a formal write-after-read hazard with lane 0's stores, compute-sanitizer)
-        const bool work = !SLICED || active;
+        // sliced kernels (multi-warp groups), B200MF_GUARD_IDLE: a lane without a column only takes part in the slot hand-over
+        // instead of mirroring lane 0's shared-memory reads
+        constexpr bool GUARD_IDLE = SLICED && (B200MF_GUARD_IDLE == 1 || (B200MF_GUARD_IDLE == -1 && N == 6));
+        const bool work = !GUARD_IDLE || active;
         T val[NC][N];
 #pragma unroll
         for (int c = 0; c < NC; ++c) {

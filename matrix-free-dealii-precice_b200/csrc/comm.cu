@@ -361,6 +361,7 @@ extern "C" int b200mf_comm_create(b200mf_comm **out, int rank, int world, const 
 }
 
 extern "C" int b200mf_comm_destroy(b200mf_comm *c) {
+  g_config_epoch.fetch_add(1);
   if (!c) return 0;
   if (g_nccl.lib) g_nccl.CommDestroy(c->comm);
   delete c;
@@ -368,6 +369,7 @@ extern "C" int b200mf_comm_destroy(b200mf_comm *c) {
 }
 
 extern "C" int b200mf_ctx_set_partitioner(b200mf_ctx *c, b200mf_comm *comm, const b200mf_partitioner_desc *d) {
+  g_config_epoch.fetch_add(1);
   if (!c || !comm || !d) return set_error(B200MF_ERR_ARG, "null argument");
   if (d->n_neighbors < 0) return set_error(B200MF_ERR_ARG, "bad n_neighbors");
   std::unique_ptr<b200mf_partitioner> p(new b200mf_partitioner());

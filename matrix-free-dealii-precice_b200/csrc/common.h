@@ -16,6 +16,9 @@ namespace b200mf {
 
 extern thread_local std::string g_last_error;
 extern std::atomic<int64_t> g_launches;
+// bumped by every call that changes what a recorded launch sequence would look like (streams, schedules, operator tables,
+// operator constants): captured CUDA graphs (multigrid coarse levels, solver.cu) are re-recorded when it moves
+extern std::atomic<uint64_t> g_config_epoch;
 
 int set_error(int code, const char *fmt, ...);
 

@@ -929,6 +929,17 @@ struct b200mf_mg {
   double coarse_abs_tol = 1e-10, coarse_reduction = 1e-3;
   void *coarse_work[3] = {nullptr, nullptr, nullptr};
   Scratch coarse_sc;
+  // Levels 0..graph_top of the V-cycle as one CUDA graph: they are launch-bound (hundreds of small kernels per cycle), the
+  // vectors they touch belong to this object and the host-side numbers that enter their launches (Chebyshev theta/delta/
+  // degree, operator constants) change only when the smoothers are re-estimated - the sequence is recorded once per such
+  // change (stamp) on a private stream and replayed on the contexts' stream by every further V-cycle.
+  int graph_top = -1;       // -1: off
+  int graph_state = 0;      // 0 = nothing recorded yet, 1 = replaying, -1 = recording failed (eager launches from then on)
+  bool graph_warm = false;  // the first cycle runs eagerly (lazy allocations of the operators and exchanges)
+  uint64_t graph_stamp = 0;
+  int64_t graph_launches = 0, graph_records = 0, graph_replays = 0;
+  cudaGraphExec_t graph_exec = nullptr;
+  cudaStream_t graph_stream = nullptr;
 };
 
 extern "C" int b200mf_mg_create(b200mf_mg **out, int n_levels, b200mf_chebyshev *const *smoothers, b200mf_mg_transfer *const *transfers,
@@ -956,6 +967,8 @@ extern "C" int b200mf_mg_create(b200mf_mg **out, int n_levels, b200mf_chebyshev 
   }
   if (smoothers[n_levels - 1]->A.ctx->n_int != outer->n_int)
     return set_error(B200MF_ERR_ARG, "MG: finest level and system context have different vector layouts");
+  const char *ge = getenv("B200MF_MG_GRAPH");  // 0: eager launches on every level
+  mg->graph_top = (ge && atoi(ge) == 0) ? -1 : n_levels - 2;
   *out = mg.release();
   return 0;
 }
@@ -965,6 +978,8 @@ extern "C" int b200mf_mg_destroy(b200mf_mg *mg) {
   for (void *p : mg->solution) cudaFree(p);
   for (void *p : mg->t) cudaFree(p);
   for (void *p : mg->coarse_work) cudaFree(p);
+  if (mg->graph_exec) cudaGraphExecDestroy(mg->graph_exec);
+  if (mg->graph_stream) cudaStreamDestroy(mg->graph_stream);
   delete mg;
   return 0;
 }
@@ -982,6 +997,100 @@ extern "C" int b200mf_mg_set_coarse_solver(b200mf_mg *mg, int kind, int max_iter
   return 0;
 }
 extern "C" int b200mf_mg_coarse_iterations(const b200mf_mg *mg) { return mg ? mg->coarse_last_iterations : -1; }
+
+extern "C" int b200mf_mg_set_graph_levels(b200mf_mg *mg, int top_level) {
+  if (!mg || top_level >= mg->n_levels) return set_error(B200MF_ERR_ARG, "bad argument");
+  mg->graph_top = top_level < 0 ? -1 : top_level;
+  mg->graph_stamp = 0;
+  if (mg->graph_state > 0) mg->graph_state = 0;
+  return 0;
+}
+extern "C" int b200mf_mg_graph_info(const b200mf_mg *mg, int *top_level, int *state, int64_t *records, int64_t *replays, int64_t *launches) {
+  if (!mg) return set_error(B200MF_ERR_ARG, "null argument");
+  if (top_level) *top_level = mg->graph_top;
+  if (state) *state = mg->graph_state;
+  if (records) *records = mg->graph_records;
+  if (replays) *replays = mg->graph_replays;
+  if (launches) *launches = mg->graph_launches;
+  return 0;
+}
+
+template <typename T>
+static int mg_level_v_step(b200mf_mg *mg, int level);
+
+static uint64_t stamp_mix(uint64_t h, uint64_t v) { return h ^ (v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2)); }
+static uint64_t stamp_bits(double x) {
+  uint64_t u;
+  memcpy(&u, &x, sizeof u);
+  return u;
+}
+
+// levels 0..level of the V-cycle (defect[level] -> solution[level]), replayed from a CUDA graph where possible
+template <typename T>
+static int mg_lower_levels(b200mf_mg *mg, int level) {
+  bool usable = level == mg->graph_top && mg->graph_state >= 0 && mg->coarse_kind == 0;
+  for (int l = 0; usable && l <= level; ++l) {
+    b200mf_chebyshev *sm = mg->smoother[l];
+    usable = sm->eig_ready && !sm->A.ctx->kernel_events;  // estimates synchronise; timed launches record events the graph would own
+  }
+  if (!usable || !mg->graph_warm) {
+    if (level == mg->graph_top) mg->graph_warm = true;
+    return mg_level_v_step<T>(mg, level);
+  }
+  uint64_t stamp = stamp_mix(g_config_epoch.load(), (uint64_t)level);
+  for (int l = 0; l <= level; ++l) {
+    b200mf_chebyshev *sm = mg->smoother[l];
+    const void *inv = nullptr;
+    B2_TRY(sm->A.inv_diag(&inv));
+    stamp = stamp_mix(stamp, stamp_bits(sm->theta));
+    stamp = stamp_mix(stamp, stamp_bits(sm->delta));
+    stamp = stamp_mix(stamp, (uint64_t)sm->degree);
+    stamp = stamp_mix(stamp, (uint64_t)(uintptr_t)inv);
+  }
+  stamp |= 1;
+  cudaStream_t run = mg->smoother[level]->A.ctx->stream;
+  if (mg->graph_exec && mg->graph_stamp == stamp) {
+    B2_CUDA(cudaGraphLaunch(mg->graph_exec, run));
+    g_launches.fetch_add(mg->graph_launches);
+    ++mg->graph_replays;
+    return 0;
+  }
+  // record: the levels' launches go to a private stream (the contexts' stream may be the legacy default stream, which cannot
+  // be captured); the graph is then launched on the contexts' stream, which orders it with the finer levels
+  if (mg->graph_exec) {
+    cudaGraphExecDestroy(mg->graph_exec);
+    mg->graph_exec = nullptr;
+  }
+  if (!mg->graph_stream) B2_CUDA(cudaStreamCreateWithFlags(&mg->graph_stream, cudaStreamNonBlocking));
+  const int64_t l0 = g_launches.load();
+  for (int l = 0; l <= level; ++l) mg->smoother[l]->A.ctx->stream = mg->graph_stream;
+  cudaError_t e = cudaStreamBeginCapture(mg->graph_stream, cudaStreamCaptureModeThreadLocal);
+  int rc = 0;
+  cudaGraph_t graph = nullptr;
+  if (e == cudaSuccess) {
+    rc = mg_level_v_step<T>(mg, level);
+    e = cudaStreamEndCapture(mg->graph_stream, &graph);
+  }
+  for (int l = 0; l <= level; ++l) mg->smoother[l]->A.ctx->stream = run;
+  const int64_t recorded = g_launches.load() - l0;
+  if (rc == 0 && e == cudaSuccess) e = cudaGraphInstantiate(&mg->graph_exec, graph, 0);
+  if (graph) cudaGraphDestroy(graph);
+  if (rc != 0 || e != cudaSuccess) {  // not fatal: these levels run as plain launches from now on (b200mf_mg_graph_info: state -1)
+    fprintf(stderr, "b200mf: multigrid levels 0..%d could not be recorded as a CUDA graph (%s); launching them one by one\n", level,
+            rc != 0 ? b200mf_last_error() : cudaGetErrorString(e));
+    cudaGetLastError();
+    mg->graph_exec = nullptr;
+    mg->graph_state = -1;
+    g_launches.fetch_add(-recorded);
+    return mg_level_v_step<T>(mg, level);
+  }
+  mg->graph_stamp = stamp;
+  mg->graph_launches = recorded;
+  mg->graph_state = 1;
+  ++mg->graph_records;
+  B2_CUDA(cudaGraphLaunch(mg->graph_exec, run));  // recording did not execute anything
+  return 0;
+}
 
 template <typename T>
 static int mg_level_v_step(b200mf_mg *mg, int level) {
@@ -1010,7 +1119,7 @@ static int mg_level_v_step(b200mf_mg *mg, int level) {
   b200mf_ctx *cc = mg->smoother[level - 1]->A.ctx;
   B2_CUDA(cudaMemsetAsync(mg->defect[level - 1], 0, cc->n_int * sizeof(T), cc->stream));
   B2_TRY(b200mf_mg_transfer_restrict_and_add(mg->transfer[level - 1], mg->defect[level - 1], t));
-  B2_TRY(mg_level_v_step<T>(mg, level - 1));
+  B2_TRY(mg_lower_levels<T>(mg, level - 1));
   B2_TRY(b200mf_mg_transfer_prolongate_and_add(mg->transfer[level - 1], sol, mg->solution[level - 1]));
   return cheb_apply_t<T>(sm, sol, def, false);  // post-smoothing (step)
 }

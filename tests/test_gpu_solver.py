@@ -141,6 +141,51 @@ def test_gmg_cg_laplace(level_dtype):
     assert info["converged"]
     assert abs(info["iterations"] - r_ref.iterations) <= 1, (info, r_ref.iterations)
     assert rel(x.download(), x_ref) < 1e-8
+    gi = mg.graph_info()  # the levels below the finest one ran from the recorded graph, not as single launches
+    assert gi["state"] == 1 and gi["top_level"] == len(meshes) - 2 and gi["replays"] >= info["iterations"] - 2, gi
+
+
+@pytest.mark.parametrize("level_dtype", ["f64", "f32"])
+def test_mg_graph_replay_equals_plain_launches(level_dtype):
+    """b200mf_mg_set_graph_levels: the V-cycle whose lower levels are replayed from a CUDA graph returns what the plainly
+    launched V-cycle returns (first cycle eager, second records, later ones replay), also after the smoothers are
+    re-estimated (new Chebyshev constants -> recorded again) and with the recording switched off and on again."""
+    p = 2
+    meshes = hierarchy(p, (1, 1, 1), 3, 1, clamp=ALL_FACES)
+    m = meshes[-1]
+    rng = np.random.default_rng(3)
+    mfs, ops, sms, trs = gmg_gpu_laplace(meshes, level_dtype)
+    sys_mf = MatrixFree.from_mesh(m, 1)
+    mg = PreconditionMG(sms, trs, sys_mf)
+    plain = PreconditionMG(sms, trs, sys_mf)
+    plain.set_graph_levels(-1)
+    tol = 1e-12 if level_dtype == "f64" else 2e-5
+    s, d, e = DeviceVector(sys_mf), DeviceVector(sys_mf), DeviceVector(sys_mf)
+    from b200mf import lib as _lib
+    for cycle in range(8):
+        if cycle == 4:  # new eigenvalue estimates on a changed operator
+            for op in ops:
+                op.set_delta_t(0.05)
+                op.compute_diagonal()
+            for sm in sms:
+                sm.estimate_eigenvalues()
+        if cycle == 6:
+            mg.set_graph_levels(-1)
+        if cycle == 7:
+            mg.set_graph_levels(len(meshes) - 2)
+        b = rng.uniform(-1, 1, m.n_nodes)
+        b[m.constrained_dofs(1)] = 0
+        s.upload(b)
+        n0 = _lib.load().b200mf_launch_count()
+        mg.vmult(d, s)
+        n1 = _lib.load().b200mf_launch_count()
+        plain.vmult(e, s)
+        n2 = _lib.load().b200mf_launch_count()
+        assert n1 - n0 == n2 - n1, (cycle, n1 - n0, n2 - n1)  # replays are accounted with the launches they stand for
+        assert rel(d.download(), e.download()) < tol, cycle
+    gi = mg.graph_info()
+    assert gi["state"] == 1 and gi["records"] >= 3 and gi["replays"] >= 3, gi
+    assert plain.graph_info()["records"] == 0
 
 
 def nh_level(m, u):
