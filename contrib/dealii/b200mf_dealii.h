@@ -664,4 +664,105 @@ namespace B200MF
     mutable PinnedStaging                                   staging;
     std::shared_ptr<dealii::DiagonalMatrix<VectorType>>     inverse_diagonal_entries, diagonal_entries;
   };
+
+  // The boundary faces with a given id as a library face set (b200mf_face_set_create): cell = position of (batch, lane) in the
+  // cell order of make_context, face number = deal.II's 2 * direction + side, Q1 vertices from the cell iterator (deal.II numbers
+  // hexahedron vertices lexicographically, vertex m at (m & 1, m >> 1 & 1, m >> 2 & 1)).  Face order = (face batch, lane): the
+  // order in which the reference walks them (mf_elasticity.h:1849-1897, heat_transfer.h:617-652, boundary_mass_operator.h:146-158).
+  template <int dim, typename Number>
+  b200mf_face_set *
+  make_face_set(const dealii::MatrixFree<dim, Number> &mf, b200mf_ctx *ctx, const dealii::types::boundary_id interface_id)
+  {
+    static_assert(dim == 3, "the device kernels are 3-D");
+    const unsigned int        n_lanes = dealii::VectorizedArray<Number>::size();
+    std::vector<std::int64_t> compact(mf.n_cell_batches() * n_lanes, -1); // batch * n_lanes + lane -> cell of the context
+    std::int64_t              running = 0;
+    for (unsigned int b = 0; b < mf.n_cell_batches(); ++b)
+      for (unsigned int l = 0; l < mf.n_active_entries_per_cell_batch(b); ++l)
+        compact[b * n_lanes + l] = running++;
+    std::vector<std::int64_t> cells;
+    std::vector<std::int32_t> face_no;
+    std::vector<double>       vertices;
+    for (unsigned int face = mf.n_inner_face_batches(); face < mf.n_inner_face_batches() + mf.n_boundary_face_batches(); ++face)
+      {
+        if (mf.get_boundary_id(face) != interface_id)
+          continue;
+        const auto &info = mf.get_face_info(face);
+        for (unsigned int l = 0; l < mf.n_active_entries_per_face_batch(face); ++l)
+          {
+            const unsigned int cell = info.cells_interior[l];
+            cells.push_back(compact[cell]);
+            face_no.push_back(info.interior_face_no);
+            const auto it = mf.get_cell_iterator(cell / n_lanes, cell % n_lanes);
+            for (unsigned int m = 0; m < 8; ++m)
+              for (unsigned int e = 0; e < 3; ++e)
+                vertices.push_back(it->vertex(m)[e]);
+          }
+      }
+    b200mf_face_set *fs = nullptr;
+    check(b200mf_face_set_create(&fs, ctx, cells.size(), cells.data(), face_no.data(), vertices.data()));
+    return fs;
+  }
+
+  // Drop-in for ::BoundaryProjector<dim> (include/adapter/boundary_projector.h:16-110), used by
+  // LaplaceProblem::evaluate_boundary_flux (heat_transfer.h:935-939): the boundary mass operator, its row-sum diagonal and the
+  // Jacobi-preconditioned CG all run inside b200mf_boundary_mass_project.
+  template <int dim>
+  class BoundaryProjector
+  {
+  public:
+    using VectorType = dealii::LinearAlgebra::distributed::Vector<double>;
+
+    BoundaryProjector(const dealii::types::boundary_id                       interface_id,
+                      std::shared_ptr<const dealii::MatrixFree<dim, double>> data_,
+                      b200mf_comm                                           *comm = nullptr)
+      : data(data_)
+    {
+      ctx = make_context<dim, 1, double>(*data, comm);
+      fs  = make_face_set<dim, double>(*data, ctx, interface_id);
+      check(b200mf_boundary_mass_create(&op, fs));
+    }
+    BoundaryProjector(const BoundaryProjector &) = delete;
+    BoundaryProjector &
+    operator=(const BoundaryProjector &) = delete;
+    ~BoundaryProjector()
+    {
+      b200mf_boundary_mass_destroy(op);
+      b200mf_face_set_destroy(fs);
+      b200mf_ctx_destroy(ctx);
+    }
+
+    void
+    project(VectorType &residual) // :86-110
+    {
+      DeviceVector        r(ctx);
+      std::vector<double> scratch;
+      r.upload(residual, scratch);
+      project(r);
+      r.download(residual, scratch);
+      residual.update_ghost_values(); // :109
+    }
+    void
+    project(DeviceVector &residual) // performance mode: the residual was assembled on the device
+    {
+      check(b200mf_boundary_mass_project(op, residual.data(), &last_iterations, nullptr));
+    }
+    int
+    last_step() const
+    {
+      return last_iterations;
+    }
+    b200mf_ctx *
+    context() const
+    {
+      return ctx;
+    }
+
+  private:
+    std::shared_ptr<const dealii::MatrixFree<dim, double>> data;
+    b200mf_ctx                                            *ctx = nullptr;
+    b200mf_face_set                                       *fs  = nullptr;
+    b200mf_boundary_mass                                  *op  = nullptr;
+    int                                                    last_iterations = 0;
+  };
 } // namespace B200MF

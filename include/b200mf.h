@@ -269,6 +269,31 @@ int b200mf_face_set_set_traction(b200mf_face_set *fs, const double *traction_q, 
  * :1899-1905, with b200mf_vec_compress_add and b200mf_vec_set_zero_constrained) */
 int b200mf_face_set_assemble_traction(b200mf_face_set *fs, void *rhs_dvec, const void *total_displacement_dvec);
 
+/* Heat solver on the same face sets (scalar context: the data of b200mf_face_set_set_traction has ONE component per face
+ * quadrature point, the heat flux read from the coupling partner).
+ * assemble_flux: rhs += scale * int_Gamma flux(q) phi dA - the interface faces of LaplaceProblem::assemble_rhs
+ * (include/heat_transfer/heat_transfer.h:617-652, scale = -delta_t); no compress(add) (the caller's :654). */
+int b200mf_face_set_assemble_flux(b200mf_face_set *fs, void *rhs_dvec, double scale);
+
+/* MatrixFreeOperators::BoundaryMassOperator (include/adapter/boundary_mass_operator.h): dst = int_Gamma u phi dA over the
+ * faces of the set (apply_add :137-161, with the ghost update and compress(add) of the reference inside; constrained rows
+ * act as the identity like every MatrixFreeOperators::Base operator).  compute_diagonal (:79-118) stores M_Gamma * 1 (the
+ * row sums - not the diagonal) and its inverse where the entry is positive; rows off the interface keep 0.
+ * restrict: dst = src on the locally owned DoFs of the faces, 0 elsewhere (include/adapter/boundary_projector.h:93-95).
+ * project (boundary_projector.h:86-110, called from LaplaceProblem::evaluate_boundary_flux, heat_transfer.h:935-939):
+ * residual <- solution of M_Gamma x = residual|Gamma by CG, ReductionControl(500, 0, 1e-12), PreconditionJacobi(0.8),
+ * start vector = residual; ghost values of the result updated.  B200MF_ERR_NUMERIC if CG does not converge. */
+typedef struct b200mf_boundary_mass b200mf_boundary_mass;
+int b200mf_boundary_mass_create(b200mf_boundary_mass **op, b200mf_face_set *fs); /* the face set must outlive the operator */
+int b200mf_boundary_mass_destroy(b200mf_boundary_mass *op);
+b200mf_ctx *b200mf_boundary_mass_ctx(b200mf_boundary_mass *op);
+int b200mf_boundary_mass_vmult(b200mf_boundary_mass *op, void *dst_dvec, const void *src_dvec);
+int b200mf_boundary_mass_vmult_add(b200mf_boundary_mass *op, void *dst_dvec, const void *src_dvec);
+int b200mf_boundary_mass_compute_diagonal(b200mf_boundary_mass *op);
+int b200mf_boundary_mass_diagonal(b200mf_boundary_mass *op, const void **diag_dvec, const void **inv_diag_dvec);
+int b200mf_boundary_mass_restrict(b200mf_boundary_mass *op, void *dst_dvec, const void *src_dvec);
+int b200mf_boundary_mass_project(b200mf_boundary_mass *op, void *residual_dvec, int *iterations, double *final_residual);
+
 b200mf_ctx *b200mf_nh_ctx(b200mf_nh *op);           /* the MatrixFree the operator was built on (data_in_use, :213) */
 b200mf_ctx *b200mf_laplace_ctx(b200mf_laplace *op); /* MatrixFreeOperators::Base::get_matrix_free */
 
@@ -369,6 +394,7 @@ typedef struct {
 } b200mf_cg_result;
 int b200mf_cg_create_nh(b200mf_cg **solver, b200mf_nh *op);
 int b200mf_cg_create_laplace(b200mf_cg **solver, b200mf_laplace *op);
+int b200mf_cg_create_boundary_mass(b200mf_cg **solver, b200mf_boundary_mass *op); /* boundary_projector.h:97-104 as separate calls */
 int b200mf_cg_destroy(b200mf_cg *solver);
 int b200mf_cg_solve(b200mf_cg *solver, void *x_dvec, const void *b_dvec, const b200mf_cg_control *control, b200mf_cg_result *result);
 

@@ -82,6 +82,46 @@ class HeatProblem:
         self.cg_history.append(res["iterations"])
         return res
 
+    # ---- coupling: interface faces of assemble_rhs (:617-652) and evaluate_boundary_flux (:899-940)
+    def setup_interface(self, faces):
+        """faces: (direction, side) pairs of the box that carry the coupling interface id.  Builds what the reference keeps
+        next to the constrained system: the unconstrained MatrixFree + `inhomogeneous_operator` (:586-592, :907), the face
+        set of the interface and the BoundaryMassOperator of the projector."""
+        import copy
+
+        from .operators import BoundaryMassOperator, InterfaceTraction
+
+        free = copy.copy(self.mesh)
+        free.constrained_nodes = None
+        self.mesh_inhom = free
+        self.mf_inhom = MatrixFree.from_mesh(free, 1)
+        self.inhomogeneous_operator = LaplaceOperator(self.mf_inhom, self.dt)
+        self.interface = InterfaceTraction(self.mf_inhom, free, faces)
+        self.boundary_mass = BoundaryMassOperator(self.interface)
+        W = lambda: DeviceVector(self.mf_inhom)  # noqa: E731
+        self.flux, self._u, self._uo = W(), W(), W()
+
+    def add_interface_flux(self, flux_q):
+        """Neumann participant (:617-652): system_rhs += int_Gamma (-flux(q) dt) phi dA with the flux read from the coupling
+        partner at the face quadrature points; call between the cell loop and compress (assemble_rhs(flux_q=...))."""
+        self.interface.set_traction(np.asarray(flux_q, dtype=np.float64).reshape(-1, 1) if np.size(flux_q) > 1 else np.array([float(flux_q)]))
+        self.interface.assemble_flux(self.system_rhs, -self.dt)
+
+    def evaluate_boundary_flux(self):
+        """Dirichlet participant (:899-940): residual = (A_inhom u - M (u_old + dt f)) / dt, L2-projected onto the interface
+        (BoundaryProjector).  Returns the device vector holding the nodal flux and the projector's CG record."""
+        r = self.flux
+        self._u.copy_from(self.solution)
+        self._uo.copy_from(self.solution_old)
+        self.inhomogeneous_operator.set_delta_t(self.dt)
+        self.inhomogeneous_operator.vmult(r, self._u)                                       # :907
+        r.sadd(-1.0, 0.0, self._u)                                                          # signs switched w.r.t. assemble_rhs (:905-906)
+        self.inhomogeneous_operator.assemble_rhs(r, self._uo, None, self.source_const)      # :916-931 (with + sign, see above)
+        r.compress_add()                                                                    # :932
+        r.sadd(-1.0 / self.dt, 0.0, self._u)                                                # :933
+        info = self.boundary_mass.project(r)                                                # :935-939
+        return r, info
+
     def time_step(self):
         """one pass of the time loop (:861-940): old <- solution, assemble, solve"""
         self.solution_old.sadd(0.0, 1.0, self.solution)

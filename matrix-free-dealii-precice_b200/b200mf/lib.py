@@ -136,6 +136,17 @@ SIGNATURES = {
     "b200mf_face_set_quadrature_points": (_i32, [_vp, _vp]),
     "b200mf_face_set_set_traction": (_i32, [_vp, _vp, _vp]),
     "b200mf_face_set_assemble_traction": (_i32, [_vp, _vp, _vp]),
+    "b200mf_face_set_assemble_flux": (_i32, [_vp, _vp, _dbl]),
+    "b200mf_boundary_mass_create": (_i32, [_PP, _vp]),
+    "b200mf_boundary_mass_destroy": (_i32, [_vp]),
+    "b200mf_boundary_mass_ctx": (_vp, [_vp]),
+    "b200mf_boundary_mass_vmult": (_i32, [_vp, _vp, _vp]),
+    "b200mf_boundary_mass_vmult_add": (_i32, [_vp, _vp, _vp]),
+    "b200mf_boundary_mass_compute_diagonal": (_i32, [_vp]),
+    "b200mf_boundary_mass_diagonal": (_i32, [_vp, _PP, _PP]),
+    "b200mf_boundary_mass_restrict": (_i32, [_vp, _vp, _vp]),
+    "b200mf_boundary_mass_project": (_i32, [_vp, _vp, C.POINTER(_i32), C.POINTER(_dbl)]),
+    "b200mf_cg_create_boundary_mass": (_i32, [_PP, _vp]),
     "b200mf_nh_ctx": (_vp, [_vp]),
     "b200mf_laplace_ctx": (_vp, [_vp]),
     "b200mf_vec_dot": (_i32, [_vp, _vp, _vp, C.POINTER(_dbl)]),

@@ -488,7 +488,59 @@ class InterfaceTraction:
             self.set_traction(traction)
         _l.check(_l.load().b200mf_face_set_assemble_traction(self.h, _dv(rhs), _dv(total_displacement)))
 
+    def assemble_flux(self, rhs, scale):
+        """Scalar (heat) context: rhs += scale * int_Gamma flux(q) phi dA with the flux given to set_traction, one value per
+        face quadrature point (heat_transfer.h:617-652: scale = -delta_t)."""
+        _l.check(_l.load().b200mf_face_set_assemble_flux(self.h, _dv(rhs), float(scale)))
+
     def __del__(self):
         if getattr(self, "h", None):
             _l.load().b200mf_face_set_destroy(self.h)
+            self.h = None
+
+
+class BoundaryMassOperator:
+    """MatrixFreeOperators::BoundaryMassOperator (include/adapter/boundary_mass_operator.h) on the faces of an
+    InterfaceTraction face set, and BoundaryProjector::project (include/adapter/boundary_projector.h:86-110)."""
+
+    def __init__(self, faces: InterfaceTraction):
+        self.faces, self.mf = faces, faces.mf
+        h = C.c_void_p()
+        _l.check(_l.load().b200mf_boundary_mass_create(C.byref(h), faces.h))
+        self.h = h
+
+    def vmult(self, dst, src):
+        _l.check(_l.load().b200mf_boundary_mass_vmult(self.h, _dv(dst), _dv(src)))
+
+    def vmult_add(self, dst, src):
+        _l.check(_l.load().b200mf_boundary_mass_vmult_add(self.h, _dv(dst), _dv(src)))
+
+    def compute_diagonal(self):
+        _l.check(_l.load().b200mf_boundary_mass_compute_diagonal(self.h))
+
+    def _diag(self, which):
+        d, i = C.c_void_p(), C.c_void_p()
+        _l.check(_l.load().b200mf_boundary_mass_diagonal(self.h, C.byref(d), C.byref(i)))
+        out = np.empty(self.mf.n_dofs, dtype=np.float64)
+        _l.check(_l.load().b200mf_vec_download_f64(self.mf.h, _ptr(out), C.c_void_p(d.value if which == 0 else i.value)))
+        return out
+
+    def diagonal(self):
+        return self._diag(0)
+
+    def inverse_diagonal(self):
+        return self._diag(1)
+
+    def restrict(self, dst, src):
+        _l.check(_l.load().b200mf_boundary_mass_restrict(self.h, _dv(dst), _dv(src)))
+
+    def project(self, residual):
+        """residual <- M_Gamma^-1 residual|Gamma (CG, ReductionControl(500, 0, 1e-12), Jacobi 0.8, start = residual)"""
+        its, res = C.c_int(), C.c_double()
+        _l.check(_l.load().b200mf_boundary_mass_project(self.h, _dv(residual), C.byref(its), C.byref(res)))
+        return dict(iterations=its.value, residual=res.value)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            _l.load().b200mf_boundary_mass_destroy(self.h)
             self.h = None

@@ -501,6 +501,14 @@ static LinOp linop_laplace(b200mf_laplace *op, b200mf_ctx *ctx) {
   return A;
 }
 
+static LinOp linop_boundary_mass(b200mf_boundary_mass *op) {
+  LinOp A;
+  A.ctx = b200mf_boundary_mass_ctx(op);
+  A.vmult = [op](void *d, const void *s) { return b200mf_boundary_mass_vmult(op, d, s); };
+  A.inv_diag = [op](const void **inv) { return b200mf_boundary_mass_diagonal(op, nullptr, inv); };
+  return A;
+}
+
 static int chebyshev_create(b200mf_chebyshev **out, LinOp A, const b200mf_chebyshev_data *d) {
   if (!out || !d) return set_error(B200MF_ERR_ARG, "null argument");
   if (d->degree == 0 || d->degree < -1) return set_error(B200MF_ERR_ARG, "Chebyshev degree must be >= 1 or -1 (solver mode)");
@@ -1180,6 +1188,10 @@ extern "C" int b200mf_cg_create_laplace(b200mf_cg **out, b200mf_laplace *op) {
   if (!op) return set_error(B200MF_ERR_ARG, "null op");
   return cg_create(out, linop_laplace(op, b200mf_laplace_ctx(op)));
 }
+extern "C" int b200mf_cg_create_boundary_mass(b200mf_cg **out, b200mf_boundary_mass *op) {
+  if (!op) return set_error(B200MF_ERR_ARG, "null op");
+  return cg_create(out, linop_boundary_mass(op));
+}
 extern "C" int b200mf_cg_destroy(b200mf_cg *s) {
   if (!s) return 0;
   for (void *p : s->w) cudaFree(p);
@@ -1217,6 +1229,39 @@ extern "C" int b200mf_cg_solve(b200mf_cg *s, void *x, const void *b, const b200m
   }
   if (!s->last.converged) return set_error(B200MF_ERR_NUMERIC, "SolverCG: no convergence after %d iterations (residual %g)", s->last.iterations, s->last.residual);
   return 0;
+}
+
+// BoundaryProjector::project (include/adapter/boundary_projector.h:86-110): L2 projection of a nodal residual onto the
+// interface - M_Gamma x = residual|Gamma by CG under ReductionControl(500, 0, 1e-12) with PreconditionJacobi(0.8), started
+// from x = residual (entries off the interface have a zero row, a zero right-hand side and a zero preconditioner: they keep
+// their value); the operator's compute_diagonal() runs inside, as in the reference; ghost values updated at the end.
+extern "C" int b200mf_boundary_mass_project(b200mf_boundary_mass *op, void *residual, int *iterations, double *final_residual) {
+  if (!op || !residual) return set_error(B200MF_ERR_ARG, "null argument");
+  LinOp A = linop_boundary_mass(op);
+  b200mf_ctx *c = A.ctx;
+  B2_TRY(b200mf_boundary_mass_compute_diagonal(op));
+  void *w[4] = {nullptr, nullptr, nullptr, nullptr};  // rhs + the three CG vectors
+  struct Free {
+    void **w;
+    ~Free() {
+      for (int i = 0; i < 4; ++i) cudaFree(w[i]);
+    }
+  } guard{w};
+  for (void *&p : w) B2_TRY(vec_alloc(c, &p));
+  B2_TRY(b200mf_boundary_mass_restrict(op, w[0], residual));
+  CGPrecond P;
+  P.kind = 1;
+  P.omega = 0.8;
+  B2_TRY(A.inv_diag(&P.inv));
+  Scratch sc;
+  CGResult r;
+  int rc = c->dtype == B200MF_F64 ? cg_solve_t<double>(A, P, (double *)residual, (const double *)w[0], 0.0, 500, false, false, w + 1, sc, r, 1e-12)
+                                  : cg_solve_t<float>(A, P, (float *)residual, (const float *)w[0], 0.0, 500, false, false, w + 1, sc, r, 1e-12);
+  B2_TRY(rc);
+  if (iterations) *iterations = r.iterations;
+  if (final_residual) *final_residual = r.residual;
+  if (!r.converged) return set_error(B200MF_ERR_NUMERIC, "BoundaryProjector: no convergence after %d iterations (residual %g)", r.iterations, r.residual);
+  return update_ghost_values(c, residual);
 }
 
 // ===========================================================================

@@ -1,4 +1,5 @@
 #pragma once
+#include <array>
 #include <deal.II/base/mpi.h>
 #include <deal.II/lac/la_parallel_vector.h>
 namespace dealii
@@ -28,10 +29,24 @@ namespace dealii
     const FiniteElementData &get_fe() const { return fe; }
     FiniteElementData        fe;
   };
+  namespace types
+  {
+    using boundary_id = unsigned int;
+  }
+  struct PointMock
+  {
+    double operator[](const unsigned int) const { return 0.0; }
+  };
   struct CellMock
   {
     unsigned int material_id() const { return 0; }
+    PointMock    vertex(const unsigned int) const { return PointMock(); }
     const CellMock *operator->() const { return this; }
+  };
+  struct FaceToCellTopologyMock // internal::MatrixFreeFunctions::FaceToCellTopology
+  {
+    std::array<unsigned int, 8> cells_interior{};
+    unsigned char               interior_face_no = 0;
   };
   template <int dim, typename Number>
   class MatrixFree
@@ -45,10 +60,16 @@ namespace dealii
     unsigned int n_active_entries_per_cell_batch(const unsigned int) const { return 0; }
     CellMock     get_cell_iterator(const unsigned int, const unsigned int) const { return CellMock(); }
     const std::vector<unsigned int> &get_constrained_dofs() const { return con; }
+    unsigned int n_inner_face_batches() const { return 0; }
+    unsigned int n_boundary_face_batches() const { return 0; }
+    unsigned int n_active_entries_per_face_batch(const unsigned int) const { return 0; }
+    types::boundary_id get_boundary_id(const unsigned int) const { return 0; }
+    const FaceToCellTopologyMock &get_face_info(const unsigned int) const { return fi; }
 
   private:
     DoFHandlerMock                                     dh;
     std::shared_ptr<const Utilities::MPI::Partitioner> part;
     std::vector<unsigned int>                          con;
+    FaceToCellTopologyMock                             fi;
   };
 } // namespace dealii

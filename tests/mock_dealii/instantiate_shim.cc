@@ -44,4 +44,9 @@ void use()
   lap.compute_diagonal();
   lap.set_delta_t(0.2);
   (void)lap.m();
+  std::shared_ptr<const dealii::MatrixFree<3, double>> mfd;
+  B200MF::BoundaryProjector<3> projector(7, mfd);
+  projector.project(u);
+  projector.project(d);
+  (void)projector.last_step();
 }

@@ -162,6 +162,7 @@ def test_mg_graph_replay_equals_plain_launches(level_dtype):
     tol = 1e-12 if level_dtype == "f64" else 2e-5
     s, d, e = DeviceVector(sys_mf), DeviceVector(sys_mf), DeviceVector(sys_mf)
     from b200mf import lib as _lib
+    plain.vmult(e, s)  # the smoothers' lazy eigenvalue estimates run in the first application: keep them out of the counts
     for cycle in range(8):
         if cycle == 4:  # new eigenvalue estimates on a changed operator
             for op in ops:

@@ -214,3 +214,75 @@ def test_simd_over_cells_vmult_equals_scalar_loop(p):
     op4.initialize(displacement(m), "tensor4")
     op4.cache()
     assert not op4.vmult_simd(b, src)
+
+
+# ---------------------------------------------------------------------------
+# heat coupling faces: BoundaryMassOperator / BoundaryProjector / flux faces (oracle/boundary_oracle.py)
+def _interface_faces(m, faces):
+    cells, fno = [], []
+    for d, side in faces:
+        on = np.flatnonzero(m.cell_ijk[:, d] == (0 if side == 0 else m.ncells[d] - 1))
+        cells.append(on)
+        fno.append(np.full(on.size, 2 * d + side))
+    return np.concatenate(cells), np.concatenate(fno)
+
+
+@pytest.mark.parametrize("p", [1, 2, 3])
+def test_boundary_mass_oracle_closed_forms(p):
+    """Pins of the face restatement that need no reference run: 1^T M 1 = area of the interface; M is symmetric; the row-sum
+    'diagonal' is positive exactly on the interface DoFs; the projector reproduces polynomial data of degree <= p exactly on the
+    interface and leaves every other entry of the vector untouched (boundary_projector.h:86-110)."""
+    from b200mf.mesh import StructuredMesh
+    from oracle import boundary_oracle as BO
+
+    m = StructuredMesh((3, 2, 2), p, lower=(0.0, 0.0, 0.0), upper=(1.5, 1.0, 0.5))
+    faces = ((0, 1), (2, 0))  # x = 1.5 (area 0.5) and z = 0 (area 1.5)
+    cells, fno = _interface_faces(m, faces)
+    op = BO.BoundaryMassOperator(m, cells, fno)
+    one = np.ones(m.n_nodes)
+    out = np.zeros(m.n_nodes)
+    op.vmult(out, one)
+    assert abs(out.sum() - 2.0) < 1e-13
+    rng = np.random.default_rng(5)
+    a, b = rng.uniform(-1, 1, m.n_nodes), rng.uniform(-1, 1, m.n_nodes)
+    Ma, Mb = np.zeros_like(a), np.zeros_like(b)
+    op.vmult(Ma, a)
+    op.vmult(Mb, b)
+    assert abs(b @ Ma - a @ Mb) < 1e-13
+    diag = op.compute_diagonal()
+    on = np.zeros(m.n_nodes, bool)
+    on[op.boundary_indices] = True
+    assert np.all(diag[on] > 0) and np.all(diag[~on] == 0) and np.all(op.inverse_diagonal[~on] == 0)
+    x = m.node_coordinates()
+    assert np.array_equal(on, np.isclose(x[:, 0], 1.5) | np.isclose(x[:, 2], 0.0))
+    g = 1.0 + x[:, 0] ** p - 0.5 * x[:, 1] ** p + x[:, 1] * x[:, 2]
+    residual = np.zeros(m.n_nodes)
+    op.vmult(residual, g)            # nodal 'residual' whose interface part is M g
+    off = rng.uniform(-1, 1, m.n_nodes)
+    residual[~on] = off[~on]         # entries off the interface: zero row, zero rhs, zero preconditioner -> kept
+    r = BO.project(op, residual)
+    assert r.converged and r.iterations <= 500
+    assert np.abs(residual[on] - g[on]).max() < 1e-9
+    assert np.array_equal(residual[~on], off[~on])
+    # flux faces: int_Gamma (-q dt) phi dA with constant q sums to -q dt * area
+    rhs = BO.flux_rhs(op, np.full((len(cells), (p + 1) ** 2, 1), 3.0), -0.1)
+    assert abs(rhs.sum() + 3.0 * 0.1 * 2.0) < 1e-13
+
+
+def test_boundary_mass_oracle_curved_area():
+    """on the cylinder shell the face Jacobian is not constant: the Q1 facets of the inner wall lie just inside r_in and their
+    area tends to 2 pi r_in L from below (cases/elasticity/tube_3d.h:23-33: r_in 0.5, length 5, scaled 1e-2)"""
+    from b200mf.mesh import tube_hierarchy
+    from oracle import boundary_oracle as BO
+
+    m = tube_hierarchy(2, 1, first_refinement=1)[-1]
+    d_rad = int(np.argmin(m.ncells))  # one cell layer through the wall
+    cells, fno = _interface_faces(m, ((d_rad, 0),))
+    op = BO.BoundaryMassOperator(m, cells, fno)
+    x = op.points.reshape(-1, 3)
+    axis = int(np.argmax(x.max(0) - x.min(0)))  # the tube axis: the longest extent of the wall
+    perp = [e for e in range(3) if e != axis]
+    rad = np.sqrt(x[:, perp[0]] ** 2 + x[:, perp[1]] ** 2)
+    assert rad.max() <= 0.5e-2 + 1e-12 and rad.min() > 0.45e-2
+    exact = 2 * np.pi * 0.5e-2 * 5e-2
+    assert 0.9 * exact < op.jxw.sum() < exact
