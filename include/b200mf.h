@@ -192,6 +192,13 @@ int b200mf_nh_vmult_host(b200mf_nh *op, double *dst_host, const double *src_host
 /* compute_diagonal(), mf_nh_operator.h:1023-1060: fills diagonal and inverse (constrained -> 1) */
 int b200mf_nh_compute_diagonal(b200mf_nh *op);
 int b200mf_nh_diagonal(b200mf_nh *op, const void **diag_dvec, const void **inv_diag_dvec); /* get_matrix_diagonal_inverse :157-161 */
+/* The smoother hook (deal.II's vmult(dst, src, before, after) overload, which the reference does not provide - SURVEY.md §8b):
+ * the operator pass alone.  dst must be ZERO on entry (all local entries, ghosts included) and the constrained rows of the result
+ * are left 0: the smoother's vector update that consumes dst treats them as identity rows and zeroes dst again, so a Chebyshev
+ * iteration is two launches (cell loop + update) instead of four (memset, cell loop, identity rows, update).  Ghost exchange and
+ * compress(add) inside as in vmult.  diagonal_generation changes whenever compute_diagonal ran (for cached copies of the diagonal). */
+int b200mf_nh_vmult_cells(b200mf_nh *op, void *dst_zero_dvec, const void *src_dvec);
+uint64_t b200mf_nh_diagonal_generation(const b200mf_nh *op);
 int b200mf_nh_diagonal_host(b200mf_nh *op, double *diag_host, double *inv_diag_host);
 /* precondition_Jacobi(dst, src, omega), mf_nh_operator.h:281-291 */
 int b200mf_nh_precondition_jacobi(b200mf_nh *op, void *dst_dvec, const void *src_dvec, double omega);
@@ -227,6 +234,8 @@ int b200mf_laplace_Tvmult_add(b200mf_laplace *op, void *dst_dvec, const void *sr
  * refinement-edge rows; the reference refines globally only (heat_transfer.h:421-425), so both reduce to dst = 0 */
 int b200mf_laplace_vmult_interface_down(b200mf_laplace *op, void *dst_dvec, const void *src_dvec);
 int b200mf_laplace_vmult_interface_up(b200mf_laplace *op, void *dst_dvec, const void *src_dvec);
+int b200mf_laplace_vmult_cells(b200mf_laplace *op, void *dst_zero_dvec, const void *src_dvec); /* smoother hook, see b200mf_nh_vmult_cells */
+uint64_t b200mf_laplace_diagonal_generation(const b200mf_laplace *op);
 int64_t b200mf_laplace_m(const b200mf_laplace *op);                        /* Base::m() == n(), heat_transfer.h:81 (inherited) */
 int b200mf_laplace_el(b200mf_laplace *op, int64_t row, double *value);     /* Base::el(row, row): diagonal entry, needs compute_diagonal */
 int b200mf_laplace_vmult_dot(b200mf_laplace *op, void *dst_dvec, const void *src_dvec, double *dot_device);

@@ -103,6 +103,10 @@ SIGNATURES = {
     "b200mf_nh_cache_host": (_i32, [_vp, _vp, C.POINTER(_i64)]),
     "b200mf_nh_vmult": (_i32, [_vp, _vp, _vp]),
     "b200mf_nh_vmult_add": (_i32, [_vp, _vp, _vp]),
+    "b200mf_nh_vmult_cells": (_i32, [_vp, _vp, _vp]),
+    "b200mf_nh_diagonal_generation": (C.c_uint64, [_vp]),
+    "b200mf_laplace_vmult_cells": (_i32, [_vp, _vp, _vp]),
+    "b200mf_laplace_diagonal_generation": (C.c_uint64, [_vp]),
     "b200mf_nh_Tvmult": (_i32, [_vp, _vp, _vp]),
     "b200mf_nh_Tvmult_add": (_i32, [_vp, _vp, _vp]),
     "b200mf_nh_vmult_host": (_i32, [_vp, _vp, _vp]),

@@ -298,6 +298,10 @@ class NeoHookOperator:
     def vmult_add(self, dst, src):
         _l.check(_l.load().b200mf_nh_vmult_add(self.h, _dv(dst), _dv(src)))
 
+    def vmult_cells(self, dst_zero, src):
+        """smoother hook: the operator pass alone (dst zero on entry, constrained rows left 0)"""
+        _l.check(_l.load().b200mf_nh_vmult_cells(self.h, _dv(dst_zero), _dv(src)))
+
     def Tvmult(self, dst, src):
         if isinstance(dst, np.ndarray):
             return self.vmult(dst, src)
@@ -391,6 +395,10 @@ class LaplaceOperator:
     def vmult_add(self, dst, src):
         _l.check(_l.load().b200mf_laplace_vmult_add(self.h, _dv(dst), _dv(src)))
 
+    def vmult_cells(self, dst_zero, src):
+        """smoother hook: the operator pass alone (dst zero on entry, constrained rows left 0)"""
+        _l.check(_l.load().b200mf_laplace_vmult_cells(self.h, _dv(dst_zero), _dv(src)))
+
     def Tvmult_add(self, dst, src):
         _l.check(_l.load().b200mf_laplace_Tvmult_add(self.h, _dv(dst), _dv(src)))
 
@@ -474,12 +482,14 @@ class InterfaceTraction:
         return out
 
     def set_traction(self, traction):
-        """traction: one vector (constant) or [n_faces * nq^2, 3] values at the face quadrature points."""
+        """traction: one vector (constant) or [n_faces * nq^2, ncomp] values at the face quadrature points (ncomp = 3: traction
+        of the solid; ncomp = 1 on a scalar context: the heat flux)."""
         t = np.ascontiguousarray(traction, dtype=np.float64)
-        if t.size == 3:
+        nc = self.mf.n_components
+        if t.size == nc and self.n_q_points() != 1:
             _l.check(_l.load().b200mf_face_set_set_traction(self.h, None, _ptr(t)))
         else:
-            assert t.size == 3 * self.n_q_points()
+            assert t.size == nc * self.n_q_points()
             _l.check(_l.load().b200mf_face_set_set_traction(self.h, _ptr(t), None))
         self._traction = t
 

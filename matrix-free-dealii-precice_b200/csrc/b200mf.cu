@@ -838,6 +838,7 @@ struct b200mf_nh {
   unsigned long long *n_bad;
   void *diag, *inv_diag;
   void *tmp_src, *tmp_dst;  // for the *_host entry points
+  uint64_t diag_gen;        // bumped by compute_diagonal (consumers that keep derived copies of the inverse diagonal)
 };
 
 static void derived(const b200mf_material &m, double &kappa, double &c_1, double &lambda, double &rho_alpha) {
@@ -1056,39 +1057,45 @@ static int constrained_identity(b200mf_ctx *c, void *dst, const void *src, doubl
 }
 
 template <typename T>
-static int nh_apply_t(b200mf_nh *op, void *dst, const void *src, double *dot) {
+static int nh_apply_t(b200mf_nh *op, void *dst, const void *src, double *dot, bool identity_rows) {
   b200mf_ctx *c = op->ctx;
   const NHArgs<T> oa = nh_args<T>(op);
   B2_TRY(apply_cells_with_exchange(c, dst, src, [&](int64_t g0, int64_t g1, cudaStream_t s) {
     return run_nh<T>(c, op->variant, (const T *)src, (T *)dst, oa, g0, g1, s, dot);
   }));
-  return constrained_identity<T>(c, dst, src, dot);
+  return identity_rows ? constrained_identity<T>(c, dst, src, dot) : 0;
 }
 
-static int nh_apply(b200mf_nh *op, void *dst, const void *src, bool zero_dst, double *dot = nullptr) {
+// how an application treats dst: vmult zeroes it, vmult_add keeps it, APPLY_CELLS is the smoother hook's operator pass - dst is
+// zero on entry by contract (the previous vector update left it so) and the constrained rows are left 0 for the caller's update
+enum ApplyMode { APPLY_VMULT = 0, APPLY_ADD = 1, APPLY_CELLS = 2 };
+
+static int nh_apply(b200mf_nh *op, void *dst, const void *src, ApplyMode mode, double *dot = nullptr) {
   if (!op || !dst || !src) return set_error(B200MF_ERR_ARG, "null argument");
   if (dst == src) return set_error(B200MF_ERR_ARG, "vmult: dst aliases src");
   if (!op->cached) return set_error(B200MF_ERR_STATE, "vmult before cache()");
   b200mf_ctx *c = op->ctx;
-  if (zero_dst)
+  if (mode == APPLY_VMULT)
     B2_CUDA(cudaMemsetAsync(dst, 0, c->n_int * esize(c), c->stream));  // vmult: dst = 0, :548
-  else
+  else if (mode == APPLY_ADD)
     B2_TRY(zero_ghosts(c, dst));  // vmult_add: stale ghost entries of dst must not be summed into their owners by compress(add)
-  int rc = c->dtype == B200MF_F64 ? nh_apply_t<double>(op, dst, src, dot) : nh_apply_t<float>(op, dst, src, dot);
+  int rc = c->dtype == B200MF_F64 ? nh_apply_t<double>(op, dst, src, dot, mode != APPLY_CELLS) : nh_apply_t<float>(op, dst, src, dot, mode != APPLY_CELLS);
   B2_TRY(rc);
   B2_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int b200mf_nh_vmult(b200mf_nh *op, void *dst, const void *src) { return nh_apply(op, dst, src, true); }
-extern "C" int b200mf_nh_vmult_add(b200mf_nh *op, void *dst, const void *src) { return nh_apply(op, dst, src, false); }
-extern "C" int b200mf_nh_Tvmult(b200mf_nh *op, void *dst, const void *src) { return nh_apply(op, dst, src, true); }       // :556-561
-extern "C" int b200mf_nh_Tvmult_add(b200mf_nh *op, void *dst, const void *src) { return nh_apply(op, dst, src, false); }  // :566-571
+extern "C" int b200mf_nh_vmult(b200mf_nh *op, void *dst, const void *src) { return nh_apply(op, dst, src, APPLY_VMULT); }
+extern "C" int b200mf_nh_vmult_add(b200mf_nh *op, void *dst, const void *src) { return nh_apply(op, dst, src, APPLY_ADD); }
+extern "C" int b200mf_nh_Tvmult(b200mf_nh *op, void *dst, const void *src) { return nh_apply(op, dst, src, APPLY_VMULT); }    // :556-561
+extern "C" int b200mf_nh_Tvmult_add(b200mf_nh *op, void *dst, const void *src) { return nh_apply(op, dst, src, APPLY_ADD); }  // :566-571
+extern "C" int b200mf_nh_vmult_cells(b200mf_nh *op, void *dst, const void *src) { return nh_apply(op, dst, src, APPLY_CELLS); }
+extern "C" uint64_t b200mf_nh_diagonal_generation(const b200mf_nh *op) { return op ? op->diag_gen : 0; }
 
 // vmult with the CG dot product fused into the operator pass: *dot_device += (this rank's share of) src . (A src)
 extern "C" int b200mf_nh_vmult_dot(b200mf_nh *op, void *dst, const void *src, double *dot_device) {
   if (!dot_device) return set_error(B200MF_ERR_ARG, "null argument");
-  return nh_apply(op, dst, src, true, dot_device);
+  return nh_apply(op, dst, src, APPLY_VMULT, dot_device);
 }
 
 static int fused_dot_result(b200mf_ctx *c, double *result_host) {
@@ -1106,7 +1113,7 @@ static int fused_dot_slot(b200mf_ctx *c) {
 extern "C" int b200mf_nh_vmult_dot_host(b200mf_nh *op, void *dst, const void *src, double *result_host) {
   if (!op || !result_host) return set_error(B200MF_ERR_ARG, "null argument");
   B2_TRY(fused_dot_slot(op->ctx));
-  B2_TRY(nh_apply(op, dst, src, true, op->ctx->scalars));
+  B2_TRY(nh_apply(op, dst, src, APPLY_VMULT, op->ctx->scalars));
   return fused_dot_result(op->ctx, result_host);
 }
 
@@ -1309,7 +1316,7 @@ extern "C" int b200mf_nh_vmult_host(b200mf_nh *op, double *dst, const double *sr
     });
   }
   B2_TRY(b200mf_vec_upload_f64(c, op->tmp_src, src));
-  B2_TRY(nh_apply(op, op->tmp_dst, op->tmp_src, true));
+  B2_TRY(nh_apply(op, op->tmp_dst, op->tmp_src, APPLY_VMULT));
   return b200mf_vec_download_f64(c, dst, op->tmp_dst);
 }
 
@@ -1459,6 +1466,7 @@ extern "C" int b200mf_nh_compute_diagonal(b200mf_nh *op) {
   });
   B2_TRY(rc0);
   op->have_diag = true;
+  ++op->diag_gen;
   return 0;
 }
 
@@ -1522,6 +1530,7 @@ struct b200mf_laplace {
   void *tmp_src, *tmp_dst;
   unsigned long long *n_bad;
   bool have_diag;
+  uint64_t diag_gen;
 };
 
 extern "C" int b200mf_laplace_create(b200mf_laplace **out, b200mf_ctx *ctx, double delta_t, const double *coef) {
@@ -1585,33 +1594,36 @@ static LaplaceArgs<T> laplace_args(const b200mf_laplace *op) {
   return oa;
 }
 template <typename T>
-static int laplace_apply_t(b200mf_laplace *op, void *dst, const void *src, double *dot) {
+static int laplace_apply_t(b200mf_laplace *op, void *dst, const void *src, double *dot, bool identity_rows) {
   b200mf_ctx *c = op->ctx;
   const LaplaceArgs<T> oa = laplace_args<T>(op);
   B2_TRY(apply_cells_with_exchange(c, dst, src, [&](int64_t g0, int64_t g1, cudaStream_t s) {
     return run_laplace<T>(c, false, (const T *)src, (T *)dst, oa, g0, g1, s, dot);
   }));
-  return constrained_identity<T>(c, dst, src, dot);
+  return identity_rows ? constrained_identity<T>(c, dst, src, dot) : 0;
 }
 
-static int laplace_apply(b200mf_laplace *op, void *dst, const void *src, bool zero_dst, double *dot = nullptr) {
+static int laplace_apply(b200mf_laplace *op, void *dst, const void *src, ApplyMode mode, double *dot = nullptr) {
   if (!op || !dst || !src) return set_error(B200MF_ERR_ARG, "null argument");
   if (dst == src) return set_error(B200MF_ERR_ARG, "vmult: dst aliases src");
   b200mf_ctx *c = op->ctx;
-  if (zero_dst)
+  if (mode == APPLY_VMULT)
     B2_CUDA(cudaMemsetAsync(dst, 0, c->n_int * esize(c), c->stream));
-  else
+  else if (mode == APPLY_ADD)
     B2_TRY(zero_ghosts(c, dst));  // see nh_apply
-  int rc = c->dtype == B200MF_F64 ? laplace_apply_t<double>(op, dst, src, dot) : laplace_apply_t<float>(op, dst, src, dot);
+  const bool id = mode != APPLY_CELLS;
+  int rc = c->dtype == B200MF_F64 ? laplace_apply_t<double>(op, dst, src, dot, id) : laplace_apply_t<float>(op, dst, src, dot, id);
   B2_TRY(rc);
   B2_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int b200mf_laplace_vmult(b200mf_laplace *op, void *dst, const void *src) { return laplace_apply(op, dst, src, true); }
-extern "C" int b200mf_laplace_vmult_add(b200mf_laplace *op, void *dst, const void *src) { return laplace_apply(op, dst, src, false); }
-extern "C" int b200mf_laplace_Tvmult(b200mf_laplace *op, void *dst, const void *src) { return laplace_apply(op, dst, src, true); }
-extern "C" int b200mf_laplace_Tvmult_add(b200mf_laplace *op, void *dst, const void *src) { return laplace_apply(op, dst, src, false); }
+extern "C" int b200mf_laplace_vmult(b200mf_laplace *op, void *dst, const void *src) { return laplace_apply(op, dst, src, APPLY_VMULT); }
+extern "C" int b200mf_laplace_vmult_add(b200mf_laplace *op, void *dst, const void *src) { return laplace_apply(op, dst, src, APPLY_ADD); }
+extern "C" int b200mf_laplace_Tvmult(b200mf_laplace *op, void *dst, const void *src) { return laplace_apply(op, dst, src, APPLY_VMULT); }
+extern "C" int b200mf_laplace_Tvmult_add(b200mf_laplace *op, void *dst, const void *src) { return laplace_apply(op, dst, src, APPLY_ADD); }
+extern "C" int b200mf_laplace_vmult_cells(b200mf_laplace *op, void *dst, const void *src) { return laplace_apply(op, dst, src, APPLY_CELLS); }
+extern "C" uint64_t b200mf_laplace_diagonal_generation(const b200mf_laplace *op) { return op ? op->diag_gen : 0; }
 // MatrixFreeOperators::Base::vmult_interface_down / _up: dst = 0, then the refinement-edge rows.  The reference only refines
 // globally (mf_elasticity.h:638, heat_transfer.h:421-425: no hanging nodes, no refinement edges on any level), so there are no
 // edge rows and both are "dst = 0".
@@ -1632,13 +1644,13 @@ extern "C" int b200mf_laplace_el(b200mf_laplace *op, int64_t row, double *value)
 
 extern "C" int b200mf_laplace_vmult_dot(b200mf_laplace *op, void *dst, const void *src, double *dot_device) {
   if (!dot_device) return set_error(B200MF_ERR_ARG, "null argument");
-  return laplace_apply(op, dst, src, true, dot_device);
+  return laplace_apply(op, dst, src, APPLY_VMULT, dot_device);
 }
 
 extern "C" int b200mf_laplace_vmult_dot_host(b200mf_laplace *op, void *dst, const void *src, double *result_host) {
   if (!op || !result_host) return set_error(B200MF_ERR_ARG, "null argument");
   B2_TRY(fused_dot_slot(op->ctx));
-  B2_TRY(laplace_apply(op, dst, src, true, op->ctx->scalars));
+  B2_TRY(laplace_apply(op, dst, src, APPLY_VMULT, op->ctx->scalars));
   return fused_dot_result(op->ctx, result_host);
 }
 
@@ -1648,7 +1660,7 @@ extern "C" int b200mf_laplace_vmult_host(b200mf_laplace *op, double *dst, const 
   if (!op->tmp_src) B2_CUDA(cudaMalloc(&op->tmp_src, c->n_int * esize(c)));
   if (!op->tmp_dst) B2_CUDA(cudaMalloc(&op->tmp_dst, c->n_int * esize(c)));
   B2_TRY(b200mf_vec_upload_f64(c, op->tmp_src, src));
-  B2_TRY(laplace_apply(op, op->tmp_dst, op->tmp_src, true));
+  B2_TRY(laplace_apply(op, op->tmp_dst, op->tmp_src, APPLY_VMULT));
   return b200mf_vec_download_f64(c, dst, op->tmp_dst);
 }
 
@@ -1708,6 +1720,7 @@ extern "C" int b200mf_laplace_compute_diagonal(b200mf_laplace *op) {
   });
   B2_TRY(rc0);
   op->have_diag = true;
+  ++op->diag_gen;
   return 0;
 }
 extern "C" int b200mf_laplace_diagonal(b200mf_laplace *op, const void **diag, const void **inv) {

@@ -106,6 +106,53 @@ __global__ void cheb_update_kernel(int64_t n, T f1, T f2, const T *__restrict__ 
     dst[i] = d + f1 * (d - o) + f2 * inv[i] * (src[i] - t[i]);
   }
 }
+// The same update as the operator's "after" hook: t = A_cells dst comes without identity rows and is consumed here, so
+//   - constrained rows (marked by a negative entry of invm = -1/diag = -1) use t := dst (A acts as the identity there),
+//   - t is zeroed on the way out: the next operator pass accumulates into it without a memset of its own.
+template <typename T>
+__global__ void cheb_update_hook_kernel(int64_t n, T f1, T f2, const T *__restrict__ invm, const T *__restrict__ src, T *__restrict__ t,
+                                        T *__restrict__ dst, T *__restrict__ old) {
+  // t is read and written: all loads of a batch are issued before its stores so that they stay in flight together
+  constexpr int U = 4;
+  const int64_t tile = (int64_t)blockDim.x * U;
+  for (int64_t base = (int64_t)blockIdx.x * tile + threadIdx.x; base < n; base += (int64_t)gridDim.x * tile) {
+    T d[U], o[U], iv[U], ti[U], sr[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = base + (int64_t)u * blockDim.x;
+      if (i < n) {
+        d[u] = dst[i];
+        o[u] = old[i];
+        iv[u] = invm[i];
+        ti[u] = t[i];
+        sr[u] = src[i];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = base + (int64_t)u * blockDim.x;
+      if (i < n) {
+        T a = iv[u], tv = ti[u];
+        if (a < T(0)) {
+          a = -a;
+          tv = d[u];
+        }
+        t[i] = T(0);
+        old[i] = d[u];
+        dst[i] = d[u] + f1 * (d[u] - o[u]) + f2 * a * (sr[u] - tv);
+      }
+    }
+  }
+}
+template <typename T>
+__global__ void mark_inverse_kernel(int64_t n, const T *__restrict__ inv, T *__restrict__ invm) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) invm[i] = inv[i];
+}
+template <typename T>
+__global__ void negate_indexed_kernel(int64_t n, const uint32_t *__restrict__ idx, T *__restrict__ v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[idx[i]] = -fabs(v[idx[i]]);
+}
 template <typename TO, typename TI>
 __global__ void convert_kernel(int64_t n, const TI *__restrict__ in, TO *__restrict__ out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (TO)in[i];
@@ -146,6 +193,10 @@ struct LinOp {
   std::function<int(void *, const void *)> vmult;
   std::function<int(void *, const void *, double *)> vmult_dot;  // dst = A src and *slot += src . (A src) in one operator pass
   std::function<int(const void **)> inv_diag;
+  // the smoother hook (SURVEY.md §8b "Optional fusion hook"): operator pass without the zeroing of dst before and the
+  // identity rows after it - both move into the smoother's vector update (cheb_update_hook_kernel)
+  std::function<int(void *, const void *)> vmult_cells;
+  std::function<uint64_t()> diag_gen;  // changes whenever the operator's diagonal was recomputed
 };
 
 struct Scratch {  // a few device doubles + pinned host mirror for the reductions
@@ -482,6 +533,10 @@ struct b200mf_chebyshev {
   int degree = 1, cg_iterations = 0;
   void *old = nullptr, *tmp = nullptr, *w[3] = {nullptr, nullptr, nullptr};
   Scratch sc;
+  // smoother hook: inverse diagonal with the constrained rows marked by their sign, rebuilt when the operator's diagonal moves
+  void *invm = nullptr;
+  const void *invm_of = nullptr;
+  uint64_t invm_gen = ~0ull;
 };
 
 static LinOp linop_nh(b200mf_nh *op, b200mf_ctx *ctx) {
@@ -490,6 +545,8 @@ static LinOp linop_nh(b200mf_nh *op, b200mf_ctx *ctx) {
   A.vmult = [op](void *d, const void *s) { return b200mf_nh_vmult(op, d, s); };
   A.vmult_dot = [op](void *d, const void *s, double *slot) { return b200mf_nh_vmult_dot(op, d, s, slot); };
   A.inv_diag = [op](const void **inv) { return b200mf_nh_diagonal(op, nullptr, inv); };
+  A.vmult_cells = [op](void *d, const void *s) { return b200mf_nh_vmult_cells(op, d, s); };
+  A.diag_gen = [op]() { return b200mf_nh_diagonal_generation(op); };
   return A;
 }
 static LinOp linop_laplace(b200mf_laplace *op, b200mf_ctx *ctx) {
@@ -498,6 +555,8 @@ static LinOp linop_laplace(b200mf_laplace *op, b200mf_ctx *ctx) {
   A.vmult = [op](void *d, const void *s) { return b200mf_laplace_vmult(op, d, s); };
   A.vmult_dot = [op](void *d, const void *s, double *slot) { return b200mf_laplace_vmult_dot(op, d, s, slot); };
   A.inv_diag = [op](const void **inv) { return b200mf_laplace_diagonal(op, nullptr, inv); };
+  A.vmult_cells = [op](void *d, const void *s) { return b200mf_laplace_vmult_cells(op, d, s); };
+  A.diag_gen = [op]() { return b200mf_laplace_diagonal_generation(op); };
   return A;
 }
 
@@ -532,9 +591,32 @@ extern "C" int b200mf_chebyshev_destroy(b200mf_chebyshev *ch) {
   if (!ch) return 0;
   cudaFree(ch->old);
   cudaFree(ch->tmp);
+  cudaFree(ch->invm);
   for (void *p : ch->w) cudaFree(p);
   delete ch;
   return 0;
+}
+
+// smoother hook: (re)build the sign-marked inverse diagonal when the operator's diagonal has moved
+template <typename T>
+static int cheb_refresh_marked_inverse(b200mf_chebyshev *ch, const void *invp) {
+  b200mf_ctx *c = ch->A.ctx;
+  const uint64_t gen = ch->A.diag_gen();
+  if (ch->invm && ch->invm_of == invp && ch->invm_gen == gen) return 0;
+  if (!ch->invm) B2_TRY(vec_alloc(c, &ch->invm));
+  mark_inverse_kernel<T><<<vgrid(c->n_int, c), 256, 0, c->stream>>>(c->n_int, (const T *)invp, (T *)ch->invm);
+  B2_LAUNCHED();
+  if (c->n_constrained) {
+    negate_indexed_kernel<T><<<(unsigned)((c->n_constrained + 255) / 256), 256, 0, c->stream>>>(c->n_constrained, c->constrained, (T *)ch->invm);
+    B2_LAUNCHED();
+  }
+  ch->invm_of = invp;
+  ch->invm_gen = gen;
+  return 0;
+}
+static bool smoother_hook_enabled() {
+  static const bool on = !(getenv("B200MF_SMOOTHER_HOOK") && atoi(getenv("B200MF_SMOOTHER_HOOK")) == 0);
+  return on;
 }
 
 template <typename T>
@@ -594,6 +676,12 @@ static int cheb_estimate_t(b200mf_chebyshev *ch) {
   ch->delta = (mx - alpha) * 0.5;
   ch->theta = (mx + alpha) * 0.5;
   ch->eig_ready = true;
+  if (smoother_hook_enabled() && ch->A.vmult_cells && ch->A.diag_gen) {
+    B2_TRY(cheb_refresh_marked_inverse<T>(ch, inv));  // here, not inside a recorded V-cycle
+    // invariant of the hooked smoother: tmp is zero whenever no application is running (vec_alloc zero-fills, every hooked update
+    // re-zeroes it) - the eigenvalue CG above used it as its right-hand side.  A recorded V-cycle relies on it as well.
+    B2_CUDA(cudaMemsetAsync(ch->tmp, 0, c->n_int * sizeof(T), c->stream));
+  }
   return 0;
 }
 
@@ -618,13 +706,29 @@ static int cheb_apply_t(b200mf_chebyshev *ch, T *dst, const T *src, bool zero_st
   const int64_t n = c->n_int;
   const unsigned g = vgrid(n, c);
   T *old = (T *)ch->old, *t = (T *)ch->tmp;
+  const bool hook = smoother_hook_enabled() && ch->A.vmult_cells && ch->A.diag_gen;
+  const T *invm = nullptr;
+  if (hook) {
+    B2_TRY(cheb_refresh_marked_inverse<T>(ch, invp));
+    invm = (const T *)ch->invm;
+  }
+  // one matrix-vector product + update: t = A dst, then the three-term recurrence
+  auto step = [&](double f1, double f2) -> int {
+    if (hook) {
+      B2_TRY(ch->A.vmult_cells(t, dst));
+      cheb_update_hook_kernel<T><<<g, 256, 0, c->stream>>>(n, (T)f1, (T)f2, invm, src, t, dst, old);
+    } else {
+      B2_TRY(ch->A.vmult(t, dst));
+      cheb_update_kernel<T><<<g, 256, 0, c->stream>>>(n, (T)f1, (T)f2, inv, src, t, dst, old);
+    }
+    B2_LAUNCHED();
+    return 0;
+  };
   if (zero_start) {
     cheb_first_kernel<T><<<g, 256, 0, c->stream>>>(n, (T)(1.0 / ch->theta), inv, src, dst, old);
     B2_LAUNCHED();
   } else {
-    B2_TRY(ch->A.vmult(t, dst));
-    cheb_update_kernel<T><<<g, 256, 0, c->stream>>>(n, T(0), (T)(1.0 / ch->theta), inv, src, t, dst, old);
-    B2_LAUNCHED();
+    B2_TRY(step(0.0, 1.0 / ch->theta));
   }
   if (ch->degree < 2 || std::fabs(ch->delta) < 1e-40) return 0;
   double rhok = ch->delta / ch->theta;
@@ -633,9 +737,7 @@ static int cheb_apply_t(b200mf_chebyshev *ch, T *dst, const T *src, bool zero_st
     const double rhokp = 1.0 / (2.0 * sigma - rhok);
     const double f1 = rhokp * rhok, f2 = 2.0 * rhokp / ch->delta;
     rhok = rhokp;
-    B2_TRY(ch->A.vmult(t, dst));
-    cheb_update_kernel<T><<<g, 256, 0, c->stream>>>(n, (T)f1, (T)f2, inv, src, t, dst, old);
-    B2_LAUNCHED();
+    B2_TRY(step(f1, f2));
   }
   return 0;
 }

@@ -109,6 +109,13 @@ def test_nh_vmult_fp64(p):
     op.vmult_add(d, s)
     assert rel(d.download(), 2 * ref) < TOL64
     assert op.m() == 3 * m.n_nodes
+    # smoother hook: the operator pass alone into a zero vector - identity rows left to the consumer
+    d.set_zero()
+    op.vmult_cells(d, s)
+    con = m.constrained_dofs(3)
+    want = ref.copy()
+    want[con] = 0.0
+    assert con.any() and rel(d.download(), want) < TOL64
 
 
 @pytest.mark.parametrize("p", [2, 3])
