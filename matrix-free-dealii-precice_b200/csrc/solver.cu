@@ -41,9 +41,16 @@ __device__ __forceinline__ double block_sum(double v) {
 }
 struct Own {
   int64_t n_main, cstride, n_owned_nodes;
-  __device__ __forceinline__ bool operator()(int64_t i) const { return i < n_main && (i % cstride) < n_owned_nodes; }
+  int nc;
+  // i = c * cstride + node is owned iff node < n_owned_nodes; the component blocks are peeled off by comparison (nc <= 3) - a
+  // 64-bit modulo per vector entry costs more instructions than the update it guards
+  __device__ __forceinline__ bool operator()(int64_t i) const {
+    if (i >= n_main) return false;
+    for (int c = 1; c < nc; ++c) i -= i >= cstride ? cstride : 0;
+    return i < n_owned_nodes;
+  }
 };
-static Own own_of(const b200mf_ctx *c) { return Own{c->cstride * c->NC, c->cstride, c->n_owned_nodes}; }
+static Own own_of(const b200mf_ctx *c) { return Own{c->cstride * c->NC, c->cstride, c->n_owned_nodes, c->NC}; }
 
 template <typename T>
 __global__ void dot_kernel(Own own, const T *__restrict__ a, const T *__restrict__ b, double *out) {
