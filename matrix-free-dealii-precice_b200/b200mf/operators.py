@@ -165,7 +165,10 @@ class MatrixFree:
 
     def __del__(self):
         if getattr(self, "h", None):
-            _l.load().b200mf_ctx_destroy(self.h)
+            try:
+                _l.load().b200mf_ctx_destroy(self.h)
+            except TypeError:  # interpreter shutdown: the module globals are already gone
+                pass
             self.h = None
 
 
@@ -229,7 +232,10 @@ class DeviceVector:
 
     def __del__(self):
         if getattr(self, "ptr", None) and getattr(self.mf, "h", None):
-            _l.load().b200mf_vec_destroy(self.mf.h, self.ptr)
+            try:
+                _l.load().b200mf_vec_destroy(self.mf.h, self.ptr)
+            except TypeError:  # interpreter shutdown: the module globals are already gone
+                pass
             self.ptr = None
 
 
@@ -444,7 +450,10 @@ class LaplaceOperator:
 
     def __del__(self):
         if getattr(self, "h", None):
-            _l.load().b200mf_laplace_destroy(self.h)
+            try:
+                _l.load().b200mf_laplace_destroy(self.h)
+            except TypeError:  # interpreter shutdown: the module globals are already gone
+                pass
             self.h = None
 
 
@@ -505,7 +514,10 @@ class InterfaceTraction:
 
     def __del__(self):
         if getattr(self, "h", None):
-            _l.load().b200mf_face_set_destroy(self.h)
+            try:
+                _l.load().b200mf_face_set_destroy(self.h)
+            except TypeError:  # interpreter shutdown: the module globals are already gone
+                pass
             self.h = None
 
 
@@ -552,5 +564,8 @@ class BoundaryMassOperator:
 
     def __del__(self):
         if getattr(self, "h", None):
-            _l.load().b200mf_boundary_mass_destroy(self.h)
+            try:
+                _l.load().b200mf_boundary_mass_destroy(self.h)
+            except TypeError:  # interpreter shutdown: the module globals are already gone
+                pass
             self.h = None

@@ -52,7 +52,10 @@ class PreconditionChebyshev:
 
     def __del__(self):
         if getattr(self, "h", None):
-            _l.load().b200mf_chebyshev_destroy(self.h)
+            try:
+                _l.load().b200mf_chebyshev_destroy(self.h)
+            except TypeError:  # interpreter shutdown: the module globals are already gone
+                pass
             self.h = None
 
 
@@ -81,7 +84,10 @@ class MGTransferMatrixFree:
 
     def __del__(self):
         if getattr(self, "h", None):
-            _l.load().b200mf_mg_transfer_destroy(self.h)
+            try:
+                _l.load().b200mf_mg_transfer_destroy(self.h)
+            except TypeError:  # interpreter shutdown: the module globals are already gone
+                pass
             self.h = None
 
 
@@ -125,7 +131,10 @@ class PreconditionMG:
 
     def __del__(self):
         if getattr(self, "h", None):
-            _l.load().b200mf_mg_destroy(self.h)
+            try:
+                _l.load().b200mf_mg_destroy(self.h)
+            except TypeError:  # interpreter shutdown: the module globals are already gone
+                pass
             self.h = None
 
 

@@ -52,44 +52,100 @@ struct Own {
 };
 static Own own_of(const b200mf_ctx *c) { return Own{c->cstride * c->NC, c->cstride, c->n_owned_nodes, c->NC}; }
 
+// Streaming loops over a vector: per trip a thread takes U block-strided entries and issues the loads of all of them
+// (load(u, i)) before the first store (store(u, i)), so that U independent cache lines per array are in flight per thread - a
+// plain grid-stride loop that writes what it reads is serialised by the compiler behind each store.
+constexpr int VU = 4;
+template <class Load, class Store>
+__device__ __forceinline__ void stream_loop(int64_t n, Load load, Store store) {
+  const int64_t tile = (int64_t)blockDim.x * VU;
+  for (int64_t base = (int64_t)blockIdx.x * tile + threadIdx.x; base < n; base += (int64_t)gridDim.x * tile) {
+#pragma unroll
+    for (int u = 0; u < VU; ++u) {
+      const int64_t i = base + (int64_t)u * blockDim.x;
+      if (i < n) load(u, i);
+    }
+#pragma unroll
+    for (int u = 0; u < VU; ++u) {
+      const int64_t i = base + (int64_t)u * blockDim.x;
+      if (i < n) store(u, i);
+    }
+  }
+}
+
 template <typename T>
 __global__ void dot_kernel(Own own, const T *__restrict__ a, const T *__restrict__ b, double *out) {
   double s = 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < own.n_main; i += (int64_t)gridDim.x * blockDim.x)
-    if (own(i)) s += (double)a[i] * (double)b[i];
+  T av[VU], bv[VU];
+  stream_loop(
+      own.n_main,
+      [&](int u, int64_t i) {
+        av[u] = a[i];
+        bv[u] = b[i];
+      },
+      [&](int u, int64_t i) {
+        if (own(i)) s += (double)av[u] * (double)bv[u];
+      });
   s = block_sum(s);
   if (threadIdx.x == 0) atomicAdd(out, s);
 }
 // y = a*x + b*y
 template <typename T>
 __global__ void axpby_kernel(int64_t n, T a, const T *__restrict__ x, T b, T *__restrict__ y) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    y[i] = a * x[i] + (b == T(0) ? T(0) : b * y[i]);
+  T xv[VU], yv[VU];
+  stream_loop(
+      n,
+      [&](int u, int64_t i) {
+        xv[u] = x[i];
+        yv[u] = b == T(0) ? T(0) : y[i];
+      },
+      [&](int u, int64_t i) { y[i] = a * xv[u] + (b == T(0) ? T(0) : b * yv[u]); });
 }
 // SolverCG: x += alpha p ; r -= alpha v ; out += r.r  (add_and_dot)
 template <typename T>
-__global__ void cg_update_kernel(int64_t n, Own own, T alpha, const T *__restrict__ p, const T *__restrict__ v, T *__restrict__ x,
-                                 T *__restrict__ r, double *out) {
+__device__ __forceinline__ void cg_update_body(int64_t n, const Own &own, T alpha, const T *__restrict__ p, const T *__restrict__ v,
+                                               T *__restrict__ x, T *__restrict__ r, double *out) {
   double s = 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    x[i] += alpha * p[i];
-    const T rn = r[i] - alpha * v[i];
-    r[i] = rn;
-    if (own(i)) s += (double)rn * (double)rn;
-  }
+  T pv[VU], vv[VU], xv[VU], rv[VU];
+  stream_loop(
+      n,
+      [&](int u, int64_t i) {
+        pv[u] = p[i];
+        vv[u] = v[i];
+        xv[u] = x[i];
+        rv[u] = r[i];
+      },
+      [&](int u, int64_t i) {
+        x[i] = xv[u] + alpha * pv[u];
+        const T rn = rv[u] - alpha * vv[u];
+        r[i] = rn;
+        if (own(i)) s += (double)rn * (double)rn;
+      });
   s = block_sum(s);
   if (threadIdx.x == 0) atomicAdd(out, s);
+}
+template <typename T>
+__global__ void cg_update_kernel(int64_t n, Own own, T alpha, const T *__restrict__ p, const T *__restrict__ v, T *__restrict__ x,
+                                 T *__restrict__ r, double *out) {
+  cg_update_body<T>(n, own, alpha, p, v, x, r, out);
 }
 // z = omega * inv .* r ; out += r.z   (inv == nullptr: z = r)
 template <typename T>
 __global__ void diag_precond_dot_kernel(int64_t n, Own own, T omega, const T *__restrict__ inv, const T *__restrict__ r, T *__restrict__ z,
                                         double *out) {
   double s = 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const T ri = r[i], zi = inv ? omega * inv[i] * ri : ri;
-    z[i] = zi;
-    if (own(i)) s += (double)ri * (double)zi;
-  }
+  T rv[VU], iv[VU];
+  stream_loop(
+      n,
+      [&](int u, int64_t i) {
+        rv[u] = r[i];
+        iv[u] = inv ? inv[i] : T(1);
+      },
+      [&](int u, int64_t i) {
+        const T zi = inv ? omega * iv[u] * rv[u] : rv[u];
+        z[i] = zi;
+        if (own(i)) s += (double)rv[u] * (double)zi;
+      });
   s = block_sum(s);
   if (threadIdx.x == 0) atomicAdd(out, s);
 }
@@ -393,22 +449,19 @@ static int cg_solve_t(LinOp &A, const CGPrecond &P, T *x, const T *b, double tol
 template <typename T>
 __global__ void axpby_dev_kernel(int64_t n, const T *__restrict__ x, const double *__restrict__ b, T *__restrict__ y) {
   const T beta = (T)*b;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    y[i] = x[i] + (beta == T(0) ? T(0) : beta * y[i]);
+  T xv[VU], yv[VU];
+  stream_loop(
+      n,
+      [&](int u, int64_t i) {
+        xv[u] = x[i];
+        yv[u] = beta == T(0) ? T(0) : y[i];
+      },
+      [&](int u, int64_t i) { y[i] = xv[u] + (beta == T(0) ? T(0) : beta * yv[u]); });
 }
 template <typename T>
 __global__ void cg_update_dev_kernel(int64_t n, Own own, const double *__restrict__ a, const T *__restrict__ p, const T *__restrict__ v,
                                      T *__restrict__ x, T *__restrict__ r, double *out) {
-  const T alpha = (T)*a;
-  double s = 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    x[i] += alpha * p[i];
-    const T rn = r[i] - alpha * v[i];
-    r[i] = rn;
-    if (own(i)) s += (double)rn * (double)rn;
-  }
-  s = block_sum(s);
-  if (threadIdx.x == 0) atomicAdd(out, s);
+  cg_update_body<T>(n, own, (T)*a, p, v, x, r, out);
 }
 // after r.z: beta = r.z / (r.z)_old, keep the previous r.r in the history, clear the accumulators of this iteration
 __global__ void cg_scalars_beta_kernel(double *S, double *H, int it, int stride) {
