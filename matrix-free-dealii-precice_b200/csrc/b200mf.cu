@@ -353,7 +353,8 @@ extern "C" int b200mf_ctx_create(b200mf_ctx **out, const b200mf_ctx_desc *d) {
   if (!d->vertices && !(d->inverse_jacobian && d->jxw)) return set_error(B200MF_ERR_ARG, "need vertices or inverse_jacobian+jxw");
   if (d->n_constrained > 0 && !d->constrained_dofs) return set_error(B200MF_ERR_ARG, "constrained_dofs is null");
 
-  std::unique_ptr<b200mf_ctx> c(new b200mf_ctx());
+  // every field starts null and b200mf_ctx_destroy frees them all: an early error return below releases what was allocated so far
+  std::unique_ptr<b200mf_ctx, int (*)(b200mf_ctx *)> c(new b200mf_ctx(), b200mf_ctx_destroy);
   memset(c.get(), 0, sizeof(b200mf_ctx));
   c->degree = d->degree;
   c->N = d->degree + 1;
@@ -1670,14 +1671,15 @@ extern "C" int b200mf_laplace_assemble_rhs(b200mf_laplace *op, void *rhs, const 
   if (!op || !rhs || !solution_old) return set_error(B200MF_ERR_ARG, "null argument");
   b200mf_ctx *c = op->ctx;
   const int N = c->N, N3 = N * N * N;
-  void *src_tab = nullptr;
+  DeviceScratch tab, nat;  // freed on every return path (cudaFree waits for the work that still uses them)
+  void *&src_tab = tab.p;
   if (source_q) {  // f at the quadrature points, natural [cell][q] -> group layout
     const int64_t gs = table_stride_rt(c, 1);
     const size_t nel = (size_t)c->n_groups * gs;
     B2_CUDA(cudaMalloc(&src_tab, nel * esize(c)));
     B2_CUDA(cudaMemsetAsync(src_tab, 0, nel * esize(c), c->stream));
-    double *dn = nullptr;
-    B2_CUDA(cudaMalloc(&dn, std::max<size_t>(8, (size_t)c->n_cells * N3 * sizeof(double))));
+    B2_CUDA(cudaMalloc(&nat.p, std::max<size_t>(8, (size_t)c->n_cells * N3 * sizeof(double))));
+    double *dn = (double *)nat.p;
     B2_CUDA(cudaMemcpyAsync(dn, source_q, (size_t)c->n_cells * N3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     const int64_t padded = c->n_groups * c->cpg;
     if (c->dtype == B200MF_F64)
@@ -1685,8 +1687,7 @@ extern "C" int b200mf_laplace_assemble_rhs(b200mf_laplace *op, void *rhs, const 
     else
       table_to_group_layout_kernel<float><<<nblocks(padded * N3, 256), 256, 0, c->stream>>>(N, c->cpg, c->L, 1, table_geom_rt(c, 1), c->n_cells, padded, dn, (float *)src_tab, 0, c->cell_order);
     B2_LAUNCHED();
-    B2_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFree(dn);
+    B2_CUDA(cudaStreamSynchronize(c->stream));  // the host array may be reused by the caller
   }
   B2_TRY(update_ghost_values(c, const_cast<void *>(solution_old)));  // :599
   int rc;
@@ -1697,10 +1698,7 @@ extern "C" int b200mf_laplace_assemble_rhs(b200mf_laplace *op, void *rhs, const 
     LaplaceRhsArgs<float> oa{(const float *)c->mref, (const float *)src_tab, (const float *)c->mcell, (float)op->delta_t, (float)source_const};
     rc = run_laplace_rhs<float>(c, (const float *)solution_old, (float *)rhs, oa);
   }
-  if (src_tab) {
-    cudaStreamSynchronize(c->stream);
-    cudaFree(src_tab);
-  }
+  if (src_tab) cudaStreamSynchronize(c->stream);
   return rc;
 }
 

@@ -48,6 +48,17 @@ struct Shape1D {
 };
 void compute_shape_1d(int p, Shape1D &out);
 
+// device scratch that is released on every return path (early B2_TRY / B2_CUDA returns included)
+struct DeviceScratch {
+  void *p = nullptr;
+  DeviceScratch() = default;
+  DeviceScratch(const DeviceScratch &) = delete;
+  DeviceScratch &operator=(const DeviceScratch &) = delete;
+  ~DeviceScratch() {
+    if (p) cudaFree(p);
+  }
+};
+
 int kernel_event(b200mf_ctx *c, cudaStream_t s);  // b200mf.cu
 
 // comm.cu

@@ -493,8 +493,9 @@ static int cg_fixed_iterations_t(LinOp &A, double omega, const void *inv, T *x, 
   const unsigned g = vgrid(n, c);
   B2_TRY(sc.init());
   const int stride = max_it + 1;
-  double *H = nullptr;
-  B2_CUDA(cudaMalloc(&H, 3 * (size_t)stride * sizeof(double)));
+  DeviceScratch history;  // released on every return path
+  B2_CUDA(cudaMalloc(&history.p, 3 * (size_t)stride * sizeof(double)));
+  double *H = (double *)history.p;
   B2_CUDA(cudaMemsetAsync(H, 0, 3 * (size_t)stride * sizeof(double), st));
   B2_CUDA(cudaMemcpyAsync(r, b, n * sizeof(T), cudaMemcpyDeviceToDevice, st));  // x = 0
   B2_CUDA(cudaMemsetAsync(sc.d, 0, 8 * sizeof(double), st));
@@ -504,7 +505,6 @@ static int cg_fixed_iterations_t(LinOp &A, double omega, const void *inv, T *x, 
   res.diag.clear();
   res.offdiag.clear();
   if (res.initial_residual <= tol || max_it <= 0) {
-    cudaFree(H);
     res.iterations = 0;
     res.residual = res.initial_residual;
     res.converged = true;
@@ -560,7 +560,6 @@ static int cg_fixed_iterations_t(LinOp &A, double omega, const void *inv, T *x, 
   }
   B2_CUDA(cudaMemcpyAsync(h.data(), H, 2 * (size_t)stride * sizeof(double), cudaMemcpyDeviceToHost, st));  // alpha, beta
   B2_CUDA(cudaStreamSynchronize(st));
-  cudaFree(H);
   const int n_run = done_it ? done_it : last_it;
   // the stopping rule of the synchronising loop, replayed on the recorded history
   const int n_it = n_run;
@@ -1110,6 +1109,14 @@ struct b200mf_mg {
   int64_t graph_launches = 0, graph_records = 0, graph_replays = 0;
   cudaGraphExec_t graph_exec = nullptr;
   cudaStream_t graph_stream = nullptr;
+  ~b200mf_mg() {  // also runs on the error paths of b200mf_mg_create
+    for (void *p : defect) cudaFree(p);
+    for (void *p : solution) cudaFree(p);
+    for (void *p : t) cudaFree(p);
+    for (void *p : coarse_work) cudaFree(p);
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    if (graph_stream) cudaStreamDestroy(graph_stream);
+  }
 };
 
 extern "C" int b200mf_mg_create(b200mf_mg **out, int n_levels, b200mf_chebyshev *const *smoothers, b200mf_mg_transfer *const *transfers,
@@ -1127,13 +1134,10 @@ extern "C" int b200mf_mg_create(b200mf_mg **out, int n_levels, b200mf_chebyshev 
         return set_error(B200MF_ERR_ARG, "MG: transfer %d does not connect levels %d and %d", l - 1, l - 1, l);
       mg->transfer.push_back(transfers[l - 1]);
     }
-    void *a, *b, *t;
-    B2_TRY(vec_alloc(c, &a));
-    B2_TRY(vec_alloc(c, &b));
-    B2_TRY(vec_alloc(c, &t));
-    mg->defect.push_back(a);
-    mg->solution.push_back(b);
-    mg->t.push_back(t);
+    for (std::vector<void *> *vs : {&mg->defect, &mg->solution, &mg->t}) {
+      vs->push_back(nullptr);  // owned by mg from here on
+      B2_TRY(vec_alloc(c, &vs->back()));
+    }
   }
   if (smoothers[n_levels - 1]->A.ctx->n_int != outer->n_int)
     return set_error(B200MF_ERR_ARG, "MG: finest level and system context have different vector layouts");
@@ -1143,13 +1147,6 @@ extern "C" int b200mf_mg_create(b200mf_mg **out, int n_levels, b200mf_chebyshev 
   return 0;
 }
 extern "C" int b200mf_mg_destroy(b200mf_mg *mg) {
-  if (!mg) return 0;
-  for (void *p : mg->defect) cudaFree(p);
-  for (void *p : mg->solution) cudaFree(p);
-  for (void *p : mg->t) cudaFree(p);
-  for (void *p : mg->coarse_work) cudaFree(p);
-  if (mg->graph_exec) cudaGraphExecDestroy(mg->graph_exec);
-  if (mg->graph_stream) cudaStreamDestroy(mg->graph_stream);
   delete mg;
   return 0;
 }
