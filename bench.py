@@ -764,6 +764,9 @@ def main():
                      "note": "same Q%d workload; cellwise_morton = cells in z-curve order, nodes numbered cell by cell in first-touch "
                              "order (deal.II-like, mf_elasticity.h:416-425, 667-669); curved = smooth non-affine vertex mapping" % p}
         if args.dtype == "f64" and args.caching == "tensor2":
+            # the multigrid level operator (LevelNumber = float, mf_elasticity.h:363-367): 10 of its applications per V-cycle are
+            # about half of the Newton step below
+            sweep["Q3_fp32_level_operator"] = degree_line(torch, 3, CELLS_PER_DIR[3], "f32", args.caching, args.formulation, variant, peak, sp)
             newton = newton_block(sp)
             if not args.no_heat:
                 heat = heat_block(torch, sp)
