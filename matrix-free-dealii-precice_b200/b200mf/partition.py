@@ -265,3 +265,53 @@ def tube_partitions(degree, first_refinement, n_levels, world, rank):
         pt.clamp_global_face(1, 1)
         parts.append(pt)
     return parts
+
+
+def children_of_replicated(coarse_mesh, fine_part):
+    """[n_coarse_cells, 8] children lists for a transfer between a REPLICATED coarse level (a whole b200mf.mesh.StructuredMesh
+    on every rank) and a partitioned fine level (BrickPartition): local fine cell indices (child (cx,cy,cz) at cx + 2 cy + 4 cz)
+    for the parents whose children lie in this rank's brick, -1 for all other parents.  The brick boundaries must coincide with
+    coarse cell boundaries (every parent has all or none of its children here)."""
+    nc, b = fine_part.nc, fine_part.b
+    assert all((b[d] * nc[d]) % 2 == 0 and nc[d] % 2 == 0 for d in range(3)), "brick boundaries cut through coarse cells"
+    ijk = coarse_mesh.cell_ijk
+    assert all(coarse_mesh.ncells[d] * 2 == fine_part.grid[d] * nc[d] for d in range(3)), "levels are not one refinement apart"
+    out = np.full((coarse_mesh.n_cells, 8), -1, dtype=np.int64)
+    lo = np.array([b[d] * nc[d] for d in range(3)])
+    for ch in range(8):
+        g = 2 * ijk + np.array([(ch >> d) & 1 for d in range(3)])[None, :]  # global fine cell (i, j, k)
+        loc = g - lo[None, :]
+        here = np.all((loc >= 0) & (loc < np.array(nc)[None, :]), axis=1)
+        out[here, ch] = (loc[here, 2] * nc[1] + loc[here, 1]) * nc[0] + loc[here, 0]
+    n_here = (out >= 0).sum(axis=1)
+    assert np.all((n_here == 0) | (n_here == 8))
+    return out
+
+
+def tube_hierarchy_distributed(degree, top_refinement, world, rank):
+    """The reference's whole multigrid hierarchy of the tube (35 coarse cells, refinements 0..top_refinement) on `world` ranks:
+    the levels fine enough to be cut into `world` axial slabs whose boundaries follow the cells of the level below are
+    partitioned (BrickPartition); all coarser levels are kept whole on every rank (StructuredMesh) - p4est would leave most ranks
+    without cells there, here every rank repeats that small amount of work and no rank waits for it.
+    Returns (levels, children, first_partitioned_level)."""
+    from .mesh import children_of, cylinder_shell_mapping, tube_hierarchy
+
+    r_dist = next((r for r in range(1, top_refinement + 1) if (7 * 2 ** (r - 1)) % world == 0), None)
+    if world == 1:
+        r_dist = top_refinement + 1
+    assert r_dist is not None, f"refinement {top_refinement} is too coarse for {world} axial slabs"
+    levels = list(tube_hierarchy(degree, min(r_dist, top_refinement + 1)))  # refinements 0 .. r_dist-1, whole
+    for r in range(r_dist, top_refinement + 1):
+        axial = 7 * 2**r
+        pt = BrickPartition((1, world, 1), (5 * 2**r, axial // world, 2**r), degree, rank, upper=(1.0, 1.0, 1.0), periodic0=True,
+                            mapping=cylinder_shell_mapping(5.0, 0.5, 0.6, 1e-2))
+        pt.clamp_global_face(1, 0)
+        pt.clamp_global_face(1, 1)
+        levels.append(pt)
+    children = []
+    for l in range(len(levels) - 1):
+        if isinstance(levels[l], BrickPartition) or not isinstance(levels[l + 1], BrickPartition):
+            children.append(children_of(levels[l]))
+        else:
+            children.append(children_of_replicated(levels[l], levels[l + 1]))
+    return levels, children, r_dist

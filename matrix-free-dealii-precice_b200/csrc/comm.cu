@@ -521,6 +521,15 @@ int allreduce_sum_f64(b200mf_ctx *c, double *dptr, int n) {
   B2_NCCL(g_nccl.AllReduce(dptr, dptr, (size_t)n, ncclFloat64, ncclSum, p->comm->comm, c->stream));
   return 0;
 }
+// element-wise reduction of a whole device vector over the ranks of c's partitioner (op 0 = sum, 1 = max, 2 = min): the
+// replicated coarse levels of the multigrid transfer
+int allreduce_vector(b200mf_ctx *c, void *dptr, int64_t n, int dtype, int op, cudaStream_t s) {
+  b200mf_partitioner *p = c->part;
+  if (!p || p->comm->world == 1) return 0;
+  const ncclRedOp_t ops[3] = {ncclSum, ncclMax, ncclMin};
+  B2_NCCL(g_nccl.AllReduce(dptr, dptr, (size_t)n, dtype == B200MF_F64 ? ncclFloat64 : ncclFloat32, ops[op], p->comm->comm, s));
+  return 0;
+}
 // sum over ranks of a device counter (failure counts: every rank must take the same error path, or the peers of a
 // failing rank would walk into the next exchange alone)
 int allreduce_sum_u64(b200mf_ctx *c, unsigned long long *dptr, int n) {

@@ -70,6 +70,7 @@ int zero_ghosts(b200mf_ctx *c, void *vec);
 bool has_neighbors(const b200mf_ctx *c);
 int allreduce_sum_f64(b200mf_ctx *c, double *dptr, int n);
 int allreduce_sum_u64(b200mf_ctx *c, unsigned long long *dptr, int n);
+int allreduce_vector(b200mf_ctx *c, void *dptr, int64_t n, int dtype, int op, cudaStream_t s);
 
 }  // namespace b200mf
 

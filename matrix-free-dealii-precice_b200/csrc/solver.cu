@@ -935,7 +935,12 @@ struct b200mf_mg_transfer {
   b200mf_ctx *coarse, *fine;
   uint32_t *cidx = nullptr, *pidx = nullptr;
   float *wfine = nullptr;
-  int64_t n_coarse_cells = 0;
+  int64_t n_coarse_cells = 0;  // coarse cells with children on this rank (all of them unless the coarse level is replicated)
+  // replicated coarse level: the coarse context holds the WHOLE coarse mesh on every rank (no partitioner), the fine one is
+  // partitioned.  Each rank transfers between its fine cells and their parents; restriction sums the partial coarse vectors
+  // over the ranks, interpolation merges them - every rank then continues with an identical copy of the coarse vector.
+  bool replicated = false;
+  void *ctmp[2] = {nullptr, nullptr};
   Embed E;
 };
 
@@ -943,12 +948,25 @@ extern "C" int b200mf_mg_transfer_create(b200mf_mg_transfer **out, b200mf_ctx *c
   if (!out || !coarse || !fine || !children) return set_error(B200MF_ERR_ARG, "null argument");
   if (coarse->N != fine->N || coarse->NC != fine->NC || coarse->dtype != fine->dtype)
     return set_error(B200MF_ERR_ARG, "MG transfer: levels must share degree, components and number type");
-  if (fine->n_cells != 8 * coarse->n_cells) return set_error(B200MF_ERR_ARG, "MG transfer: fine level must have 8 children per coarse cell");
-  std::unique_ptr<b200mf_mg_transfer> t(new b200mf_mg_transfer());
+  const bool replicated = !has_neighbors(coarse) && has_neighbors(fine);
+  // the coarse cells that have their children on this rank (replicated coarse level: a subset; children = -1 elsewhere)
+  std::vector<int64_t> present;
+  for (int64_t cell = 0; cell < coarse->n_cells; ++cell) {
+    int n_here = 0;
+    for (int ch = 0; ch < 8; ++ch) n_here += children[cell * 8 + ch] >= 0;
+    if (n_here == 8)
+      present.push_back(cell);
+    else if (n_here != 0 || !replicated)
+      return set_error(B200MF_ERR_ARG, "MG transfer: coarse cell %lld has %d of its 8 children on this rank", (long long)cell, n_here);
+  }
+  if (fine->n_cells != 8 * (int64_t)present.size())
+    return set_error(B200MF_ERR_ARG, "MG transfer: fine level must have 8 children per coarse cell");
+  std::unique_ptr<b200mf_mg_transfer, int (*)(b200mf_mg_transfer *)> t(new b200mf_mg_transfer(), b200mf_mg_transfer_destroy);
   t->coarse = coarse;
   t->fine = fine;
+  t->replicated = replicated;
   const int N = coarse->N, p = N - 1, M = 2 * N - 1, N3 = N * N * N, M3 = M * M * M;
-  t->n_coarse_cells = coarse->n_cells;
+  t->n_coarse_cells = (int64_t)present.size();
   // 1-D embedding: fine patch node m sits at x_m = nodes[m]/2 (child 0), 1/2 + nodes[m-p]/2 (child 1)
   const double *nd = coarse->shape.nodes;
   memset(&t->E, 0, sizeof(Embed));
@@ -962,29 +980,35 @@ extern "C" int b200mf_mg_transfer_create(b200mf_mg_transfer **out, b200mf_ctx *c
     for (int l = 0; l < N; ++l) t->E.Rf[i * M + ch * p + l] = (float)(t->E.Rd[i * M + ch * p + l] = lagrange_1d(nd, N, l, xi));
   }
   // patch index table: fine node of patch position (mx,my,mz) through the child that contains it
-  std::vector<uint32_t> pidx((size_t)coarse->n_cells * M3);
-  const std::vector<uint32_t> &fn = *fine->h_cell_nodes;
-  for (int64_t cell = 0; cell < coarse->n_cells; ++cell)
+  const int64_t n_here = (int64_t)present.size();
+  std::vector<uint32_t> pidx((size_t)std::max<int64_t>(1, n_here) * M3), cidx((size_t)std::max<int64_t>(1, n_here) * N3);
+  const std::vector<uint32_t> &fn = *fine->h_cell_nodes, &cn = *coarse->h_cell_nodes;
+  for (int64_t k = 0; k < n_here; ++k) {
+    const int64_t cell = present[k];
+    memcpy(&cidx[(size_t)k * N3], &cn[(size_t)cell * N3], (size_t)N3 * sizeof(uint32_t));
     for (int mz = 0; mz < M; ++mz)
       for (int my = 0; my < M; ++my)
         for (int mx = 0; mx < M; ++mx) {
           const int cx = mx > p, cy = my > p, cz = mz > p;
           const int64_t child = children[cell * 8 + cx + 2 * cy + 4 * cz];
-          if (child < 0 || child >= fine->n_cells) return set_error(B200MF_ERR_ARG, "MG transfer: child index out of range");
+          if (child >= fine->n_cells) return set_error(B200MF_ERR_ARG, "MG transfer: child index out of range");
           const int lx = mx - cx * p, ly = my - cy * p, lz = mz - cz * p;
-          pidx[(size_t)cell * M3 + (mz * M + my) * M + mx] = fn[(size_t)child * N3 + (lz * N + ly) * N + lx];
+          pidx[(size_t)k * M3 + (mz * M + my) * M + mx] = fn[(size_t)child * N3 + (lz * N + ly) * N + lx];
         }
+  }
   // consistency: shared patch positions must map to the same fine node through either child
-  for (int64_t cell = 0; cell < std::min<int64_t>(coarse->n_cells, 4); ++cell) {
-    const int64_t c0 = children[cell * 8], c1 = children[cell * 8 + 1];
+  for (int64_t k = 0; k < std::min<int64_t>(n_here, 4); ++k) {
+    const int64_t c0 = children[present[k] * 8], c1 = children[present[k] * 8 + 1];
     if ((fn[(size_t)c0 * N3 + p] & NODE_MASK) != (fn[(size_t)c1 * N3] & NODE_MASK))
       return set_error(B200MF_ERR_ARG, "MG transfer: children are not in lexicographic (x fastest) order");
   }
   // multiplicity weights of the fine nodes (number of parent patches containing the node; ghosts via compress/update)
   std::vector<float> cnt(fine->n_int, 0.f);
   for (size_t i = 0; i < pidx.size(); ++i) cnt[pidx[i] & NODE_MASK] += 1.f;
-  B2_CUDA(cudaMalloc(&t->cidx, coarse->h_cell_nodes->size() * 4));
-  B2_CUDA(cudaMemcpy(t->cidx, coarse->h_cell_nodes->data(), coarse->h_cell_nodes->size() * 4, cudaMemcpyHostToDevice));
+  B2_CUDA(cudaMalloc(&t->cidx, cidx.size() * 4));
+  B2_CUDA(cudaMemcpy(t->cidx, cidx.data(), cidx.size() * 4, cudaMemcpyHostToDevice));
+  if (replicated)
+    for (void *&q : t->ctmp) B2_TRY(vec_alloc(coarse, &q));
   B2_CUDA(cudaMalloc(&t->pidx, pidx.size() * 4));
   B2_CUDA(cudaMemcpy(t->pidx, pidx.data(), pidx.size() * 4, cudaMemcpyHostToDevice));
   if (fine->part) {
@@ -1024,6 +1048,7 @@ extern "C" int b200mf_mg_transfer_destroy(b200mf_mg_transfer *t) {
   cudaFree(t->cidx);
   cudaFree(t->pidx);
   cudaFree(t->wfine);
+  for (void *q : t->ctmp) cudaFree(q);
   delete t;
   return 0;
 }
@@ -1072,6 +1097,18 @@ extern "C" int b200mf_mg_transfer_prolongate_and_add(b200mf_mg_transfer *t, void
 extern "C" int b200mf_mg_transfer_restrict_and_add(b200mf_mg_transfer *t, void *coarse_dst, const void *fine_src) {
   if (!t || !coarse_dst || !fine_src) return set_error(B200MF_ERR_ARG, "null argument");
   B2_TRY(update_ghost_values(t->fine, const_cast<void *>(fine_src)));
+  if (t->replicated) {  // this rank's share of P^T fine_src, summed over the ranks, then added to every rank's copy
+    b200mf_ctx *cc = t->coarse;
+    B2_CUDA(cudaMemsetAsync(t->ctmp[0], 0, cc->n_int * esz(cc), cc->stream));
+    B2_TRY(transfer_dispatch<2>(t, t->ctmp[0], fine_src));
+    B2_TRY(allreduce_vector(t->fine, t->ctmp[0], cc->n_int, cc->dtype, 0, cc->stream));
+    if (cc->dtype == B200MF_F64)
+      axpby_kernel<double><<<vgrid(cc->n_int, cc), 256, 0, cc->stream>>>(cc->n_int, 1.0, (const double *)t->ctmp[0], 1.0, (double *)coarse_dst);
+    else
+      axpby_kernel<float><<<vgrid(cc->n_int, cc), 256, 0, cc->stream>>>(cc->n_int, 1.f, (const float *)t->ctmp[0], 1.f, (float *)coarse_dst);
+    B2_LAUNCHED();
+    return 0;
+  }
   B2_TRY(zero_ghosts(t->coarse, coarse_dst));
   B2_TRY(transfer_dispatch<2>(t, coarse_dst, fine_src));
   return compress_add(t->coarse, coarse_dst);
@@ -1080,6 +1117,24 @@ extern "C" int b200mf_mg_transfer_restrict_and_add(b200mf_mg_transfer *t, void *
 extern "C" int b200mf_mg_transfer_interpolate(b200mf_mg_transfer *t, void *coarse_dst, const void *fine_src) {
   if (!t || !coarse_dst || !fine_src) return set_error(B200MF_ERR_ARG, "null argument");
   B2_TRY(update_ghost_values(t->fine, const_cast<void *>(fine_src)));
+  if (t->replicated) {
+    // every rank evaluates the coarse support points inside its own parents; points shared by parents of two ranks get the
+    // same value from both, all others are 0 elsewhere: max + min over the ranks merges the pieces without double counting
+    b200mf_ctx *cc = t->coarse;
+    const size_t bytes = cc->n_int * esz(cc);
+    B2_CUDA(cudaMemsetAsync(t->ctmp[0], 0, bytes, cc->stream));
+    B2_TRY(transfer_dispatch<3>(t, t->ctmp[0], fine_src));
+    B2_CUDA(cudaMemcpyAsync(t->ctmp[1], t->ctmp[0], bytes, cudaMemcpyDeviceToDevice, cc->stream));
+    B2_TRY(allreduce_vector(t->fine, t->ctmp[0], cc->n_int, cc->dtype, 1, cc->stream));
+    B2_TRY(allreduce_vector(t->fine, t->ctmp[1], cc->n_int, cc->dtype, 2, cc->stream));
+    B2_CUDA(cudaMemcpyAsync(coarse_dst, t->ctmp[0], bytes, cudaMemcpyDeviceToDevice, cc->stream));
+    if (cc->dtype == B200MF_F64)
+      axpby_kernel<double><<<vgrid(cc->n_int, cc), 256, 0, cc->stream>>>(cc->n_int, 1.0, (const double *)t->ctmp[1], 1.0, (double *)coarse_dst);
+    else
+      axpby_kernel<float><<<vgrid(cc->n_int, cc), 256, 0, cc->stream>>>(cc->n_int, 1.f, (const float *)t->ctmp[1], 1.f, (float *)coarse_dst);
+    B2_LAUNCHED();
+    return 0;
+  }
   B2_TRY(transfer_dispatch<3>(t, coarse_dst, fine_src));
   return zero_ghosts(t->coarse, coarse_dst);
 }

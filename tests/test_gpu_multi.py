@@ -197,6 +197,72 @@ def _tube_worker(rank, world, port, p, first_refinement, levels, q):
         dist.destroy_process_group()
 
 
+def _tube_full_worker(rank, world, port, p, top, q):
+    """The tube with the reference's whole hierarchy on `world` ranks: coarse levels replicated, fine levels in axial slabs."""
+    import faulthandler
+    import sys as _sys
+
+    faulthandler.enable()
+    faulthandler.dump_traceback_later(150, exit=True, file=_sys.stderr)
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from b200mf import Communicator, MatrixFree
+        from b200mf.mesh import tube_pressure_traction
+        from b200mf.partition import BrickPartition, tube_hierarchy_distributed
+        from b200mf.solid import Solid
+
+        comm = Communicator.from_torch_distributed()
+        levels, children, r_dist = tube_hierarchy_distributed(p, top, world, rank)
+        level_mf = [MatrixFree.from_partition(lv, comm, dtype="f32") if isinstance(lv, BrickPartition) else MatrixFree.from_mesh(lv, 3, dtype="f32")
+                    for lv in levels]
+        sys_mf = MatrixFree.from_partition(levels[-1], comm)
+        sol = Solid(levels, mu=115384.0, nu=0.3, rho=1200.0, delta_t=1e-4, n_cheb_cg=30, matrix_frees=(sys_mf, level_mf),
+                    children=children, traction=tube_pressure_traction(5.0e4), traction_faces=((2, 0),))
+        sol.run(1)
+        fine = levels[-1]
+        g_owned = (3 * fine.global_lex_node()[:, None] + np.arange(3)[None, :]).reshape(-1)[:fine.n_owned]
+        q.put((rank, (g_owned, sol.total_displacement()[:fine.n_owned]), list(sol.newton_iterations), list(sol.cg_history) + [sol.mg.graph_info()["state"]]))
+    except BaseException:
+        import traceback
+        q.put((rank, traceback.format_exc(), None, None))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_distributed_tube_full_hierarchy():
+    """The reference's whole 35-coarse-cell hierarchy on 2 GPUs: refinements 0 and 1 are kept whole on both ranks (replicated
+    coarse levels - restriction sums the ranks' shares, interpolation merges them), refinement 2 is cut into two axial slabs.
+    Same Newton / CG counts and displacement as the one-GPU run of the same three levels."""
+    world, p, top = 2, 2, 2
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    from b200mf.mesh import tube_hierarchy, tube_pressure_traction
+    from b200mf.solid import Solid
+
+    res = _spawn(world, _tube_full_worker, (p, top))
+    meshes = tube_hierarchy(p, top + 1)
+    ref = Solid(meshes, mu=115384.0, nu=0.3, rho=1200.0, delta_t=1e-4, n_cheb_cg=30, traction=tube_pressure_traction(5.0e4),
+                traction_faces=((2, 0),))
+    ref.run(1)
+    u_ref = ref.total_displacement()
+    got = np.full_like(u_ref, np.nan)
+    for rank, (idx, val), newton, cg in res:
+        got[idx] = val
+        assert newton == ref.newton_iterations
+        assert cg[-1] == 1  # lower levels (replicated ones and the all-reduce of the restriction included) ran from the recorded graph
+        assert max(abs(a - b) for a, b in zip(cg[:-1], ref.cg_history)) <= 1, (cg, ref.cg_history)
+    assert not np.isnan(got).any()
+    assert np.abs(got - u_ref).max() <= 1e-7 * np.abs(u_ref).max()
+
+
 def test_distributed_tube_newton():
     """BASELINE configs[3] in miniature on 2 GPUs: tube geometry (curved cells, periodic around the axis), interface traction
     on the inner wall, GMG-preconditioned Newton step, against the one-GPU run of the same hierarchy."""

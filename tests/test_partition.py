@@ -224,3 +224,33 @@ def test_tube_partition_matches_global_periodic_mesh(world, p):
             expect = other.global_lex_node()[back["ghost_start"]:back["ghost_start"] + back["ghost_count"]]
             assert (np.sort(sent) == np.sort(expect)).all() and (sent == expect).all()
     assert sum(pt.n_owned for pt in parts) == 3 * g.n_nodes == parts[0].n_global_dofs
+
+
+@pytest.mark.parametrize("world,top", [(2, 2), (2, 3), (8, 4)])
+def test_tube_hierarchy_with_replicated_coarse_levels(world, top):
+    """tube_hierarchy_distributed: the levels below the first one that can be cut into `world` aligned slabs stay whole on every
+    rank; the children lists of the transfer between the last whole level and the first partitioned one name, per rank, exactly
+    the local copies of the global children, and every parent is claimed by exactly one rank."""
+    from b200mf.mesh import children_of, tube_hierarchy
+    from b200mf.partition import BrickPartition, tube_hierarchy_distributed
+
+    p = 1
+    full = tube_hierarchy(p, top + 1)
+    claimed = None
+    for rank in range(world):
+        levels, children, r_dist = tube_hierarchy_distributed(p, top, world, rank)
+        assert len(levels) == top + 1 and len(children) == top
+        assert [isinstance(l, BrickPartition) for l in levels] == [r >= r_dist for r in range(top + 1)]
+        assert (7 * 2 ** (r_dist - 1)) % world == 0
+        for r in range(r_dist - 1):
+            assert np.array_equal(children[r], children_of(full[r]))
+        ch, pt = children[r_dist - 1], levels[r_dist]
+        here = (ch >= 0).all(axis=1)
+        assert np.array_equal(here, (ch >= 0).any(axis=1)) and here.sum() * 8 == pt.n_cells
+        gi = pt.cell_ijk + np.array([pt.b[d] * pt.nc[d] for d in range(3)])[None, :]
+        nf = full[r_dist].ncells
+        glob = (gi[:, 2] * nf[1] + gi[:, 1]) * nf[0] + gi[:, 0]
+        assert np.array_equal(glob[ch[here]], children_of(full[r_dist - 1])[here])
+        assert np.allclose(pt.vertices[ch[here][:, 0]], full[r_dist].vertices[children_of(full[r_dist - 1])[here][:, 0]])
+        claimed = here.astype(int) if claimed is None else claimed + here
+    assert np.all(claimed == 1)
