@@ -349,6 +349,11 @@ int b200mf_chebyshev_step(b200mf_chebyshev *cheb, void *dst_dvec, const void *sr
  * MGTransferMatrixFree<3,float> between two uniformly refined levels (mf_elasticity.h:863-877, 881-929;
  * heat_transfer.h:761-762).  children: [n_coarse_cells][8] cell indices on the fine context, child (cx,cy,cz)
  * at cx + 2 cy + 4 cz (the order of the caller's cell arrays).
+ * Replicated coarse level: if `coarse` has no partitioner but `fine` has one, the coarse context is the WHOLE coarse mesh, held by
+ * every rank (the levels a distributed triangulation leaves most ranks without cells on).  children rows are then all -1 for the
+ * parents whose children live on other ranks (a parent has all 8 or none of them here).  restrict_and_add sums the ranks' shares
+ * with one all-reduce and adds the sum to every rank's copy, prolongate* need no communication, interpolate merges the ranks'
+ * pieces; the coarse vector is identical on all ranks afterwards and everything below runs redundantly without exchanges.
  * ------------------------------------------------------------------------ */
 typedef struct b200mf_mg_transfer b200mf_mg_transfer;
 int b200mf_mg_transfer_create(b200mf_mg_transfer **t, b200mf_ctx *coarse, b200mf_ctx *fine, const int64_t *children);
