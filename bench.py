@@ -160,6 +160,13 @@ class ClockSampler:
                 "samples": len(sm), "how": "NVML clock + clocks-event-reasons polled every ~10 ms inside the timed region"}
 
 
+def host_stream_gbs():
+    """STREAM triad of the host (all threads) through the oracle library: what the CPU arm's algorithmic GB/s is to be read against."""
+    from oracle import c_oracle as CO
+
+    return CO.host_stream_triad_gbs()
+
+
 def cpu_oracle_rate(p, ncell_dir, min_seconds=10.0, max_reps=100000):
     """DoFs/s of the CPU oracle port (oracle/mf_oracle.c, OpenMP over cells, all host threads)."""
     from b200mf.mesh import StructuredMesh, synthetic_displacement
@@ -245,7 +252,7 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": cfg,
         "cpu_baseline": {"value": val, "unit": "DoFs/s", "cores": CO.num_threads(), "kind": "port", "sample": sample,
-                         "algorithmic_GB/s": alg_gbs},
+                         "algorithmic_GB/s": alg_gbs, "host_stream_triad_GB/s": CO.host_stream_triad_gbs()},
         "e2e": {"value": val, "unit": "DoFs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference needs deal.II>=9.6 + preCICE>=3 (absent): CPU arm = oracle/mf_oracle.c port, vectorised over cells like "
                 "deal.II's MatrixFree (VectorizedArray), OpenMP over cell batches",
@@ -777,7 +784,8 @@ def main():
         v, ncpu, reps, threads, sec = cpu_oracle_rate(p, args.cpu_cells)
         cpu = {"value": v, "unit": "DoFs/s", "cores": threads, "kind": "port",
                "sample": f"Q{p} box {args.cpu_cells}^3 cells = {ncpu} DoFs x {reps} vmults ({sec:.2f} s each); {cpu_arm_description()}",
-               "algorithmic_GB/s": v * algorithmic_bytes_per_cell(p) / (3 * p**3) / 1e9}
+               "algorithmic_GB/s": v * algorithmic_bytes_per_cell(p) / (3 * p**3) / 1e9,
+               "host_stream_triad_GB/s": host_stream_gbs()}
 
     if rank == 0:
         line = {

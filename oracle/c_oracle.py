@@ -47,6 +47,8 @@ def lib():
         L.orc_nh_simd_destroy.argtypes = [vp]
         L.orc_nh_vmult_simd.argtypes = [vp, vp, vp, vp]
         L.orc_simd_isa.restype = C.c_char_p
+        L.orc_stream_triad_gbs.restype = C.c_double
+        L.orc_stream_triad_gbs.argtypes = [C.c_long, C.c_int]
         _LIB = L
     return _LIB
 
@@ -147,6 +149,11 @@ class NeoHookOperator:
 
 def simd_isa():
     return lib().orc_simd_isa().decode()
+
+
+def host_stream_triad_gbs(n=100_000_000, reps=5):
+    """STREAM-triad bandwidth of the host with all OpenMP threads (24 B per element), best of `reps` passes."""
+    return float(lib().orc_stream_triad_gbs(int(n), int(reps)))
 
 
 class LaplaceOperator:

@@ -915,3 +915,40 @@ int orc_num_threads(void)
   return 1;
 #endif
 }
+
+
+/* Host memory bandwidth, STREAM triad convention (a = b + s c, 24 B per element counted), all OpenMP threads, first-touch
+ * placement by the same static schedule; best of `reps` passes in GB/s.  Reported next to the CPU arm's algorithmic GB/s so that
+ * the arm can be judged against what the host's memory system delivers (bench.py cpu_baseline). */
+double orc_stream_triad_gbs(long n, int reps)
+{
+  double *a = (double *)malloc((size_t)n * sizeof(double)), *b = (double *)malloc((size_t)n * sizeof(double)),
+         *c = (double *)malloc((size_t)n * sizeof(double));
+  if (!a || !b || !c) {
+    free(a);
+    free(b);
+    free(c);
+    return -1.0;
+  }
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < n; ++i) {
+    a[i] = 0.0;
+    b[i] = 1.0 + 1e-9 * (double)i;
+    c[i] = 2.0;
+  }
+  double best = 0.0;
+  for (int r = 0; r < reps; ++r) {
+    const double t0 = omp_get_wtime();
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < n; ++i) a[i] = b[i] + 3.0 * c[i];
+    const double t1 = omp_get_wtime();
+    const double gbs = 24.0 * (double)n / (t1 - t0) / 1e9;
+    if (gbs > best) best = gbs;
+  }
+  volatile double sink = a[n / 2];
+  (void)sink;
+  free(a);
+  free(b);
+  free(c);
+  return best;
+}

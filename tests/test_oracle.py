@@ -286,3 +286,8 @@ def test_boundary_mass_oracle_curved_area():
     assert rad.max() <= 0.5e-2 + 1e-12 and rad.min() > 0.45e-2
     exact = 2 * np.pi * 0.5e-2 * 5e-2
     assert 0.9 * exact < op.jxw.sum() < exact
+
+
+def test_host_stream_triad_is_reported():
+    """bench.py puts the host's STREAM-triad bandwidth next to the CPU arm's algorithmic GB/s (oracle/mf_oracle.c)"""
+    assert CO.host_stream_triad_gbs(2_000_000, 2) > 0.1
